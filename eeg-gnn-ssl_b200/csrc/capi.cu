@@ -1,0 +1,442 @@
+// C ABI of libdcgru_b200 (declared in include/dcgru_b200.h): argument checks, shared-memory /
+// tiling plans, workspace carving and kernel launches.  No device memory is allocated here.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "common.cuh"
+#include "dw.cuh"
+#include "dcgru_b200.h"
+
+using namespace dcgru;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+#define CUDA_TRY(expr)                                                                   \
+    do {                                                                                 \
+        cudaError_t e_ = (expr);                                                         \
+        if (e_ != cudaSuccess) return fail("%s: %s", #expr, cudaGetErrorString(e_));     \
+    } while (0)
+
+struct DevInfo { int sms = 0; int smem = 0; bool ok = false; };
+DevInfo& devinfo() {
+    static DevInfo d[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    DevInfo& r = d[dev];
+    if (!r.ok) {
+        cudaDeviceGetAttribute(&r.sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&r.smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        r.ok = r.sms > 0;
+    }
+    return r;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int check_desc(const dcgru_cell_desc* d) {
+    if (!d) return fail("null descriptor");
+    if (d->num_nodes < 1 || d->num_nodes > NP) return fail("num_nodes=%d unsupported (1..%d)", d->num_nodes, NP);
+    if (d->hid_dim != 32 && d->hid_dim != 64 && d->hid_dim != 128)
+        return fail("hid_dim=%d unsupported (32, 64 or 128)", d->hid_dim);
+    if (d->input_dim < 4 || d->input_dim % 4) return fail("input_dim=%d must be a positive multiple of 4", d->input_dim);
+    if (d->num_supports < 1 || d->num_supports > 2) return fail("num_supports=%d unsupported (1 or 2)", d->num_supports);
+    if (d->max_diffusion_step < 0 || d->max_diffusion_step > 3)
+        return fail("max_diffusion_step=%d unsupported (0..3)", d->max_diffusion_step);
+    if (d->activation != DCGRU_ACT_TANH && d->activation != DCGRU_ACT_RELU) return fail("bad activation");
+    return 0;
+}
+inline int Mof(const dcgru_cell_desc* d) { return d->num_supports * d->max_diffusion_step + 1; }
+
+const double kCost[9] = {0, 1.6, 1.25, 0, 1.0, 0, 0, 0, 0.95};
+
+// forward plan: samples per CTA, K-chunk, shared memory
+struct FwdPlan { int SB = 0, KC = 0, smem = 0, FoPad = 0; };
+bool plan_fwd(int H, int cmax, int M, int B, int Fo /*0 = encoder*/, FwdPlan* out) {
+    const DevInfo& di = devinfo();
+    double best = 1e30;
+    for (int SB = 1; SB <= 8; SB *= 2) {
+        int hs = H * SB;
+        if (hs != 64 && hs != 128 && hs != 256) continue;
+        int fopad = 0;
+        if (Fo > 0) { int q = (64 / SB) * 4; fopad = (Fo + q - 1) / q * q; }
+        for (int KC = 16; KC >= 2; KC /= 2) {
+            FwdLayout L = fwd_layout(SB, H, cmax, M, KC);
+            if (L.total * 4 > di.smem) continue;
+            if (Fo > 0 && H * fopad > 2 * L.wbuf) continue;
+            long ctas = (B + SB - 1) / SB;
+            long waves = (ctas + di.sms - 1) / di.sms;
+            double cost = waves * SB * kCost[SB];
+            if (cost < best) { best = cost; out->SB = SB; out->KC = KC; out->smem = L.total * 4; out->FoPad = fopad; }
+            break;   // largest KC that fits for this SB
+        }
+    }
+    return best < 1e30;
+}
+struct BwdPlan { int SB = 0, smem = 0; };
+bool plan_bwd(int H, int M, int B, int Fo, BwdPlan* out) {
+    const DevInfo& di = devinfo();
+    double best = 1e30;
+    for (int SB = 1; SB <= 8; SB *= 2) {
+        BwdLayout L = bwd_layout(SB, H, M, Fo);
+        if (L.total * 4 > di.smem) continue;
+        if (bwd_zcols(L.kb, M) < 4) continue;
+        long ctas = (B + SB - 1) / SB;
+        long waves = (ctas + di.sms - 1) / di.sms;
+        double cost = waves * SB * kCost[SB];
+        if (cost < best) { best = cost; out->SB = SB; out->smem = L.total * 4; }
+    }
+    return best < 1e30;
+}
+
+// ---- weight-gradient job tables --------------------------------------------------------------------
+int otile(int n) { return n <= 192 ? n : (n % 192 == 0 ? 192 : 128); }   // 3H/2H/H for H in {32,64,128}
+
+int build_cell_jobs(int fin, int H, int M, DwJob* jobs) {
+    int n = 0;
+    const int zc = 64 / M;
+    auto add = [&](int type, int zlen, int kkbase, int o_begin, int o_len) {
+        int ot = otile(o_len);
+        for (int o0 = 0; o0 < o_len; o0 += ot)
+            for (int z0 = 0; z0 < zlen; z0 += zc) {
+                DwJob j;
+                j.type = type; j.z0 = z0; j.nz = (zlen - z0 < zc) ? zlen - z0 : zc;
+                j.kk0 = kkbase + z0 * M; j.o0 = o_begin + o0; j.nco = ot;
+                if (n < DW_MAXJOBS) jobs[n] = j;
+                ++n;
+            }
+    };
+    add(0, fin, 0, 0, 3 * H);
+    add(1, H, fin * M, 0, 2 * H);
+    add(2, H, fin * M, 2 * H, H);
+    return n;
+}
+int build_proj_jobs(int Fo, int H, DwJob* jobs) {
+    int n = 0;
+    int ot = otile(H);
+    for (int o0 = 0; o0 < H; o0 += ot)
+        for (int z0 = 0; z0 < Fo; z0 += 64) {
+            DwJob j;
+            j.type = 3; j.z0 = z0; j.nz = (Fo - z0 < 64) ? Fo - z0 : 64; j.kk0 = z0; j.o0 = o0; j.nco = ot;
+            if (n < DW_MAXJOBS) jobs[n] = j;
+            ++n;
+        }
+    return n;
+}
+int dw_nsplit(int B, int njobs) {
+    const DevInfo& di = devinfo();
+    int ngroups = (B + 3) / 4;
+    int want = (4 * di.sms + njobs - 1) / njobs;
+    if (want < 1) want = 1;
+    return ngroups < want ? ngroups : want;
+}
+
+size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct Carver {
+    char* base; size_t off = 0, cap;
+    Carver(void* b, size_t c) : base((char*)b), cap(c) {}
+    float* take(size_t nfloats) {
+        size_t o = off;
+        off = align_up(off + nfloats * 4);
+        return (float*)(base + o);
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+int dcgru_version(void) { return 100; }
+const char* dcgru_last_error(void) { return g_err.c_str(); }
+
+int dcgru_graph_poly(int32_t batch, int32_t num_nodes, int32_t max_diffusion_step, int32_t num_supports,
+                     const float* const* supports, const int64_t* support_bstride, float* P, void* stream) {
+    if (batch < 1) return fail("batch < 1");
+    if (num_nodes < 1 || num_nodes > NP) return fail("num_nodes=%d unsupported", num_nodes);
+    if (num_supports < 1 || num_supports > 2) return fail("num_supports=%d unsupported", num_supports);
+    if (max_diffusion_step < 0 || max_diffusion_step > 3) return fail("max_diffusion_step unsupported");
+    long long bs[2] = {0, 0};
+    for (int s = 0; s < num_supports; ++s) {
+        if (!supports || !supports[s]) return fail("null support %d", s);
+        bs[s] = support_bstride ? support_bstride[s] : (long long)num_nodes * num_nodes;
+    }
+    if (max_diffusion_step > 0 && !P) return fail("null P");
+    CUDA_TRY(launch_graph_poly(batch, num_nodes, max_diffusion_step, num_supports, supports, bs, P,
+                               (cudaStream_t)stream));
+    return 0;
+}
+
+int dcgru_corr_supports(int32_t batch, int32_t seq_len, int32_t num_nodes, int32_t feat, const float* clip,
+                        int64_t stride_b, int64_t stride_t, float scale, float shift, int32_t top_k,
+                        float* adj, float* support0, float* support1, void* stream) {
+    if (batch < 1 || seq_len < 1 || feat < 1) return fail("empty clip");
+    if (num_nodes < 2 || num_nodes > NP) return fail("num_nodes=%d unsupported", num_nodes);
+    if (top_k < 0) return fail("top_k < 0 (the reference raises ValueError for top_k=None)");
+    if (!clip || !support0 || !support1) return fail("null pointer");
+    if ((size_t)num_nodes * (feat | 1) * 4 > (size_t)devinfo().smem) return fail("feature dim too large");
+    CUDA_TRY(launch_corr_supports(batch, seq_len, num_nodes, feat, clip, stride_b, stride_t, scale, shift, top_k,
+                                  adj, support0, support1, (cudaStream_t)stream));
+    return 0;
+}
+
+int dcgru_encoder_layer_fwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq_len, const float* x,
+                            int64_t x_stride_t, int64_t x_stride_b, const float* h0, const float* P,
+                            const dcgru_cell_params* w, float* h_seq, float* ruc, void* stream) {
+    if (check_desc(d)) return 1;
+    if (batch < 1 || seq_len < 1) return fail("empty batch/sequence");
+    if (!x || !h0 || !w || !h_seq || !w->Wg || !w->bg || !w->Wc || !w->bc) return fail("null pointer");
+    const int M = Mof(d);
+    if (M > 1 && !P) return fail("null P");
+    if (!aligned16(x) || !aligned16(h0) || !aligned16(h_seq) || !aligned16(w->Wg) || !aligned16(w->Wc) ||
+        (x_stride_t % 4) || (x_stride_b % 4))
+        return fail("x/h0/h_seq/weights must be 16-byte aligned with strides multiple of 4 floats");
+    FwdPlan pl;
+    if (!plan_fwd(d->hid_dim, d->input_dim + d->hid_dim, M, batch, 0, &pl))
+        return fail("no tiling fits shared memory (input_dim=%d hid=%d M=%d)", d->input_dim, d->hid_dim, M);
+    FwdParams p;
+    memset(&p, 0, sizeof p);
+    p.B = batch; p.T = seq_len; p.N = d->num_nodes; p.H = d->hid_dim; p.M = M; p.act = d->activation;
+    p.ncell = 1; p.KC = pl.KC; p.mode = 0;
+    p.cell[0] = CellW{w->Wg, w->bg, w->Wc, w->bc, d->input_dim};
+    p.P = P; p.x = x; p.xs_t = x_stride_t; p.xs_b = x_stride_b; p.h0 = h0; p.hseq = h_seq; p.ruc = ruc;
+    CUDA_TRY(launch_seq_fwd(p, pl.SB, pl.smem, (cudaStream_t)stream));
+    return 0;
+}
+
+static size_t enc_bwd_ws(const dcgru_cell_desc* d, int B, int T, bool carve, void* ws, float** WgT, float** WcT,
+                         float** dA, float** part, float** partb, int* nsplit, int* njobs, DwJob* jobs) {
+    const int H = d->hid_dim, M = Mof(d), CM = (d->input_dim + H) * M;
+    DwJob tmp[DW_MAXJOBS];
+    int nj = build_cell_jobs(d->input_dim, H, M, jobs ? jobs : tmp);
+    int ns = dw_nsplit(B, nj);
+    Carver c(ws, 0);
+    float* a = c.take((size_t)2 * H * CM);
+    float* b = c.take((size_t)H * CM);
+    float* e = c.take((size_t)T * B * d->num_nodes * 3 * H);
+    float* f = c.take((size_t)ns * CM * 3 * H);
+    float* g = c.take((size_t)ns * 3 * H);
+    if (carve) { *WgT = a; *WcT = b; *dA = e; *part = f; *partb = g; *nsplit = ns; *njobs = nj; }
+    return c.off;
+}
+
+size_t dcgru_encoder_layer_bwd_workspace(const dcgru_cell_desc* d, int32_t batch, int32_t seq_len) {
+    if (check_desc(d) || batch < 1 || seq_len < 1) return 0;
+    return enc_bwd_ws(d, batch, seq_len, false, nullptr, 0, 0, 0, 0, 0, 0, 0, 0);
+}
+
+int dcgru_encoder_layer_bwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq_len, const float* x,
+                            int64_t x_stride_t, int64_t x_stride_b, const float* h0, const float* P,
+                            const dcgru_cell_params* w, const float* h_seq, const float* ruc,
+                            const float* d_hseq, const float* d_hlast, float* dx, float* dh0,
+                            const dcgru_cell_grads* g, void* workspace, size_t workspace_bytes, void* stream) {
+    if (check_desc(d)) return 1;
+    if (batch < 1 || seq_len < 1) return fail("empty batch/sequence");
+    if (!x || !h0 || !w || !h_seq || !ruc || !dh0 || !g || !workspace) return fail("null pointer");
+    if (!g->dWg || !g->dbg || !g->dWc || !g->dbc) return fail("null gradient pointer");
+    const int M = Mof(d), H = d->hid_dim, fin = d->input_dim, CM = (fin + H) * M;
+    if (M > 1 && !P) return fail("null P");
+    if (!aligned16(workspace) || !aligned16(h_seq) || !aligned16(ruc)) return fail("unaligned pointer");
+    if (dcgru_encoder_layer_bwd_workspace(d, batch, seq_len) > workspace_bytes) return fail("workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    float *WgT, *WcT, *dA, *part, *partb;
+    int nsplit, njobs;
+    DwParams q;
+    memset(&q, 0, sizeof q);
+    enc_bwd_ws(d, batch, seq_len, true, workspace, &WgT, &WcT, &dA, &part, &partb, &nsplit, &njobs, q.jobs);
+    if (njobs > DW_MAXJOBS) return fail("too many weight-gradient jobs (%d)", njobs);
+    CUDA_TRY(launch_transpose(w->Wg, CM, 2 * H, WgT, CM, st));
+    CUDA_TRY(launch_transpose(w->Wc, CM, H, WcT, CM, st));
+    BwdPlan pl;
+    if (!plan_bwd(H, M, batch, 0, &pl)) return fail("no backward tiling fits shared memory");
+    BwdParams p;
+    memset(&p, 0, sizeof p);
+    p.B = batch; p.T = seq_len; p.N = d->num_nodes; p.H = H; p.M = M; p.act = d->activation; p.ncell = 1; p.mode = 0;
+    p.cell[0] = CellWT{WgT, WcT, fin};
+    p.P = P; p.h0 = h0; p.hseq = h_seq; p.ruc = ruc; p.d_hseq = d_hseq; p.d_hlast = d_hlast;
+    p.dx = dx; p.dh0 = dh0; p.dA = dA;
+    CUDA_TRY(launch_seq_bwd(p, pl.SB, pl.smem, st));
+    // bulk weight gradients
+    q.B = batch; q.T = seq_len; q.N = d->num_nodes; q.H = H; q.M = M; q.nsplit = nsplit; q.mode = 0;
+    q.layer = 0; q.ncell = 1; q.fin = fin; q.Fo = 0;
+    q.P = P; q.x = x; q.xs_t = x_stride_t; q.xs_b = x_stride_b; q.h0 = h0; q.hseq = h_seq; q.ruc = ruc; q.dA = dA;
+    q.part = part; q.partb = partb;
+    CUDA_TRY(launch_dw(q, njobs, otile(3 * H), st));
+    CUDA_TRY(launch_reduce_cell(part, partb, nsplit, CM, H, g->dWg, g->dbg, g->dWc, g->dbc, st));
+    return 0;
+}
+
+// ---- decoder ------------------------------------------------------------------------------------------
+static int check_dec(const dcgru_cell_desc* d, int L, int B, int T) {
+    if (check_desc(d)) return 1;
+    if (L < 1 || L > DCGRU_MAX_LAYERS) return fail("num_layers=%d unsupported (1..%d)", L, DCGRU_MAX_LAYERS);
+    if (B < 1 || T < 1) return fail("empty batch/sequence");
+    if (T > 64) return fail("decoder seq_len=%d > 64 unsupported", T);
+    return 0;
+}
+
+size_t dcgru_decoder_fwd_workspace(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T) {
+    if (check_dec(d, L, B, T)) return 0;
+    // projWT (H, FoPad) with the largest possible padding (SB = 1 -> multiples of 256)
+    return align_up((size_t)d->hid_dim * ((d->input_dim + 255) / 256 * 256) * 4);
+}
+
+int dcgru_decoder_fwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T, const float* targets,
+                      uint64_t teacher_mask, const float* h0, const float* P, const dcgru_cell_params* w,
+                      const float* proj_w, const float* proj_b, const float* drop_mask, float* out,
+                      float* h_all, float* ruc, void* workspace, size_t workspace_bytes, void* stream) {
+    if (check_dec(d, L, B, T)) return 1;
+    if (!h0 || !w || !proj_w || !proj_b || !out || !h_all || !workspace) return fail("null pointer");
+    if (teacher_mask && !targets) return fail("teacher forcing requested without targets");
+    const int M = Mof(d), H = d->hid_dim, Fo = d->input_dim;
+    if (M > 1 && !P) return fail("null P");
+    if (dcgru_decoder_fwd_workspace(d, L, B, T) > workspace_bytes) return fail("workspace too small");
+    int cmax = (Fo > H ? Fo : H) + H;
+    FwdPlan pl;
+    if (!plan_fwd(H, cmax, M, B, Fo, &pl)) return fail("no decoder tiling fits shared memory");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* projWT = (float*)workspace;
+    CUDA_TRY(launch_transpose(proj_w, Fo, H, projWT, pl.FoPad, st));
+    FwdParams p;
+    memset(&p, 0, sizeof p);
+    p.B = B; p.T = T; p.N = d->num_nodes; p.H = H; p.M = M; p.act = d->activation; p.ncell = L; p.KC = pl.KC; p.mode = 1;
+    for (int l = 0; l < L; ++l) {
+        if (!w[l].Wg || !w[l].bg || !w[l].Wc || !w[l].bc) return fail("null weights (layer %d)", l);
+        p.cell[l] = CellW{w[l].Wg, w[l].bg, w[l].Wc, w[l].bc, l == 0 ? Fo : H};
+    }
+    p.P = P; p.h0 = h0; p.hseq = h_all; p.ruc = ruc; p.targets = targets; p.teacher_mask = teacher_mask;
+    p.projWT = projWT; p.projb = proj_b; p.dropmask = drop_mask; p.out = out; p.Fo = Fo; p.FoPad = pl.FoPad;
+    CUDA_TRY(launch_seq_fwd(p, pl.SB, pl.smem, st));
+    return 0;
+}
+
+struct DecWs {
+    float *WgT[DCGRU_MAX_LAYERS], *WcT[DCGRU_MAX_LAYERS];
+    float *dA, *dY, *scratch, *part0, *partb0, *part1, *partb1, *partp, *partpb;
+    int ns0, nj0, ns1, nj1, nsp, njp;
+    size_t bytes;
+};
+static void dec_bwd_ws(const dcgru_cell_desc* d, int L, int B, int T, void* ws, DecWs* o) {
+    const int H = d->hid_dim, M = Mof(d), Fo = d->input_dim, N = d->num_nodes;
+    const int CM0 = (Fo + H) * M, CM1 = 2 * H * M;
+    DwJob tmp[DW_MAXJOBS];
+    o->nj0 = build_cell_jobs(Fo, H, M, tmp);  o->ns0 = dw_nsplit(B, o->nj0);
+    o->nj1 = build_cell_jobs(H, H, M, tmp);   o->ns1 = dw_nsplit(B, o->nj1);
+    o->njp = build_proj_jobs(Fo, H, tmp);     o->nsp = dw_nsplit(B, o->njp);
+    Carver c(ws, 0);
+    for (int l = 0; l < L; ++l) {
+        int CM = l == 0 ? CM0 : CM1;
+        o->WgT[l] = c.take((size_t)2 * H * CM);
+        o->WcT[l] = c.take((size_t)H * CM);
+    }
+    o->dA = c.take((size_t)T * L * B * N * 3 * H);
+    o->dY = c.take((size_t)T * B * N * Fo);
+    o->scratch = c.take((size_t)B * N * (Fo > H ? Fo : H));
+    o->part0 = c.take((size_t)o->ns0 * CM0 * 3 * H);
+    o->partb0 = c.take((size_t)o->ns0 * 3 * H);
+    o->part1 = c.take((size_t)(L > 1 ? L - 1 : 0) * o->ns1 * CM1 * 3 * H);
+    o->partb1 = c.take((size_t)(L > 1 ? L - 1 : 0) * o->ns1 * 3 * H);
+    o->partp = c.take((size_t)o->nsp * Fo * H);
+    o->partpb = c.take((size_t)o->nsp * Fo);
+    o->bytes = c.off;
+}
+
+size_t dcgru_decoder_bwd_workspace(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T) {
+    if (check_dec(d, L, B, T)) return 0;
+    DecWs o;
+    dec_bwd_ws(d, L, B, T, nullptr, &o);
+    return o.bytes;
+}
+
+int dcgru_decoder_bwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T, const float* targets,
+                      uint64_t teacher_mask, const float* h0, const float* P, const dcgru_cell_params* w,
+                      const float* proj_w, const float* drop_mask, const float* out, const float* h_all,
+                      const float* ruc, const float* d_out, float* dh0, const dcgru_cell_grads* g,
+                      float* dproj_w, float* dproj_b, void* workspace, size_t workspace_bytes, void* stream) {
+    if (check_dec(d, L, B, T)) return 1;
+    if (!h0 || !w || !proj_w || !out || !h_all || !ruc || !d_out || !dh0 || !g || !dproj_w || !dproj_b || !workspace)
+        return fail("null pointer");
+    if (teacher_mask && !targets) return fail("teacher forcing requested without targets");
+    const int M = Mof(d), H = d->hid_dim, Fo = d->input_dim, N = d->num_nodes;
+    if (M > 1 && !P) return fail("null P");
+    // weight tying (model/model.py:126,142-143): layers >= 1 either all share one cell or none do
+    bool tied = L > 2;
+    for (int l = 2; l < L; ++l) tied = tied && (w[l].Wg == w[1].Wg);
+    for (int l = 2; l < L; ++l)
+        if (!tied && w[l].Wg == w[1].Wg) return fail("partially tied decoder cells are unsupported");
+    if (tied)
+        for (int l = 2; l < L; ++l)
+            if (g[l].dWg != g[1].dWg) return fail("gradient buffers of tied cells must alias");
+    DecWs o;
+    dec_bwd_ws(d, L, B, T, workspace, &o);
+    if (o.bytes > workspace_bytes) return fail("workspace too small");
+    if (o.nj0 > DW_MAXJOBS || o.nj1 > DW_MAXJOBS || o.njp > DW_MAXJOBS) return fail("too many weight-gradient jobs");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t NH = (size_t)N * H;
+    BwdPlan pl;
+    if (!plan_bwd(H, M, B, Fo, &pl)) return fail("no decoder backward tiling fits shared memory");
+    BwdParams p;
+    memset(&p, 0, sizeof p);
+    p.B = B; p.T = T; p.N = N; p.H = H; p.M = M; p.act = d->activation; p.ncell = L; p.mode = 1;
+    for (int l = 0; l < L; ++l) {
+        int fin = l == 0 ? Fo : H, CM = (fin + H) * M;
+        if (l <= 1 || !tied) {
+            CUDA_TRY(launch_transpose(w[l].Wg, CM, 2 * H, o.WgT[l], CM, st));
+            CUDA_TRY(launch_transpose(w[l].Wc, CM, H, o.WcT[l], CM, st));
+            p.cell[l] = CellWT{o.WgT[l], o.WcT[l], fin};
+        } else {
+            p.cell[l] = p.cell[1];
+        }
+    }
+    p.P = P; p.h0 = h0; p.hseq = h_all; p.ruc = ruc; p.dh0 = dh0; p.dA = o.dA;
+    p.d_out = d_out; p.proj_w = proj_w; p.dropmask = drop_mask; p.teacher_mask = teacher_mask;
+    p.dY = o.dY; p.scratch = o.scratch; p.Fo = Fo;
+    CUDA_TRY(cudaMemsetAsync(dh0, 0, (size_t)L * B * NH * 4, st));
+    CUDA_TRY(launch_seq_bwd(p, pl.SB, pl.smem, st));
+    // ---- bulk gradients ----------------------------------------------------------------------------
+    DwParams q;
+    memset(&q, 0, sizeof q);
+    q.B = B; q.T = T; q.N = N; q.H = H; q.M = M; q.mode = 1; q.ncell = L; q.Fo = Fo;
+    q.P = P; q.h0 = h0; q.hseq = h_all; q.ruc = ruc; q.dA = o.dA; q.targets = targets; q.out = out;
+    q.teacher_mask = teacher_mask; q.dY = o.dY; q.dropmask = drop_mask;
+    // cell 0
+    q.layer = 0; q.fin = Fo; q.nsplit = o.ns0; q.part = o.part0; q.partb = o.partb0;
+    build_cell_jobs(Fo, H, M, q.jobs);
+    CUDA_TRY(launch_dw(q, o.nj0, otile(3 * H), st));
+    CUDA_TRY(launch_reduce_cell(o.part0, o.partb0, o.ns0, (Fo + H) * M, H, g[0].dWg, g[0].dbg, g[0].dWc, g[0].dbc, st));
+    // cells >= 1
+    build_cell_jobs(H, H, M, q.jobs);
+    const size_t psz = (size_t)2 * H * M * 3 * H;
+    for (int l = 1; l < L; ++l) {
+        q.layer = l; q.fin = H; q.nsplit = o.ns1;
+        q.part = o.part1 + (size_t)(l - 1) * o.ns1 * psz;
+        q.partb = o.partb1 + (size_t)(l - 1) * o.ns1 * 3 * H;
+        CUDA_TRY(launch_dw(q, o.nj1, otile(3 * H), st));
+        if (!tied)
+            CUDA_TRY(launch_reduce_cell(q.part, q.partb, o.ns1, 2 * H * M, H, g[l].dWg, g[l].dbg, g[l].dWc, g[l].dbc, st));
+    }
+    if (tied)
+        CUDA_TRY(launch_reduce_cell(o.part1, o.partb1, (L - 1) * o.ns1, 2 * H * M, H, g[1].dWg, g[1].dbg, g[1].dWc,
+                                    g[1].dbc, st));
+    // Linear
+    q.layer = L - 1; q.fin = Fo; q.nsplit = o.nsp; q.part = o.partp; q.partb = o.partpb;
+    build_proj_jobs(Fo, H, q.jobs);
+    CUDA_TRY(launch_dw(q, o.njp, otile(H), st));
+    CUDA_TRY(launch_reduce_flat(o.partp, o.nsp, (size_t)Fo * H, dproj_w, st));
+    CUDA_TRY(launch_reduce_flat(o.partpb, o.nsp, (size_t)Fo, dproj_b, st));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+/*
+ * dcgru_b200 -- C ABI of the B200-native DCGRU forward/backward path.
+ *
+ * The reference (tsy935/eeg-gnn-ssl) has no FFI for this path: its boundary is the Python
+ * class surface of model/cell.py and model/model.py.  These entry points are what
+ * a binding for that surface has to call; every one cites the reference code it replaces.
+ * All tensors are dense fp32, row-major, device pointers owned by the caller; the library
+ * allocates nothing persistent, keeps no thread-local state except the last error string,
+ * launches on the caller's stream and never synchronises it.
+ *
+ * Return value: 0 on success, non-zero on error (message via dcgru_last_error()).
+ *
+ * Notation: B batch, T steps, N nodes (<= 20; the reference uses 19), Fin/Fo feature dims,
+ * H rnn units, K max_diffusion_step, S number of supports, M = S*K + 1, C = Fin + H.
+ */
+#ifndef DCGRU_B200_H
+#define DCGRU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCGRU_MAX_LAYERS 4
+#define DCGRU_ACT_TANH 0
+#define DCGRU_ACT_RELU 1
+
+/* One DCGRU cell's hyper-parameters: the constructor arguments of
+ * DCGRUCell (model/cell.py:126-175) that change the arithmetic. */
+typedef struct dcgru_cell_desc {
+    int32_t num_nodes;          /* N   (model/cell.py:147) */
+    int32_t input_dim;          /* Fin (model/cell.py:162) */
+    int32_t hid_dim;            /* H   (model/cell.py:148) */
+    int32_t max_diffusion_step; /* K   (model/cell.py:149) */
+    int32_t num_supports;       /* S   (model/cell.py:151-158) */
+    int32_t activation;         /* DCGRU_ACT_* (model/cell.py:146: anything but 'tanh' is relu) */
+} dcgru_cell_desc;
+
+/* One cell's parameters: dconv_gate.{weight,biases}, dconv_candidate.{weight,biases}
+ * (model/cell.py:40-48,160-175).  weight rows are indexed c*M + m (model/cell.py:98-114). */
+typedef struct dcgru_cell_params {
+    const float *Wg; /* (C*M, 2H) */
+    const float *bg; /* (2H)      */
+    const float *Wc; /* (C*M, H)  */
+    const float *bc; /* (H)       */
+} dcgru_cell_params;
+
+typedef struct dcgru_cell_grads {
+    float *dWg, *dbg, *dWc, *dbc; /* same shapes, overwritten */
+} dcgru_cell_grads;
+
+int dcgru_version(void);
+const char *dcgru_last_error(void);
+
+/* ---- graph -> diffusion polynomials -------------------------------------------------------
+ * Replaces the hop recurrence of DiffusionGraphConv.forward (model/cell.py:76-93): since
+ * diffusion is linear, term_m = P_m Z with per-sample N x N matrices P_m (the
+ * carried-x0 quirk across supports is reproduced).  supports[s] points at (B,N,N) with
+ * batch stride support_bstride[s] elements (0 broadcasts one (N,N) matrix).
+ * P out: (B, M-1, N, N).                                                                     */
+int dcgru_graph_poly(int32_t batch, int32_t num_nodes, int32_t max_diffusion_step,
+                     int32_t num_supports, const float *const *supports,
+                     const int64_t *support_bstride, float *P, void *stream);
+
+/* ---- correlation graph -> supports --------------------------------------------------------
+ * Replaces SeizureDataset._get_indiv_graphs + _compute_supports('dual_random_walk')
+ * (data/dataloader_detection.py:258-307,335-354; data/data_utils.py:174-222;
+ * utils.py:220-230) for a whole batch on the device.
+ * clip: (B, T, N, F) with element strides (sb, st); value used = clip*scale + shift
+ * (scale=std, shift=mean undoes the scalar StandardScaler, utils.py:402-403; 1,0 for raw).
+ * adj out (B,N,N) (may be NULL), support0/support1 out (B,N,N).                              */
+int dcgru_corr_supports(int32_t batch, int32_t seq_len, int32_t num_nodes, int32_t feat,
+                        const float *clip, int64_t stride_b, int64_t stride_t,
+                        float scale, float shift, int32_t top_k,
+                        float *adj, float *support0, float *support1, void *stream);
+
+/* ---- encoder layer -------------------------------------------------------------------------
+ * One launch = one RNN layer over all T steps (the inner loop of DCRNNEncoder.forward,
+ * model/model.py:93-96, around DCGRUCell.forward, model/cell.py:182-210).
+ * x:     input sequence, element (t,b,:) at x + t*x_stride_t + b*x_stride_b, N*Fin contiguous
+ * h0:    (B, N*H)
+ * P:     (B, M-1, N, N) from dcgru_graph_poly
+ * h_seq: (T, B, N*H) out -- every step's hidden state (the layer's output sequence)
+ * ruc:   (T, B, N, 3H) out -- r | u | c per node, saved for backward (NULL: inference)       */
+int dcgru_encoder_layer_fwd(const dcgru_cell_desc *d, int32_t batch, int32_t seq_len,
+                            const float *x, int64_t x_stride_t, int64_t x_stride_b,
+                            const float *h0, const float *P, const dcgru_cell_params *w,
+                            float *h_seq, float *ruc, void *stream);
+
+size_t dcgru_encoder_layer_bwd_workspace(const dcgru_cell_desc *d, int32_t batch,
+                                         int32_t seq_len);
+
+/* Backward of the above (what autograd derives for the reference).
+ * d_hseq:  (T,B,N*H) upstream gradient of h_seq (NULL = zeros)
+ * d_hlast: (B,N*H)  extra upstream gradient of h_seq[T-1] (the layer's output_hidden; NULL)
+ * dx:      (T,B,N*Fin) out, or NULL when the input needs no gradient (layer 0)
+ * dh0:     (B,N*H) out                                                                        */
+int dcgru_encoder_layer_bwd(const dcgru_cell_desc *d, int32_t batch, int32_t seq_len,
+                            const float *x, int64_t x_stride_t, int64_t x_stride_b,
+                            const float *h0, const float *P, const dcgru_cell_params *w,
+                            const float *h_seq, const float *ruc,
+                            const float *d_hseq, const float *d_hlast,
+                            float *dx, float *dh0, const dcgru_cell_grads *g,
+                            void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- decoder -------------------------------------------------------------------------------
+ * One launch = DCGRUDecoder.forward (model/model.py:149-204): To autoregressive steps x L
+ * cells + Linear(H->Fo) per node.  d describes cell 0 (input_dim = Fo); cells >= 1 have
+ * input_dim = H.  w[l] may alias for l >= 1 (weight tying, model/model.py:126,142-143).
+ * targets:      (To,B,N*Fo) teacher inputs, or NULL
+ * teacher_mask: bit t set => input of step t+1 is targets[t] (the outcome of the reference's
+ *               per-step random.random() draw, model/model.py:198-202); To <= 64
+ * h0:           (L,B,N*H) encoder context
+ * proj_w:       (Fo,H), proj_b: (Fo)   (nn.Linear, model/model.py:146)
+ * drop_mask:    (To,B,N,H) multiplicative dropout mask or NULL (model/model.py:192)
+ * out:          (To,B,N*Fo)
+ * h_all:        (To,L,B,N*H) out, ruc: (To,L,B,N,3H) out (saved for backward)                 */
+size_t dcgru_decoder_fwd_workspace(const dcgru_cell_desc *d, int32_t num_layers,
+                                   int32_t batch, int32_t seq_len);
+int dcgru_decoder_fwd(const dcgru_cell_desc *d, int32_t num_layers, int32_t batch,
+                      int32_t seq_len, const float *targets, uint64_t teacher_mask,
+                      const float *h0, const float *P, const dcgru_cell_params *w,
+                      const float *proj_w, const float *proj_b, const float *drop_mask,
+                      float *out, float *h_all, float *ruc,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
+size_t dcgru_decoder_bwd_workspace(const dcgru_cell_desc *d, int32_t num_layers,
+                                   int32_t batch, int32_t seq_len);
+/* g[l] for tied layers (w[l] aliasing w[1]) must alias too; gradients of tied cells are summed.
+ * d_out: (To,B,N*Fo) upstream; dh0: (L,B,N*H) out; dproj_w (Fo,H), dproj_b (Fo) out.         */
+int dcgru_decoder_bwd(const dcgru_cell_desc *d, int32_t num_layers, int32_t batch,
+                      int32_t seq_len, const float *targets, uint64_t teacher_mask,
+                      const float *h0, const float *P, const dcgru_cell_params *w,
+                      const float *proj_w, const float *drop_mask,
+                      const float *out, const float *h_all, const float *ruc,
+                      const float *d_out, float *dh0, const dcgru_cell_grads *g,
+                      float *dproj_w, float *dproj_b,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCGRU_B200_H */

@@ -3,7 +3,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 #include "dw.cuh"
@@ -28,6 +31,32 @@ int fail(const char* fmt, ...) {
     do {                                                                                 \
         cudaError_t e_ = (expr);                                                         \
         if (e_ != cudaSuccess) return fail("%s: %s", #expr, cudaGetErrorString(e_));     \
+    } while (0)
+
+// ---- optional per-kernel device timing (bench.py's roofline leg) -------------------------------------
+// When enabled, every kernel launch below is bracketed by two cudaEvents recorded on the launching
+// stream; dcgru_timing_collect() synchronises them and reports count / total ms per kernel name.
+struct TimingRec { const char* name; cudaEvent_t a, b; };
+std::mutex g_tmu;
+bool g_timing = false;
+std::vector<TimingRec> g_recs;
+struct Timed {
+    cudaStream_t st; cudaEvent_t b = nullptr;
+    Timed(const char* name, cudaStream_t s) : st(s) {
+        if (!g_timing) return;
+        std::lock_guard<std::mutex> lk(g_tmu);
+        TimingRec r; r.name = name;
+        if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+        cudaEventRecord(r.a, st);
+        b = r.b;
+        g_recs.push_back(r);
+    }
+    ~Timed() { if (b) cudaEventRecord(b, st); }
+};
+#define LAUNCH(name, expr)          \
+    do {                            \
+        Timed t_(name, st);         \
+        CUDA_TRY(expr);             \
     } while (0)
 
 struct DevInfo { int sms = 0; int smem = 0; bool ok = false; };
@@ -160,6 +189,35 @@ struct Carver {
 extern "C" {
 
 int dcgru_version(void) { return 100; }
+
+int dcgru_timing_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_tmu);
+    for (auto& r : g_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_recs.clear();
+    g_timing = on != 0;
+    return 0;
+}
+
+int dcgru_timing_collect(char* buf, size_t cap) {
+    std::lock_guard<std::mutex> lk(g_tmu);
+    std::map<std::string, std::pair<long, double>> agg;
+    for (auto& r : g_recs) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.b) != cudaSuccess || cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess)
+            return fail("timing events not complete");
+        auto& e = agg[r.name];
+        e.first += 1; e.second += ms;
+    }
+    std::string out;
+    char line[160];
+    for (auto& kv : agg) {
+        snprintf(line, sizeof line, "%s %ld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += line;
+    }
+    if (!buf || out.size() + 1 > cap) return fail("timing buffer too small");
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return 0;
+}
 const char* dcgru_last_error(void) { return g_err.c_str(); }
 
 int dcgru_graph_poly(int32_t batch, int32_t num_nodes, int32_t max_diffusion_step, int32_t num_supports,
@@ -174,8 +232,8 @@ int dcgru_graph_poly(int32_t batch, int32_t num_nodes, int32_t max_diffusion_ste
         bs[s] = support_bstride ? support_bstride[s] : (long long)num_nodes * num_nodes;
     }
     if (max_diffusion_step > 0 && !P) return fail("null P");
-    CUDA_TRY(launch_graph_poly(batch, num_nodes, max_diffusion_step, num_supports, supports, bs, P,
-                               (cudaStream_t)stream));
+    cudaStream_t st = (cudaStream_t)stream;
+    LAUNCH("graph_poly", launch_graph_poly(batch, num_nodes, max_diffusion_step, num_supports, supports, bs, P, st));
     return 0;
 }
 
@@ -187,8 +245,9 @@ int dcgru_corr_supports(int32_t batch, int32_t seq_len, int32_t num_nodes, int32
     if (top_k < 0) return fail("top_k < 0 (the reference raises ValueError for top_k=None)");
     if (!clip || !support0 || !support1) return fail("null pointer");
     if ((size_t)num_nodes * (feat | 1) * 4 > (size_t)devinfo().smem) return fail("feature dim too large");
-    CUDA_TRY(launch_corr_supports(batch, seq_len, num_nodes, feat, clip, stride_b, stride_t, scale, shift, top_k,
-                                  adj, support0, support1, (cudaStream_t)stream));
+    cudaStream_t st = (cudaStream_t)stream;
+    LAUNCH("corr_supports", launch_corr_supports(batch, seq_len, num_nodes, feat, clip, stride_b, stride_t, scale,
+                                                 shift, top_k, adj, support0, support1, st));
     return 0;
 }
 
@@ -212,7 +271,8 @@ int dcgru_encoder_layer_fwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
     p.ncell = 1; p.KC = pl.KC; p.mode = 0;
     p.cell[0] = CellW{w->Wg, w->bg, w->Wc, w->bc, d->input_dim};
     p.P = P; p.x = x; p.xs_t = x_stride_t; p.xs_b = x_stride_b; p.h0 = h0; p.hseq = h_seq; p.ruc = ruc;
-    CUDA_TRY(launch_seq_fwd(p, pl.SB, pl.smem, (cudaStream_t)stream));
+    cudaStream_t st = (cudaStream_t)stream;
+    LAUNCH("seq_fwd", launch_seq_fwd(p, pl.SB, pl.smem, st));
     return 0;
 }
 
@@ -257,8 +317,8 @@ int dcgru_encoder_layer_bwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
     memset(&q, 0, sizeof q);
     enc_bwd_ws(d, batch, seq_len, true, workspace, &WgT, &WcT, &dA, &part, &partb, &nsplit, &njobs, q.jobs);
     if (njobs > DW_MAXJOBS) return fail("too many weight-gradient jobs (%d)", njobs);
-    CUDA_TRY(launch_transpose(w->Wg, CM, 2 * H, WgT, CM, st));
-    CUDA_TRY(launch_transpose(w->Wc, CM, H, WcT, CM, st));
+    LAUNCH("transpose", launch_transpose(w->Wg, CM, 2 * H, WgT, CM, st));
+    LAUNCH("transpose", launch_transpose(w->Wc, CM, H, WcT, CM, st));
     BwdPlan pl;
     if (!plan_bwd(H, M, batch, 0, &pl)) return fail("no backward tiling fits shared memory");
     BwdParams p;
@@ -267,14 +327,14 @@ int dcgru_encoder_layer_bwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
     p.cell[0] = CellWT{WgT, WcT, fin};
     p.P = P; p.h0 = h0; p.hseq = h_seq; p.ruc = ruc; p.d_hseq = d_hseq; p.d_hlast = d_hlast;
     p.dx = dx; p.dh0 = dh0; p.dA = dA;
-    CUDA_TRY(launch_seq_bwd(p, pl.SB, pl.smem, st));
+    LAUNCH("seq_bwd", launch_seq_bwd(p, pl.SB, pl.smem, st));
     // bulk weight gradients
     q.B = batch; q.T = seq_len; q.N = d->num_nodes; q.H = H; q.M = M; q.nsplit = nsplit; q.mode = 0;
     q.layer = 0; q.ncell = 1; q.fin = fin; q.Fo = 0;
     q.P = P; q.x = x; q.xs_t = x_stride_t; q.xs_b = x_stride_b; q.h0 = h0; q.hseq = h_seq; q.ruc = ruc; q.dA = dA;
     q.part = part; q.partb = partb;
-    CUDA_TRY(launch_dw(q, njobs, otile(3 * H), st));
-    CUDA_TRY(launch_reduce_cell(part, partb, nsplit, CM, H, g->dWg, g->dbg, g->dWc, g->dbc, st));
+    LAUNCH("dw", launch_dw(q, njobs, otile(3 * H), st));
+    LAUNCH("reduce", launch_reduce_cell(part, partb, nsplit, CM, H, g->dWg, g->dbg, g->dWc, g->dbc, st));
     return 0;
 }
 
@@ -308,7 +368,7 @@ int dcgru_decoder_fwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T,
     if (!plan_fwd(H, cmax, M, B, Fo, &pl)) return fail("no decoder tiling fits shared memory");
     cudaStream_t st = (cudaStream_t)stream;
     float* projWT = (float*)workspace;
-    CUDA_TRY(launch_transpose(proj_w, Fo, H, projWT, pl.FoPad, st));
+    LAUNCH("transpose", launch_transpose(proj_w, Fo, H, projWT, pl.FoPad, st));
     FwdParams p;
     memset(&p, 0, sizeof p);
     p.B = B; p.T = T; p.N = d->num_nodes; p.H = H; p.M = M; p.act = d->activation; p.ncell = L; p.KC = pl.KC; p.mode = 1;
@@ -318,7 +378,7 @@ int dcgru_decoder_fwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T,
     }
     p.P = P; p.h0 = h0; p.hseq = h_all; p.ruc = ruc; p.targets = targets; p.teacher_mask = teacher_mask;
     p.projWT = projWT; p.projb = proj_b; p.dropmask = drop_mask; p.out = out; p.Fo = Fo; p.FoPad = pl.FoPad;
-    CUDA_TRY(launch_seq_fwd(p, pl.SB, pl.smem, st));
+    LAUNCH("seq_fwd", launch_seq_fwd(p, pl.SB, pl.smem, st));
     return 0;
 }
 
@@ -393,8 +453,8 @@ int dcgru_decoder_bwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T,
     for (int l = 0; l < L; ++l) {
         int fin = l == 0 ? Fo : H, CM = (fin + H) * M;
         if (l <= 1 || !tied) {
-            CUDA_TRY(launch_transpose(w[l].Wg, CM, 2 * H, o.WgT[l], CM, st));
-            CUDA_TRY(launch_transpose(w[l].Wc, CM, H, o.WcT[l], CM, st));
+            LAUNCH("transpose", launch_transpose(w[l].Wg, CM, 2 * H, o.WgT[l], CM, st));
+            LAUNCH("transpose", launch_transpose(w[l].Wc, CM, H, o.WcT[l], CM, st));
             p.cell[l] = CellWT{o.WgT[l], o.WcT[l], fin};
         } else {
             p.cell[l] = p.cell[1];
@@ -404,7 +464,7 @@ int dcgru_decoder_bwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T,
     p.d_out = d_out; p.proj_w = proj_w; p.dropmask = drop_mask; p.teacher_mask = teacher_mask;
     p.dY = o.dY; p.scratch = o.scratch; p.Fo = Fo;
     CUDA_TRY(cudaMemsetAsync(dh0, 0, (size_t)L * B * NH * 4, st));
-    CUDA_TRY(launch_seq_bwd(p, pl.SB, pl.smem, st));
+    LAUNCH("seq_bwd", launch_seq_bwd(p, pl.SB, pl.smem, st));
     // ---- bulk gradients ----------------------------------------------------------------------------
     DwParams q;
     memset(&q, 0, sizeof q);
@@ -414,8 +474,8 @@ int dcgru_decoder_bwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T,
     // cell 0
     q.layer = 0; q.fin = Fo; q.nsplit = o.ns0; q.part = o.part0; q.partb = o.partb0;
     build_cell_jobs(Fo, H, M, q.jobs);
-    CUDA_TRY(launch_dw(q, o.nj0, otile(3 * H), st));
-    CUDA_TRY(launch_reduce_cell(o.part0, o.partb0, o.ns0, (Fo + H) * M, H, g[0].dWg, g[0].dbg, g[0].dWc, g[0].dbc, st));
+    LAUNCH("dw", launch_dw(q, o.nj0, otile(3 * H), st));
+    LAUNCH("reduce", launch_reduce_cell(o.part0, o.partb0, o.ns0, (Fo + H) * M, H, g[0].dWg, g[0].dbg, g[0].dWc, g[0].dbc, st));
     // cells >= 1
     build_cell_jobs(H, H, M, q.jobs);
     const size_t psz = (size_t)2 * H * M * 3 * H;
@@ -423,19 +483,19 @@ int dcgru_decoder_bwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T,
         q.layer = l; q.fin = H; q.nsplit = o.ns1;
         q.part = o.part1 + (size_t)(l - 1) * o.ns1 * psz;
         q.partb = o.partb1 + (size_t)(l - 1) * o.ns1 * 3 * H;
-        CUDA_TRY(launch_dw(q, o.nj1, otile(3 * H), st));
+        LAUNCH("dw", launch_dw(q, o.nj1, otile(3 * H), st));
         if (!tied)
-            CUDA_TRY(launch_reduce_cell(q.part, q.partb, o.ns1, 2 * H * M, H, g[l].dWg, g[l].dbg, g[l].dWc, g[l].dbc, st));
+            LAUNCH("reduce", launch_reduce_cell(q.part, q.partb, o.ns1, 2 * H * M, H, g[l].dWg, g[l].dbg, g[l].dWc, g[l].dbc, st));
     }
     if (tied)
-        CUDA_TRY(launch_reduce_cell(o.part1, o.partb1, (L - 1) * o.ns1, 2 * H * M, H, g[1].dWg, g[1].dbg, g[1].dWc,
+        LAUNCH("reduce", launch_reduce_cell(o.part1, o.partb1, (L - 1) * o.ns1, 2 * H * M, H, g[1].dWg, g[1].dbg, g[1].dWc,
                                     g[1].dbc, st));
     // Linear
     q.layer = L - 1; q.fin = Fo; q.nsplit = o.nsp; q.part = o.partp; q.partb = o.partpb;
     build_proj_jobs(Fo, H, q.jobs);
-    CUDA_TRY(launch_dw(q, o.njp, otile(H), st));
-    CUDA_TRY(launch_reduce_flat(o.partp, o.nsp, (size_t)Fo * H, dproj_w, st));
-    CUDA_TRY(launch_reduce_flat(o.partpb, o.nsp, (size_t)Fo, dproj_b, st));
+    LAUNCH("dw", launch_dw(q, o.njp, otile(H), st));
+    LAUNCH("reduce", launch_reduce_flat(o.partp, o.nsp, (size_t)Fo * H, dproj_w, st));
+    LAUNCH("reduce", launch_reduce_flat(o.partpb, o.nsp, (size_t)Fo, dproj_b, st));
     return 0;
 }
 

@@ -54,6 +54,12 @@ typedef struct dcgru_cell_grads {
 int dcgru_version(void);
 const char *dcgru_last_error(void);
 
+/* Diagnostics (no reference counterpart; used by bench.py's roofline leg): when enabled, each kernel
+ * launched by this library is bracketed by cudaEvents on the launching stream.  collect() waits for
+ * them and writes "name count total_ms\n" lines into buf.  enable(0/1) also clears the records.    */
+int dcgru_timing_enable(int on);
+int dcgru_timing_collect(char *buf, size_t cap);
+
 /* ---- graph -> diffusion polynomials -------------------------------------------------------
  * Replaces the hop recurrence of DiffusionGraphConv.forward (model/cell.py:76-93): since
  * diffusion is linear, term_m = P_m Z with per-sample N x N matrices P_m (the

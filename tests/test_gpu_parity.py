@@ -146,24 +146,31 @@ def _rand_case(dev, B, T, H, K, S, L, act, fin=100, seed=0):
     h0 = 0.5 * torch.randn(L, B, N * H, generator=g)
     wt = torch.randn(T, B, N * H, generator=g)
     wl = torch.randn(L, B, N * H, generator=g)
-    # oracle in fp64
-    layers = []
-    for c in enc.encoding_cells:
-        layers.append({k: v.detach().double().requires_grad_(True) for k, v in zip(
-            ("Wg", "bg", "Wc", "bc"), c.flat_params())})
-    h0d = h0.double().requires_grad_(True)
-    oh, top = O.encoder_forward(x.double(), h0d, [s.double() for s in sup], layers, K, N, act)
-    ((top * wt.double()).sum() + (oh * wl.double()).sum()).backward()
+    # oracle in fp64 (truth) and in fp32 (what the reference's own arithmetic achieves)
+    def run_oracle(dt):
+        layers = []
+        for c in enc.encoding_cells:
+            layers.append({k: v.detach().to(dt).requires_grad_(True) for k, v in zip(
+                ("Wg", "bg", "Wc", "bc"), c.flat_params())})
+        h0d = h0.detach().clone().to(dt).requires_grad_(True)
+        oh, top = O.encoder_forward(x.to(dt), h0d, [s.to(dt) for s in sup], layers, K, N, act)
+        ((top * wt.to(dt)).sum() + (oh * wl.to(dt)).sum()).backward()
+        out = {"top": top.detach(), "oh": oh.detach(), "dh0": h0d.grad}
+        for l in range(L):
+            for k in ("Wg", "bg", "Wc", "bc"):
+                out[f"L{l}.{k}"] = layers[l][k].grad
+        return out
+    ref64, ref32 = run_oracle(torch.float64), run_oracle(torch.float32)
     # ours
     enc = enc.to(dev)
     h0g = h0.to(dev).requires_grad_(True)
     oh2, top2 = enc(x.to(dev), h0g, [s.to(dev) for s in sup])
     ((top2 * wt.to(dev)).sum() + (oh2 * wl.to(dev)).sum()).backward()
-    res = {"top": (top2, top), "oh": (oh2, oh), "dh0": (h0g.grad, h0d.grad)}
+    ours = {"top": top2.detach(), "oh": oh2.detach(), "dh0": h0g.grad}
     for l, c in enumerate(enc.encoding_cells):
         for k, p in zip(("Wg", "bg", "Wc", "bc"), c.flat_params()):
-            res[f"L{l}.{k}"] = (p.grad, layers[l][k].grad)
-    return res
+            ours[f"L{l}.{k}"] = p.grad
+    return ours, ref64, ref32
 
 
 @pytest.mark.parametrize("B,T,H,K,S,L,act", [
@@ -175,10 +182,11 @@ def _rand_case(dev, B, T, H, K, S, L, act, fin=100, seed=0):
     (150, 2, 64, 2, 1, 1, "tanh"),      # more CTAs than one per sample group size 1
 ])
 def test_encoder_vs_oracle_fp64(dev, B, T, H, K, S, L, act):
-    res = _rand_case(dev, B, T, H, K, S, L, act)
-    for k, (ours, ref) in res.items():
-        e = rel_err(ours.detach().cpu().numpy(), ref.detach().numpy())
-        assert e < TOL, (k, e)
+    ours, ref64, ref32 = _rand_case(dev, B, T, H, K, S, L, act)
+    for k in ours:
+        e = rel_err(ours[k].cpu().numpy(), ref64[k].numpy())
+        e32 = rel_err(ref32[k].numpy(), ref64[k].numpy())      # fp32 round-off of the same math on CPU
+        assert e < max(TOL, 4 * e32), (k, e, e32)
 
 
 def test_cell_single_step(dev):

@@ -1,0 +1,120 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol the header declares,
+argument validation fails loudly, and the drop-in modules keep the reference's structure."""
+import ctypes as C
+import os
+import re
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import ROOT, load_golden
+
+
+def _ensure_built():
+    import __graft_entry__ as g
+    if not os.path.exists(os.path.join(ROOT, "eeg-gnn-ssl_b200", "lib", "libdcgru_b200.so")):
+        g.build()
+
+
+def test_library_exports_every_declared_symbol():
+    _ensure_built()
+    from eeg_gnn_ssl_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "dcgru_b200.h")).read()
+    declared = set(re.findall(r"\b(dcgru_[a-z_0-9]+)\s*\(", hdr))
+    assert {"dcgru_encoder_layer_fwd", "dcgru_encoder_layer_bwd", "dcgru_decoder_fwd", "dcgru_decoder_bwd",
+            "dcgru_graph_poly", "dcgru_corr_supports"} <= declared
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert set(_lib.SYMBOLS) <= declared
+    assert L.dcgru_version() >= 100
+
+
+def test_argument_validation_reports_errors():
+    _ensure_built()
+    from eeg_gnn_ssl_b200 import _lib
+    L = _lib.lib()
+    bad = _lib.CellDesc(19, 100, 48, 2, 1, 0)
+    assert L.dcgru_encoder_layer_bwd_workspace(C.byref(bad), 4, 4) == 0
+    assert b"hid_dim" in L.dcgru_last_error()
+    bad = _lib.CellDesc(33, 100, 64, 2, 1, 0)
+    assert L.dcgru_decoder_bwd_workspace(C.byref(bad), 3, 4, 4) == 0
+    assert b"num_nodes" in L.dcgru_last_error()
+    ok = _lib.CellDesc(19, 100, 64, 2, 1, 0)
+    assert L.dcgru_encoder_layer_bwd_workspace(C.byref(ok), 512, 60) > 400e6   # dA alone is 448 MB
+    assert L.dcgru_decoder_bwd_workspace(C.byref(ok), 3, 4, 65) == 0            # To > 64
+    rc = L.dcgru_encoder_layer_fwd(C.byref(ok), 4, 4, None, 0, 0, None, None, None, None, None, None)
+    assert rc != 0 and b"null" in L.dcgru_last_error()
+
+
+def test_cpu_tensors_are_rejected_not_emulated():
+    from eeg_gnn_ssl_b200.model.cell import DCGRUCell
+    cell = DCGRUCell(100, 64, 2, 19)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        cell([torch.eye(19)], torch.zeros(2, 1900), torch.zeros(2, 19 * 64))
+
+
+def _args(**kw):
+    base = dict(num_nodes=19, num_rnn_layers=3, rnn_units=64, input_dim=100, output_dim=100,
+                max_diffusion_step=2, dcgru_activation="tanh", filter_type="laplacian", dropout=0.0,
+                cl_decay_steps=3000, use_curriculum_learning=False)
+    base.update(kw)
+    return types.SimpleNamespace(**base)
+
+
+def test_state_dict_layout_matches_reference():
+    from eeg_gnn_ssl_b200.model.model import DCRNNModel_nextTimePred
+    _, a = load_golden("ssl_distance")
+    m = DCRNNModel_nextTimePred(_args(rnn_units=32))
+    assert list(m.state_dict().keys()) == [str(k) for k in a["state_keys"]]
+    sd = m.state_dict()
+    # tied decoder cells: same storage under both indices; named_parameters lists it once
+    assert sd["decoder.decoding_cells.1.dconv_gate.weight"].data_ptr() == \
+        sd["decoder.decoding_cells.2.dconv_gate.weight"].data_ptr()
+    names = [n for n, _ in m.named_parameters()]
+    assert not any(".decoding_cells.2." in n for n in names)
+    for n, p in m.named_parameters():
+        assert tuple(p.shape) == a["param:" + n].shape, n
+    # utils.build_finetune_model re-binds these attributes (utils.py:172-174)
+    enc0 = m.encoder.encoding_cells[0]
+    enc0.dconv_gate, enc0.dconv_candidate = enc0.dconv_gate, enc0.dconv_candidate
+
+
+@pytest.mark.parametrize("name,seed", [("ssl_distance", 21), ("enc_cfg1_distance", 123)])
+def test_seed_for_seed_init_parity(name, seed):
+    """same seed -> bit-identical weights as the reference constructor"""
+    from eeg_gnn_ssl_b200.model.model import DCRNNModel_nextTimePred, DCRNNModel_classification
+    meta, a = load_golden(name)
+    keys = ("num_nodes", "num_rnn_layers", "rnn_units", "input_dim", "output_dim", "max_diffusion_step",
+            "dcgru_activation", "filter_type", "dropout", "cl_decay_steps", "use_curriculum_learning")
+    args = types.SimpleNamespace(**{k: meta[k] for k in keys})
+    torch.manual_seed(seed)
+    m = DCRNNModel_nextTimePred(args) if meta["kind"] == "ssl" else DCRNNModel_classification(args, meta["classes"])
+    for n, p in m.named_parameters():
+        if n.endswith("weight"):            # biases were perturbed after construction in make_golden.py
+            assert np.array_equal(p.detach().numpy(), a["param:" + n]), n
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/pretrained"), reason="reference checkpoints not present")
+@pytest.mark.parametrize("ckpt,ft", [("pretrained_distance_graph_12s.pth.tar", "laplacian"),
+                                     ("pretrained_correlation_graph_60s.pth.tar", "dual_random_walk")])
+def test_pretrained_checkpoints_load_strict(ckpt, ft):
+    from eeg_gnn_ssl_b200.model.model import DCRNNModel_nextTimePred
+    sd = torch.load(os.path.join("/root/reference/pretrained", ckpt), map_location="cpu",
+                    weights_only=True)["model_state"]
+    m = DCRNNModel_nextTimePred(_args(filter_type=ft))
+    m.load_state_dict(sd, strict=True)
+
+
+def test_hyphenated_directory_works_as_drop_in_root():
+    """`eeg-gnn-ssl_b200/` first on sys.path makes the reference's own import lines resolve here"""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); from model.model import DCRNNModel_classification, "
+            "DCRNNModel_nextTimePred; from model.cell import DCGRUCell; print(DCGRUCell.__module__)"
+            % os.path.join(ROOT, "eeg-gnn-ssl_b200"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.strip() == "model.cell"

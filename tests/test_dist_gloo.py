@@ -1,0 +1,56 @@
+"""world_size-2 gloo test of the data-parallel plumbing (FlatGradSync): averaged shard gradients ==
+full-batch gradient, one flat buffer, parameters broadcast from rank 0."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from eeg_gnn_ssl_b200.dist import FlatGradSync, broadcast_parameters, shard_batch
+    torch.manual_seed(100 + rank)                       # different init per rank on purpose
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 1))
+    broadcast_parameters(model)
+    sync = FlatGradSync(model.parameters(), world_size=world)
+    g = torch.Generator().manual_seed(0)
+    x, y = torch.randn(8, 6, generator=g), torch.randn(8, 1, generator=g)
+    sync.zero()
+    xs, ys = shard_batch(x, rank, world), shard_batch(y, rank, world)
+    torch.nn.functional.mse_loss(model(xs), ys).backward()
+    assert all(p.grad.data_ptr() >= sync.flat.data_ptr() for p in model.parameters())   # still views
+    sync.sync()
+    flat_dp = sync.flat.clone()
+    # single-process reference on the full batch with rank 0's weights
+    sync.zero()                                          # (zero_grad() would drop the views)
+    torch.nn.functional.mse_loss(model(x), y).backward()
+    q.put((rank, float((flat_dp - sync.flat).abs().max()), [p.detach().clone() for p in model.parameters()]))
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_matches_full_batch():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, err, _ in res:
+        assert err < 1e-6
+    for a, b in zip(res[0][2], res[1][2]):
+        assert torch.equal(a, b)                         # broadcast made the replicas identical

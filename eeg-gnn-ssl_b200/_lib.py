@@ -10,6 +10,7 @@ SYMBOLS = [
     "dcgru_version", "dcgru_last_error", "dcgru_graph_poly", "dcgru_corr_supports",
     "dcgru_encoder_layer_fwd", "dcgru_encoder_layer_bwd_workspace", "dcgru_encoder_layer_bwd",
     "dcgru_decoder_fwd_workspace", "dcgru_decoder_fwd", "dcgru_decoder_bwd_workspace", "dcgru_decoder_bwd",
+    "dcgru_timing_enable", "dcgru_timing_collect", "dcgru_tc_selftest",
 ]
 
 MAX_LAYERS = 4
@@ -59,6 +60,9 @@ def lib():
     L.dcgru_decoder_bwd_workspace.restype = sz
     L.dcgru_decoder_bwd.argtypes = [pd, i32, i32, i32, vp, u64, vp, vp, pp, vp, vp, vp, vp, vp, vp, vp, pg,
                                     vp, vp, vp, sz, vp]
+    L.dcgru_tc_selftest.argtypes = [vp, vp, vp, i32, i32, vp]
+    L.dcgru_timing_enable.argtypes = [C.c_int]
+    L.dcgru_timing_collect.argtypes = [C.c_char_p, sz]
     for name in SYMBOLS:
         if name not in ("dcgru_last_error", "dcgru_encoder_layer_bwd_workspace",
                         "dcgru_decoder_fwd_workspace", "dcgru_decoder_bwd_workspace"):

@@ -2,6 +2,7 @@
 // tiling plans, workspace carving and kernel launches.  No device memory is allocated here.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -172,6 +173,64 @@ int dw_nsplit(int B, int njobs) {
     return ngroups < want ? ngroups : want;
 }
 
+// ---- tensor-core weight-gradient plan (dw_tc.cu) ------------------------------------------------------
+bool tc_enabled() {
+    const char* e = getenv("DCGRU_DISABLE_TC");      // read per call so tests can compare both paths
+    return !(e && e[0] == '1');
+}
+// jobs for dw_tc_kernel: 128-row slabs of W rows; DwJob.nz = rows in the slab, DwJob.z0 = carries the db row
+int build_cell_jobs_tc(int fin, int H, int M, DwJob* jobs) {
+    int n = 0;
+    auto add = [&](int type, int kbegin, int kend, int o_begin, int o_len) {
+        int ot = otile(o_len);
+        for (int o0 = 0; o0 < o_len; o0 += ot) {
+            bool have_db = (type != 0);
+            for (int k0 = kbegin; k0 < kend; k0 += 128) {
+                DwJob j;
+                j.type = type; j.kk0 = k0; j.nz = (kend - k0 < 128) ? kend - k0 : 128; j.o0 = o_begin + o0; j.nco = ot;
+                j.z0 = 0;
+                if (!have_db && j.nz < 128) { j.z0 = 1; have_db = true; }
+                if (n < DW_MAXJOBS) jobs[n] = j;
+                ++n;
+            }
+            if (!have_db) {                  // no slab has a spare row: an empty slab that only carries db
+                DwJob j;
+                j.type = 0; j.kk0 = 0; j.nz = 0; j.o0 = o_begin + o0; j.nco = ot; j.z0 = 1;
+                if (n < DW_MAXJOBS) jobs[n] = j;
+                ++n;
+            }
+        }
+    };
+    add(0, 0, fin * M, 0, 3 * H);
+    add(1, fin * M, (fin + H) * M, 0, 2 * H);
+    add(2, fin * M, (fin + H) * M, 2 * H, H);
+    return n;
+}
+struct CellDwPlan { bool tc; int njobs, nsplit, nco_max; };
+CellDwPlan plan_cell_dw(int fin, int H, int M, int B, int T, DwJob* jobs) {
+    DwJob tmp[DW_MAXJOBS];
+    if (!jobs) jobs = tmp;
+    CellDwPlan pl;
+    const DevInfo& di = devinfo();
+    pl.nco_max = otile(3 * H);
+    pl.tc = tc_enabled() && M >= 3 && (H == 64 || H == 128) && di.sms > 0 &&
+            dw_tc_smem_bytes(M, pl.nco_max) + 64 <= di.smem;
+    if (pl.tc) {
+        pl.njobs = build_cell_jobs_tc(fin, H, M, jobs);
+        if (pl.njobs > DW_MAXJOBS) pl.tc = false;
+    }
+    if (pl.tc) {
+        long nchunk = ((long)T * B + 1) / 2;
+        long want = (2L * di.sms + pl.njobs - 1) / pl.njobs;
+        if (want < 1) want = 1;
+        pl.nsplit = (int)(nchunk < want ? nchunk : want);
+    } else {
+        pl.njobs = build_cell_jobs(fin, H, M, jobs);
+        pl.nsplit = dw_nsplit(B, pl.njobs);
+    }
+    return pl;
+}
+
 size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct Carver {
@@ -189,6 +248,15 @@ struct Carver {
 extern "C" {
 
 int dcgru_version(void) { return 100; }
+
+int dcgru_tc_selftest(const float* A, const float* B, float* C, int32_t N, int32_t K, void* stream) {
+    if (!A || !B || !C) return fail("null pointer");
+    if (K < 32 || K % 32) return fail("K=%d must be a positive multiple of 32", K);
+    if (N != 64 && N != 128 && N != 192 && N != 256) return fail("N=%d unsupported", N);
+    cudaStream_t st = (cudaStream_t)stream;
+    LAUNCH("tc_selftest", launch_tc_selftest(A, B, C, N, K, st));
+    return 0;
+}
 
 int dcgru_timing_enable(int on) {
     std::lock_guard<std::mutex> lk(g_tmu);
@@ -279,9 +347,8 @@ int dcgru_encoder_layer_fwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
 static size_t enc_bwd_ws(const dcgru_cell_desc* d, int B, int T, bool carve, void* ws, float** WgT, float** WcT,
                          float** dA, float** part, float** partb, int* nsplit, int* njobs, DwJob* jobs) {
     const int H = d->hid_dim, M = Mof(d), CM = (d->input_dim + H) * M;
-    DwJob tmp[DW_MAXJOBS];
-    int nj = build_cell_jobs(d->input_dim, H, M, jobs ? jobs : tmp);
-    int ns = dw_nsplit(B, nj);
+    CellDwPlan dp = plan_cell_dw(d->input_dim, H, M, B, T, jobs);
+    int nj = dp.njobs, ns = dp.nsplit;
     Carver c(ws, 0);
     float* a = c.take((size_t)2 * H * CM);
     float* b = c.take((size_t)H * CM);
@@ -333,7 +400,10 @@ int dcgru_encoder_layer_bwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
     q.layer = 0; q.ncell = 1; q.fin = fin; q.Fo = 0;
     q.P = P; q.x = x; q.xs_t = x_stride_t; q.xs_b = x_stride_b; q.h0 = h0; q.hseq = h_seq; q.ruc = ruc; q.dA = dA;
     q.part = part; q.partb = partb;
-    LAUNCH("dw", launch_dw(q, njobs, otile(3 * H), st));
+    if (plan_cell_dw(fin, H, M, batch, seq_len, nullptr).tc)
+        LAUNCH("dw_tc", launch_dw_tc(q, njobs, otile(3 * H), st));
+    else
+        LAUNCH("dw", launch_dw(q, njobs, otile(3 * H), st));
     LAUNCH("reduce", launch_reduce_cell(part, partb, nsplit, CM, H, g->dWg, g->dbg, g->dWc, g->dbc, st));
     return 0;
 }
@@ -386,14 +456,15 @@ struct DecWs {
     float *WgT[DCGRU_MAX_LAYERS], *WcT[DCGRU_MAX_LAYERS];
     float *dA, *dY, *scratch, *part0, *partb0, *part1, *partb1, *partp, *partpb;
     int ns0, nj0, ns1, nj1, nsp, njp;
+    bool tc0, tc1;
     size_t bytes;
 };
 static void dec_bwd_ws(const dcgru_cell_desc* d, int L, int B, int T, void* ws, DecWs* o) {
     const int H = d->hid_dim, M = Mof(d), Fo = d->input_dim, N = d->num_nodes;
     const int CM0 = (Fo + H) * M, CM1 = 2 * H * M;
     DwJob tmp[DW_MAXJOBS];
-    o->nj0 = build_cell_jobs(Fo, H, M, tmp);  o->ns0 = dw_nsplit(B, o->nj0);
-    o->nj1 = build_cell_jobs(H, H, M, tmp);   o->ns1 = dw_nsplit(B, o->nj1);
+    { CellDwPlan a = plan_cell_dw(Fo, H, M, B, T, tmp); o->nj0 = a.njobs; o->ns0 = a.nsplit; o->tc0 = a.tc; }
+    { CellDwPlan a = plan_cell_dw(H, H, M, B, T, tmp);  o->nj1 = a.njobs; o->ns1 = a.nsplit; o->tc1 = a.tc; }
     o->njp = build_proj_jobs(Fo, H, tmp);     o->nsp = dw_nsplit(B, o->njp);
     Carver c(ws, 0);
     for (int l = 0; l < L; ++l) {
@@ -473,17 +544,19 @@ int dcgru_decoder_bwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T,
     q.teacher_mask = teacher_mask; q.dY = o.dY; q.dropmask = drop_mask;
     // cell 0
     q.layer = 0; q.fin = Fo; q.nsplit = o.ns0; q.part = o.part0; q.partb = o.partb0;
-    build_cell_jobs(Fo, H, M, q.jobs);
-    LAUNCH("dw", launch_dw(q, o.nj0, otile(3 * H), st));
+    plan_cell_dw(Fo, H, M, B, T, q.jobs);
+    if (o.tc0) LAUNCH("dw_tc", launch_dw_tc(q, o.nj0, otile(3 * H), st));
+    else LAUNCH("dw", launch_dw(q, o.nj0, otile(3 * H), st));
     LAUNCH("reduce", launch_reduce_cell(o.part0, o.partb0, o.ns0, (Fo + H) * M, H, g[0].dWg, g[0].dbg, g[0].dWc, g[0].dbc, st));
     // cells >= 1
-    build_cell_jobs(H, H, M, q.jobs);
+    plan_cell_dw(H, H, M, B, T, q.jobs);
     const size_t psz = (size_t)2 * H * M * 3 * H;
     for (int l = 1; l < L; ++l) {
         q.layer = l; q.fin = H; q.nsplit = o.ns1;
         q.part = o.part1 + (size_t)(l - 1) * o.ns1 * psz;
         q.partb = o.partb1 + (size_t)(l - 1) * o.ns1 * 3 * H;
-        LAUNCH("dw", launch_dw(q, o.nj1, otile(3 * H), st));
+        if (o.tc1) LAUNCH("dw_tc", launch_dw_tc(q, o.nj1, otile(3 * H), st));
+        else LAUNCH("dw", launch_dw(q, o.nj1, otile(3 * H), st));
         if (!tied)
             LAUNCH("reduce", launch_reduce_cell(q.part, q.partb, o.ns1, 2 * H * M, H, g[l].dWg, g[l].dbg, g[l].dWc, g[l].dbc, st));
     }

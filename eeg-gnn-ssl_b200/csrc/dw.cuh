@@ -49,4 +49,7 @@ cudaError_t launch_graph_poly(int B, int N, int K, int S, const float* const* su
 cudaError_t launch_corr_supports(int B, int T, int N, int F, const float* clip, long long sb, long long st_,
                                  float scale, float shift, int top_k, float* adj, float* s0, float* s1,
                                  cudaStream_t st);
+int dw_tc_smem_bytes(int M, int nco_max);
+cudaError_t launch_dw_tc(const DwParams& p, int njobs, int nco_max, cudaStream_t st);
+cudaError_t launch_tc_selftest(const float* A, const float* B, float* C, int N, int K, cudaStream_t st);
 }  // namespace dcgru

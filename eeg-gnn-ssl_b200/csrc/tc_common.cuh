@@ -1,0 +1,140 @@
+// tcgen05 / TMEM / mbarrier building blocks (sm_100a) shared by the tensor-core kernels.
+//
+// Arithmetic: "3xTF32" -- every fp32 operand x is split into hi = x with the low 13 mantissa bits
+// cleared (exactly representable in TF32) and lo = x - hi (exact in fp32); a product a*b is issued as
+// three kind::tf32 MMAs  a_hi*b_hi + a_hi*b_lo + a_lo*b_hi  accumulating in fp32 in TMEM.  The dropped
+// a_lo*b_lo term and the TF32 rounding of the lo parts are ~2^-21 relative, i.e. fp32-level accuracy,
+// which is what the 1e-4 parity bar against the fp32 reference needs over 60 recurrent steps.
+//
+// Operand tiles in shared memory use the canonical K-major no-swizzle UMMA layout with the K-groups
+// outermost:   element (row r, k)  ->  tile[(k/4)][r] (a float4 holding k%4 = 0..3)
+//   core matrix = 8 rows x 16 B contiguous,  SBO (next 8 rows) = 128 B,  LBO (next 4 k) = rows*16 B
+// so a thread that owns 4 consecutive k of one row writes one 16-byte word and consecutive rows are
+// consecutive words (conflict-free), and a sub-range of rows is just an address offset.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dcgru {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// ---- descriptors (cute/arch/mma_sm100_desc.hpp bit layout) -----------------------------------------
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;                 // descriptor version 1 (Blackwell); layout_type 0 = no swizzle
+    return d;
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+                 ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- TMEM ---------------------------------------------------------------------------------------------
+// one full warp; ncols power of two >= 32; the base address is written to *slot (shared memory)
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
+                 ::"r"(smem_u32(slot)), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// 32 lanes x 32 consecutive columns: thread i of the warp gets lane (base_lane + i), v[j] = column j
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+// ---- mbarrier -----------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+// bounded spin: a lost arrival traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t it = 0; it < (1u << 26); ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) return;
+    }
+    asm volatile("trap;\n");
+}
+
+// ---- 3xTF32 split ---------------------------------------------------------------------------------------
+// round-to-nearest on both parts keeps the representation error unbiased (a truncating split showed a
+// systematic ~3e-6 relative error at K=320 on hardware; with rounding it is random-walk ~1e-7)
+__device__ __forceinline__ float rna_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = rna_tf32(x);
+    lo = rna_tf32(x - hi);
+}
+__device__ __forceinline__ void split4(const float4& v, float4& hi, float4& lo) {
+    split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);
+    split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+}
+
+// D[128 x N] (+)= A[128 x 8*ksteps] * B[N x 8*ksteps]^T in 3xTF32.  a_hi/a_lo/b_hi/b_lo are shared-memory
+// byte addresses of K-group-major tiles with a_rows / b_rows rows.  One thread calls this.
+__device__ __forceinline__ void issue_3xtf32(uint32_t tmem_d, uint32_t a_hi, uint32_t a_lo, int a_rows,
+                                             uint32_t b_hi, uint32_t b_lo, int b_rows, int ksteps,
+                                             uint32_t idesc, bool accumulate_first) {
+    const uint32_t a_lbo = a_rows * 16, b_lbo = b_rows * 16;
+    uint32_t acc = accumulate_first ? 1u : 0u;
+    for (int k = 0; k < ksteps; ++k) {
+        const uint32_t ao = 2 * k * a_lbo, bo = 2 * k * b_lbo;
+        uint64_t ah = make_smem_desc(a_hi + ao, a_lbo, 128), al = make_smem_desc(a_lo + ao, a_lbo, 128);
+        uint64_t bh = make_smem_desc(b_hi + bo, b_lbo, 128), bl = make_smem_desc(b_lo + bo, b_lbo, 128);
+        umma_tf32(tmem_d, al, bh, idesc, acc);      // small terms first
+        umma_tf32(tmem_d, ah, bl, idesc, 1u);
+        umma_tf32(tmem_d, ah, bh, idesc, 1u);
+        acc = 1u;
+    }
+}
+
+}  // namespace tc
+}  // namespace dcgru

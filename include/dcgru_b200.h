@@ -60,6 +60,11 @@ const char *dcgru_last_error(void);
 int dcgru_timing_enable(int on);
 int dcgru_timing_collect(char *buf, size_t cap);
 
+/* Hardware self-test of the tcgen05/TMEM plumbing the tensor-core kernels are built from:
+ * C[128 x N] = A[128 x K] * B[N x K]^T in 3xTF32 (fp32-level accuracy); A, B, C device pointers,
+ * row-major, K % 32 == 0, N in {64, 128, 192, 256}.                                              */
+int dcgru_tc_selftest(const float *A, const float *B, float *C, int32_t N, int32_t K, void *stream);
+
 /* ---- graph -> diffusion polynomials -------------------------------------------------------
  * Replaces the hop recurrence of DiffusionGraphConv.forward (model/cell.py:76-93): since
  * diffusion is linear, term_m = P_m Z with per-sample N x N matrices P_m (the

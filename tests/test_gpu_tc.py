@@ -1,0 +1,63 @@
+"""Tensor-core (tcgen05) path: hardware self-test of the UMMA plumbing and parity of the TC kernels."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("N,K", [(64, 32), (128, 64), (192, 320), (256, 96)])
+def test_tcgen05_3xtf32_gemm(dev, N, K):
+    from eeg_gnn_ssl_b200 import _lib
+    g = torch.Generator().manual_seed(N + K)
+    A = torch.randn(128, K, generator=g)
+    B = torch.randn(N, K, generator=g)
+    Ad, Bd = A.to(dev), B.to(dev)
+    Cd = torch.full((128, N), float("nan"), device=dev)
+    L = _lib.lib()
+    _lib.check(L.dcgru_tc_selftest(C.c_void_p(Ad.data_ptr()), C.c_void_p(Bd.data_ptr()), C.c_void_p(Cd.data_ptr()),
+                                   N, K, C.c_void_p(torch.cuda.current_stream().cuda_stream)), "tc_selftest")
+    torch.cuda.synchronize()
+    ref = A.double() @ B.double().t()
+    got = Cd.cpu().double()
+    err = float((got - ref).abs().max() / ref.abs().max())
+    tf32 = float(((A.to(dev) @ B.to(dev).t()).cpu().double() - ref).abs().max() / ref.abs().max())
+    print(f"N={N} K={K}: 3xTF32 rel err {err:.3e} (fp32 matmul on device: {tf32:.3e})")
+    assert np.isfinite(got.numpy()).all()
+    assert err < 2e-6, err
+
+
+def _grads(dev, B, T, H, K, S, L, seed=0):
+    from eeg_gnn_ssl_b200.model.model import DCRNNEncoder
+    g = torch.Generator().manual_seed(seed)
+    ft = "dual_random_walk" if S == 2 else "laplacian"
+    torch.manual_seed(seed)
+    enc = DCRNNEncoder(100, K, H, 19, L, dcgru_activation="tanh", filter_type=ft).to(dev)
+    x = torch.randn(T, B, 19, 100, generator=g).to(dev)
+    sup = [(torch.softmax(torch.randn(B, 19, 19, generator=g), -1)).to(dev) for _ in range(S)]
+    h0 = (0.3 * torch.randn(L, B, 19 * H, generator=g)).to(dev)
+    w = torch.randn(T, B, 19 * H, generator=g).to(dev)
+    _, top = enc(x, h0, sup)
+    (top * w).sum().backward()
+    return {n: p.grad.detach().cpu().double() for n, p in enc.named_parameters()}
+
+
+@pytest.mark.parametrize("B,T,H,K,S,L", [(37, 5, 64, 2, 1, 2), (11, 3, 64, 2, 2, 2), (9, 2, 128, 3, 2, 2)])
+def test_tc_weight_gradients_match_simt(dev, monkeypatch, B, T, H, K, S, L):
+    """dw_tc_kernel (tcgen05, 3xTF32) against the fp32 FMA kernel on the same saved activations"""
+    monkeypatch.setenv("DCGRU_DISABLE_TC", "1")
+    ref = _grads(dev, B, T, H, K, S, L)
+    monkeypatch.setenv("DCGRU_DISABLE_TC", "0")
+    got = _grads(dev, B, T, H, K, S, L)
+    for n in ref:
+        e = float((got[n] - ref[n]).abs().max() / ref[n].abs().max())
+        assert e < 1e-5, (n, e)

@@ -214,14 +214,14 @@ CellDwPlan plan_cell_dw(int fin, int H, int M, int B, int T, DwJob* jobs) {
     const DevInfo& di = devinfo();
     pl.nco_max = otile(3 * H);
     pl.tc = tc_enabled() && M >= 3 && (H == 64 || H == 128) && di.sms > 0 &&
-            dw_tc_smem_bytes(M, pl.nco_max) + 64 <= di.smem;
+            dw_tc_smem_bytes(M, pl.nco_max) + 1088 <= di.smem;   // + static smem (mbarriers, 1 KB alignment)
     if (pl.tc) {
         pl.njobs = build_cell_jobs_tc(fin, H, M, jobs);
         if (pl.njobs > DW_MAXJOBS) pl.tc = false;
     }
     if (pl.tc) {
         long nchunk = ((long)T * B + 1) / 2;
-        long want = (2L * di.sms + pl.njobs - 1) / pl.njobs;
+        long want = di.sms / pl.njobs;           // one resident CTA per SM: exactly one wave
         if (want < 1) want = 1;
         pl.nsplit = (int)(nchunk < want ? nchunk : want);
     } else {
@@ -319,9 +319,15 @@ int dcgru_corr_supports(int32_t batch, int32_t seq_len, int32_t num_nodes, int32
     return 0;
 }
 
+size_t dcgru_encoder_layer_fwd_workspace(const dcgru_cell_desc* d, int32_t batch, int32_t seq_len) {
+    if (check_desc(d) || batch < 1 || seq_len < 1) return 0;
+    return align_up(seq_fwd_tc_wimg_bytes(d->input_dim)) + 256;
+}
+
 int dcgru_encoder_layer_fwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq_len, const float* x,
                             int64_t x_stride_t, int64_t x_stride_b, const float* h0, const float* P,
-                            const dcgru_cell_params* w, float* h_seq, float* ruc, void* stream) {
+                            const dcgru_cell_params* w, float* h_seq, float* ruc, void* workspace,
+                            size_t workspace_bytes, void* stream) {
     if (check_desc(d)) return 1;
     if (batch < 1 || seq_len < 1) return fail("empty batch/sequence");
     if (!x || !h0 || !w || !h_seq || !w->Wg || !w->bg || !w->Wc || !w->bc) return fail("null pointer");
@@ -330,6 +336,16 @@ int dcgru_encoder_layer_fwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
     if (!aligned16(x) || !aligned16(h0) || !aligned16(h_seq) || !aligned16(w->Wg) || !aligned16(w->Wc) ||
         (x_stride_t % 4) || (x_stride_b % 4))
         return fail("x/h0/h_seq/weights must be 16-byte aligned with strides multiple of 4 floats");
+    cudaStream_t st = (cudaStream_t)stream;
+    // tensor-core path (tcgen05, 3xTF32): K=2 / one support / 64 units -- the reference's default cell
+    if (tc_enabled() && ruc && workspace && aligned16(workspace) &&
+        workspace_bytes >= seq_fwd_tc_wimg_bytes(d->input_dim) &&
+        seq_fwd_tc_supported(d->num_nodes, d->input_dim, d->hid_dim, M, devinfo().smem)) {
+        LAUNCH("seq_fwd_tc", launch_seq_fwd_tc(batch, seq_len, d->num_nodes, d->input_dim, d->activation, x,
+                                               x_stride_t, x_stride_b, h0, P, w->Wg, w->bg, w->Wc, w->bc,
+                                               (float*)workspace, h_seq, ruc, st));
+        return 0;
+    }
     FwdPlan pl;
     if (!plan_fwd(d->hid_dim, d->input_dim + d->hid_dim, M, batch, 0, &pl))
         return fail("no tiling fits shared memory (input_dim=%d hid=%d M=%d)", d->input_dim, d->hid_dim, M);
@@ -339,13 +355,13 @@ int dcgru_encoder_layer_fwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
     p.ncell = 1; p.KC = pl.KC; p.mode = 0;
     p.cell[0] = CellW{w->Wg, w->bg, w->Wc, w->bc, d->input_dim};
     p.P = P; p.x = x; p.xs_t = x_stride_t; p.xs_b = x_stride_b; p.h0 = h0; p.hseq = h_seq; p.ruc = ruc;
-    cudaStream_t st = (cudaStream_t)stream;
     LAUNCH("seq_fwd", launch_seq_fwd(p, pl.SB, pl.smem, st));
     return 0;
 }
 
 static size_t enc_bwd_ws(const dcgru_cell_desc* d, int B, int T, bool carve, void* ws, float** WgT, float** WcT,
-                         float** dA, float** part, float** partb, int* nsplit, int* njobs, DwJob* jobs) {
+                         float** dA, float** part, float** partb, int* nsplit, int* njobs, DwJob* jobs,
+                         float** ptbuf = nullptr) {
     const int H = d->hid_dim, M = Mof(d), CM = (d->input_dim + H) * M;
     CellDwPlan dp = plan_cell_dw(d->input_dim, H, M, B, T, jobs);
     int nj = dp.njobs, ns = dp.nsplit;
@@ -355,7 +371,8 @@ static size_t enc_bwd_ws(const dcgru_cell_desc* d, int B, int T, bool carve, voi
     float* e = c.take((size_t)T * B * d->num_nodes * 3 * H);
     float* f = c.take((size_t)ns * CM * 3 * H);
     float* g = c.take((size_t)ns * 3 * H);
-    if (carve) { *WgT = a; *WcT = b; *dA = e; *part = f; *partb = g; *nsplit = ns; *njobs = nj; }
+    float* pt = c.take(dw_tc_pt_floats(B, M));
+    if (carve) { *WgT = a; *WcT = b; *dA = e; *part = f; *partb = g; *nsplit = ns; *njobs = nj; *ptbuf = pt; }
     return c.off;
 }
 
@@ -378,11 +395,11 @@ int dcgru_encoder_layer_bwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
     if (!aligned16(workspace) || !aligned16(h_seq) || !aligned16(ruc)) return fail("unaligned pointer");
     if (dcgru_encoder_layer_bwd_workspace(d, batch, seq_len) > workspace_bytes) return fail("workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
-    float *WgT, *WcT, *dA, *part, *partb;
+    float *WgT, *WcT, *dA, *part, *partb, *ptbuf;
     int nsplit, njobs;
     DwParams q;
     memset(&q, 0, sizeof q);
-    enc_bwd_ws(d, batch, seq_len, true, workspace, &WgT, &WcT, &dA, &part, &partb, &nsplit, &njobs, q.jobs);
+    enc_bwd_ws(d, batch, seq_len, true, workspace, &WgT, &WcT, &dA, &part, &partb, &nsplit, &njobs, q.jobs, &ptbuf);
     if (njobs > DW_MAXJOBS) return fail("too many weight-gradient jobs (%d)", njobs);
     LAUNCH("transpose", launch_transpose(w->Wg, CM, 2 * H, WgT, CM, st));
     LAUNCH("transpose", launch_transpose(w->Wc, CM, H, WcT, CM, st));
@@ -400,8 +417,11 @@ int dcgru_encoder_layer_bwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
     q.layer = 0; q.ncell = 1; q.fin = fin; q.Fo = 0;
     q.P = P; q.x = x; q.xs_t = x_stride_t; q.xs_b = x_stride_b; q.h0 = h0; q.hseq = h_seq; q.ruc = ruc; q.dA = dA;
     q.part = part; q.partb = partb;
-    if (plan_cell_dw(fin, H, M, batch, seq_len, nullptr).tc)
+    if (plan_cell_dw(fin, H, M, batch, seq_len, nullptr).tc) {
+        LAUNCH("make_pt", launch_make_pt(P, batch, M, d->num_nodes, ptbuf, st));
+        q.dY = ptbuf;                             // dw_tc_kernel reads the padded P^T through this field
         LAUNCH("dw_tc", launch_dw_tc(q, njobs, otile(3 * H), st));
+    }
     else
         LAUNCH("dw", launch_dw(q, njobs, otile(3 * H), st));
     LAUNCH("reduce", launch_reduce_cell(part, partb, nsplit, CM, H, g->dWg, g->dbg, g->dWc, g->dbc, st));
@@ -454,6 +474,7 @@ int dcgru_decoder_fwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T,
 
 struct DecWs {
     float *WgT[DCGRU_MAX_LAYERS], *WcT[DCGRU_MAX_LAYERS];
+    float *ptbuf;
     float *dA, *dY, *scratch, *part0, *partb0, *part1, *partb1, *partp, *partpb;
     int ns0, nj0, ns1, nj1, nsp, njp;
     bool tc0, tc1;
@@ -481,6 +502,7 @@ static void dec_bwd_ws(const dcgru_cell_desc* d, int L, int B, int T, void* ws, 
     o->partb1 = c.take((size_t)(L > 1 ? L - 1 : 0) * o->ns1 * 3 * H);
     o->partp = c.take((size_t)o->nsp * Fo * H);
     o->partpb = c.take((size_t)o->nsp * Fo);
+    o->ptbuf = c.take(dw_tc_pt_floats(B, M));
     o->bytes = c.off;
 }
 
@@ -543,7 +565,9 @@ int dcgru_decoder_bwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T,
     q.P = P; q.h0 = h0; q.hseq = h_all; q.ruc = ruc; q.dA = o.dA; q.targets = targets; q.out = out;
     q.teacher_mask = teacher_mask; q.dY = o.dY; q.dropmask = drop_mask;
     // cell 0
+    if (o.tc0 || o.tc1) LAUNCH("make_pt", launch_make_pt(P, B, M, N, o.ptbuf, st));
     q.layer = 0; q.fin = Fo; q.nsplit = o.ns0; q.part = o.part0; q.partb = o.partb0;
+    q.dY = o.tc0 ? o.ptbuf : o.dY;
     plan_cell_dw(Fo, H, M, B, T, q.jobs);
     if (o.tc0) LAUNCH("dw_tc", launch_dw_tc(q, o.nj0, otile(3 * H), st));
     else LAUNCH("dw", launch_dw(q, o.nj0, otile(3 * H), st));
@@ -552,7 +576,7 @@ int dcgru_decoder_bwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T,
     plan_cell_dw(H, H, M, B, T, q.jobs);
     const size_t psz = (size_t)2 * H * M * 3 * H;
     for (int l = 1; l < L; ++l) {
-        q.layer = l; q.fin = H; q.nsplit = o.ns1;
+        q.layer = l; q.fin = H; q.nsplit = o.ns1; q.dY = o.tc1 ? o.ptbuf : o.dY;
         q.part = o.part1 + (size_t)(l - 1) * o.ns1 * psz;
         q.partb = o.partb1 + (size_t)(l - 1) * o.ns1 * 3 * H;
         if (o.tc1) LAUNCH("dw_tc", launch_dw_tc(q, o.nj1, otile(3 * H), st));
@@ -564,7 +588,7 @@ int dcgru_decoder_bwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T,
         LAUNCH("reduce", launch_reduce_cell(o.part1, o.partb1, (L - 1) * o.ns1, 2 * H * M, H, g[1].dWg, g[1].dbg, g[1].dWc,
                                     g[1].dbc, st));
     // Linear
-    q.layer = L - 1; q.fin = Fo; q.nsplit = o.nsp; q.part = o.partp; q.partb = o.partpb;
+    q.layer = L - 1; q.fin = Fo; q.nsplit = o.nsp; q.part = o.partp; q.partb = o.partpb; q.dY = o.dY;
     build_proj_jobs(Fo, H, q.jobs);
     LAUNCH("dw", launch_dw(q, o.njp, otile(H), st));
     LAUNCH("reduce", launch_reduce_flat(o.partp, o.nsp, (size_t)Fo * H, dproj_w, st));

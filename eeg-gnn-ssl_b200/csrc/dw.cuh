@@ -50,6 +50,13 @@ cudaError_t launch_corr_supports(int B, int T, int N, int F, const float* clip, 
                                  float scale, float shift, int top_k, float* adj, float* s0, float* s1,
                                  cudaStream_t st);
 int dw_tc_smem_bytes(int M, int nco_max);
+size_t dw_tc_pt_floats(int B, int M);
+cudaError_t launch_make_pt(const float* P, int B, int M, int N, float* PT, cudaStream_t st);
 cudaError_t launch_dw_tc(const DwParams& p, int njobs, int nco_max, cudaStream_t st);
+size_t seq_fwd_tc_wimg_bytes(int fin);
+bool seq_fwd_tc_supported(int N, int fin, int H, int M, int smem_limit);
+cudaError_t launch_seq_fwd_tc(int B, int T, int N, int fin, int act, const float* x, long long xs_t, long long xs_b,
+                              const float* h0, const float* P, const float* Wg, const float* bg, const float* Wc,
+                              const float* bc, float* wimg, float* hseq, float* ruc, cudaStream_t st);
 cudaError_t launch_tc_selftest(const float* A, const float* B, float* C, int N, int K, cudaStream_t st);
 }  // namespace dcgru

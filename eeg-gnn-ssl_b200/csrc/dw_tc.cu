@@ -7,10 +7,13 @@
 //   B[n = o][k = row]   = dA^T         : loaded row-major from HBM, transposed in registers
 // Both are written hi/lo-split straight into K-group-major UMMA tiles (tc_common.cuh), 40 K-rows
 // (= 2 sample steps x 20 padded nodes = 5 MMA k-steps) per chunk, double buffered: while the tensor
-// core consumes chunk i the threads produce chunk i+1.  The accumulator (128 x N fp32) lives in
-// TMEM for the CTA's whole row range and is written once as a split-K partial; dw.cu's
-// reduce_cell_kernel sums the partials in fixed order.  The bias gradient rides along as an extra
-// all-ones A row in a slab that has a spare row (db[o] = sum_rows 1 * dA[row][o]).
+// core consumes chunk i the 512 threads produce chunk i+1; the global loads of chunk i+1 are issued
+// into registers before the shared-memory work of chunk i so their latency is hidden.
+// The accumulator (128 x N fp32) lives in TMEM; because the tensor core truncates when it adds into
+// the fp32 accumulator, it is flushed into the CTA's split-K partial every FLUSH chunks so that the
+// accumulation bias stays far below the 1e-4 parity budget.  dw.cu's reduce_cell_kernel sums the
+// partials in fixed order.  The bias gradient rides along as an extra all-ones A row in a slab that
+// has a spare row (db[o] = sum_rows 1 * dA[row][o]).
 #include "common.cuh"
 #include "dw.cuh"
 #include "tc_common.cuh"
@@ -18,44 +21,93 @@
 namespace dcgru {
 using namespace tc;
 
+constexpr int TNT = 512;                // threads
 constexpr int TKR = 40;                 // K rows per chunk
 constexpr int TKG = TKR / 4;            // K groups per chunk
-constexpr int TZC = 48;                 // max source columns a 128-row slab can touch (+ slack)
+constexpr int TFLUSH = 16;              // chunks between TMEM -> partial flushes (640 K rows)
+constexpr int PTS = NP * NP;            // one padded transposed polynomial
 
 struct DwTcSmem {
-    int a_bytes, b_bytes, stage_bytes, zc_off, pt_off, total;
+    int a_bytes, b_bytes, stage_bytes, zc_off, pt_off, total, zld;
 };
 __host__ __device__ inline DwTcSmem dwtc_smem(int M, int nco) {
     DwTcSmem s;
     s.a_bytes = TKG * 128 * 16;                     // one of hi / lo
     s.b_bytes = TKG * nco * 16;
     s.stage_bytes = 2 * s.a_bytes + 2 * s.b_bytes;
+    s.zld = ((128 / M + 2) + 3) & ~3;               // source columns a 128-row slab can touch
     s.zc_off = 2 * s.stage_bytes;
-    s.pt_off = s.zc_off + 2 * NP * TZC * 4;
-    s.total = s.pt_off + 2 * (M - 1) * NP * NP * 4;
+    s.pt_off = s.zc_off + 2 * NP * s.zld * 4;
+    s.total = s.pt_off + 2 * (M - 1) * PTS * 4;
     return s;
 }
 
-__global__ void __launch_bounds__(NT, 1) dw_tc_kernel(const DwParams p) {
+// PT[b][m1][j][n] = P[b][m1][n][j], zero padded to NP x NP (contiguous per sample -> float4 copies)
+__global__ void make_pt_kernel(const float* P, int B, int M1, int N, float* PT) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)B * M1 * PTS;
+    if (i >= total) return;
+    int n = (int)(i % NP), j = (int)((i / NP) % NP);
+    size_t bm = i / PTS;
+    PT[i] = (n < N && j < N) ? P[(bm * N + n) * N + j] : 0.f;
+}
+
+struct SrcOne {             // where one sample step of a chunk lives (all scalars: stays in registers)
+    const float* zsrc;      // base pointer of the Z source rows (nullptr = zeros)
+    const float* rsrc;      // r gate rows (type 2)
+    const float* dA;        // dA rows
+    const float* pt;        // padded P^T of the sample
+    bool valid;
+};
+
+// sample step q = t*B + b (32-bit arithmetic: T*B < 2^31)
+__device__ __forceinline__ SrcOne sample_source(const DwParams& p, const DwJob& job, unsigned q) {
+    const int N = p.N, H = p.H, B = p.B;
+    const size_t NH = (size_t)N * H;
+    SrcOne o;
+    o.valid = q < (unsigned)p.T * (unsigned)B;
+    const unsigned tq = o.valid ? q / (unsigned)B : 0u;
+    const int t = (int)tq, b = o.valid ? (int)(q - tq * (unsigned)B) : 0;
+    o.pt = p.dY + (size_t)b * (p.M - 1) * PTS;               // dY field carries the PT buffer for this kernel
+    const size_t cs = (p.mode == 0) ? (size_t)t * B * NH * 3 : ((size_t)t * p.ncell + p.layer) * B * NH * 3;
+    o.dA = p.dA + cs + (size_t)b * N * 3 * H;
+    o.rsrc = p.ruc + cs + (size_t)b * N * 3 * H;
+    const float* z = nullptr;
+    if (job.type == 0) {
+        if (p.mode == 0) z = p.x + (size_t)t * p.xs_t + (size_t)b * p.xs_b;
+        else if (p.layer == 0) {
+            const size_t nfo = (size_t)N * p.Fo;
+            if (t > 0) z = (((p.teacher_mask >> (t - 1)) & 1ull) ? p.targets : p.out) + ((size_t)(t - 1) * B + b) * nfo;
+        } else z = p.hseq + (((size_t)t * p.ncell + (p.layer - 1)) * B + b) * NH;
+    } else {
+        if (p.mode == 0) z = (t == 0) ? p.h0 + (size_t)b * NH : p.hseq + ((size_t)(t - 1) * B + b) * NH;
+        else z = (t == 0) ? p.h0 + ((size_t)p.layer * B + b) * NH
+                          : p.hseq + (((size_t)(t - 1) * p.ncell + p.layer) * B + b) * NH;
+    }
+    o.zsrc = o.valid ? z : nullptr;
+    return o;
+}
+
+__global__ void __launch_bounds__(TNT, 1) dw_tc_kernel(const DwParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t mbar[2];
     __shared__ uint32_t tmem_slot;
     const DwJob job = p.jobs[blockIdx.x];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int N = p.N, H = p.H, M = p.M, M1 = M - 1, B = p.B, H3 = 3 * H;
+    const int N = p.N, H = p.H, M = p.M, M1 = M - 1, H3 = 3 * H;
     const int nco = job.nco, kk0 = job.kk0, nkk = job.nz;          // nz field = rows of this slab
     const DwTcSmem L = dwtc_smem(M, nco);
-    float* Zc = reinterpret_cast<float*>(smem + L.zc_off);          // [2][NP][TZC]
+    const int ZLD = L.zld;
+    float* Zc = reinterpret_cast<float*>(smem + L.zc_off);          // [2][NP][ZLD]
     float* PT = reinterpret_cast<float*>(smem + L.pt_off);          // [2][M1][NP(j)][NP(n)]
-    // source columns this slab needs: absolute z columns c_lo..c_hi of [x | h]
-    const int c_lo = kk0 / M, c_hi = (kk0 + nkk - 1) / M;
+    const int c_lo = kk0 / M, c_hi = (kk0 + nkk - 1) / M;           // absolute columns of [x | h]
     const int ncz = (nkk > 0) ? (c_hi - c_lo + 1) : 0;
-    const int zoff = (job.type == 0) ? 0 : p.fin;                    // h columns start after the x columns
+    const int zoff = (job.type == 0) ? 0 : p.fin;
     const bool ones_row = (job.z0 != 0);                             // z0 field = "carry the db row" flag
 
     if (warp == 0) tmem_alloc<256>(&tmem_slot);
     if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_fence_init(); }
-    for (int idx = tid; idx < 2 * L.stage_bytes / 16; idx += NT)
+    for (int idx = tid; idx < 2 * L.stage_bytes / 16; idx += TNT)
         reinterpret_cast<float4*>(smem)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     tc_fence_before();
     __syncthreads();
@@ -63,10 +115,135 @@ __global__ void __launch_bounds__(NT, 1) dw_tc_kernel(const DwParams p) {
     const uint32_t taddr = tmem_slot;
     const uint32_t idesc = make_idesc_tf32(128, nco);
 
-    const size_t NH = (size_t)N * H;
-    const long total_q = (long)p.T * B;                              // sample steps
-    const long nchunk = (total_q + 1) / 2;
-    int it = 0;
+    // ---- per-thread task table (identical for every chunk) ------------------------------------------------
+    // A: (sample, source column, node quad)
+    const int a_cnt = 2 * ncz * 5;
+    int a_s = 0, a_q5 = 0, a_ccl = 0;
+    if (tid < a_cnt) { a_ccl = tid % ncz; int t1 = tid / ncz; a_q5 = t1 % 5; a_s = t1 / 5; }
+    // B: (K group, output column): 4 rows of one dA column -> one float4 of the tile; consecutive lanes own
+    // consecutive columns, so both the global loads and the shared stores are contiguous
+    constexpr int BS = 4;                                             // TKG*192/512 rounded up
+    int b_off[BS], b_src[BS];                                         // tile slot kg*nco + o (or -1) / dA offset, s in bit 30
+    unsigned b_nmask = 0;                                             // 4 node-valid bits per slot
+#pragma unroll
+    for (int k = 0; k < BS; ++k) {
+        int idx = tid + k * TNT;
+        b_off[k] = -1; b_src[k] = 0;
+        if (idx < TKG * nco) {
+            const int kg = idx / nco, o = idx - kg * nco;
+            const int s = kg >= 5, q5 = kg - 5 * s;
+            b_off[k] = idx;
+            b_src[k] = (s << 30) | ((4 * q5) * H3 + job.o0 + o);
+            for (int i = 0; i < 4; ++i)
+                if (4 * q5 + i < N) b_nmask |= 1u << (4 * k + i);
+        }
+    }
+    // Z: up to 4 source elements per thread
+    constexpr int ZS = 4;
+    int z_sm[ZS], z_src[ZS], z_r[ZS];                                 // smem offset / (node*stride + col), s in bit 30 / r-gate offset
+    const long long zstride = (job.type == 0) ? p.fin : H;
+#pragma unroll
+    for (int k = 0; k < ZS; ++k) {
+        int idx = tid + k * TNT;
+        z_sm[k] = -1; z_src[k] = 0; z_r[k] = 0;
+        if (idx < 2 * NP * ncz) {
+            int ccl = idx % ncz, j = (idx / ncz) % NP, s = idx / (ncz * NP);
+            z_sm[k] = (s * NP + j) * ZLD + ccl;
+            z_src[k] = (j < N) ? ((s << 30) | (int)(j * zstride + (c_lo + ccl - zoff))) : -1;
+            z_r[k] = j * 3 * H + (c_lo + ccl - zoff);
+        }
+    }
+    // P^T: float4 slots
+    constexpr int PS = 3;
+    const int pt_f4 = 2 * M1 * PTS / 4;
+
+    float4 breg[BS];
+    float zreg[ZS], rreg[ZS];
+    float4 preg[PS];
+    bool cur_v0 = false, cur_v1 = false;       // validity of the two sample steps held in the registers
+    const int pt_half = M1 * PTS / 4;          // float4s of one sample's P^T
+
+    auto prefetch = [&](long ch) {
+        const SrcOne s0 = sample_source(p, job, (unsigned)(2 * ch));
+        const SrcOne s1 = sample_source(p, job, (unsigned)(2 * ch + 1));
+        cur_v0 = s0.valid; cur_v1 = s1.valid;
+        // dA rows of this thread's B task
+#pragma unroll
+        for (int k = 0; k < BS; ++k) {
+            breg[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (b_off[k] >= 0) {
+                const int s = (b_src[k] >> 30) & 1;
+                if (s ? s1.valid : s0.valid) {
+                    const float* da = (s ? s1.dA : s0.dA) + (b_src[k] & 0x3FFFFFFF);
+                    const unsigned nm = b_nmask >> (4 * k);
+                    if (nm & 1u) breg[k].x = da[0];
+                    if (nm & 2u) breg[k].y = da[H3];
+                    if (nm & 4u) breg[k].z = da[2 * H3];
+                    if (nm & 8u) breg[k].w = da[3 * H3];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < ZS; ++k) {
+            float v = 0.f, rr = 1.f;
+            if (z_sm[k] >= 0 && z_src[k] >= 0) {
+                const int s = (z_src[k] >> 30) & 1, off = z_src[k] & 0x3FFFFFFF;
+                const float* zs = s ? s1.zsrc : s0.zsrc;
+                if (zs != nullptr) {
+                    v = zs[off];
+                    if (job.type == 2) rr = (s ? s1.rsrc : s0.rsrc)[z_r[k]];
+                }
+            }
+            zreg[k] = v;
+            rreg[k] = rr;                                             // multiplied when stored: keeps the loads in flight
+        }
+#pragma unroll
+        for (int k = 0; k < PS; ++k) {
+            int idx = tid + k * TNT;
+            preg[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < pt_f4) {
+                const int s = idx >= pt_half;
+                const int r = idx - s * pt_half;
+                if (s ? s1.valid : s0.valid) preg[k] = reinterpret_cast<const float4*>(s ? s1.pt : s0.pt)[r];
+            }
+        }
+    };
+
+    const size_t psz = (size_t)(p.fin + H) * M * H3;
+    float* part = p.part + (size_t)blockIdx.y * psz;
+    bool flushed = false;
+    // TMEM -> partial (+=).  Called by all threads after the MMAs issued so far have completed.
+    auto flush = [&]() {
+        tc_fence_after();
+        const int row = 32 * (warp & 3) + lane;
+        const int cg = warp >> 2, ncol = nco / 4;
+        for (int cb = cg * ncol; cb < (cg + 1) * ncol; cb += 16) {
+            float v[16];
+            tmem_ld16(taddr + ((uint32_t)(32 * (warp & 3)) << 16) + cb, v);
+            if (row < nkk) {
+                float4* dst = reinterpret_cast<float4*>(part + (size_t)(kk0 + row) * H3 + job.o0 + cb);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float4 o = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    if (flushed) { float4 q = dst[j]; o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w; }
+                    dst[j] = o;
+                }
+            }
+            if (ones_row && row == 127) {
+                float* pb = p.partb + (size_t)blockIdx.y * H3 + job.o0 + cb;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) pb[j] = (flushed ? pb[j] : 0.f) + v[j];
+            }
+        }
+        flushed = true;
+        tc_fence_before();
+        __syncthreads();
+    };
+
+    const long nchunk = ((long)p.T * p.B + 1) / 2;
+    int it = 0;              // chunks done by this CTA
+    int since_flush = 0;     // chunks accumulated in TMEM since the last flush
+    if ((long)blockIdx.y < nchunk) prefetch(blockIdx.y);
     for (long ch = blockIdx.y; ch < nchunk; ch += gridDim.y, ++it) {
         const int s_ = it & 1;
         if (it >= 2) mbar_wait(&mbar[s_], ((it >> 1) - 1) & 1);
@@ -75,85 +252,64 @@ __global__ void __launch_bounds__(NT, 1) dw_tc_kernel(const DwParams p) {
         float4* a_lo = reinterpret_cast<float4*>(st + L.a_bytes);
         float4* b_hi = reinterpret_cast<float4*>(st + 2 * L.a_bytes);
         float4* b_lo = reinterpret_cast<float4*>(st + 2 * L.a_bytes + L.b_bytes);
-        // ---- the two sample steps of this chunk ------------------------------------------------------
-        long q[2] = {2 * ch, 2 * ch + 1};
-        int tq[2], bq[2];
-        bool vq[2];
-        for (int s = 0; s < 2; ++s) {
-            vq[s] = q[s] < total_q;
-            tq[s] = vq[s] ? (int)(q[s] / B) : 0;
-            bq[s] = vq[s] ? (int)(q[s] % B) : 0;
+        const bool v0 = cur_v0, v1 = cur_v1;
+        // ---- registers of this chunk -> shared memory --------------------------------------------------------
+#pragma unroll
+        for (int k = 0; k < ZS; ++k)
+            if (z_sm[k] >= 0) Zc[z_sm[k]] = zreg[k] * rreg[k];
+#pragma unroll
+        for (int k = 0; k < PS; ++k) {
+            int idx = tid + k * TNT;
+            if (idx < pt_f4) reinterpret_cast<float4*>(PT)[idx] = preg[k];
         }
-        // ---- PT[s][m1][j][n] and Zc[s][j][ccl] ---------------------------------------------------------
-        for (int idx = tid; idx < 2 * M1 * NP * NP; idx += NT) {
-            int n = idx % NP, j = (idx / NP) % NP, sm = idx / (NP * NP);
-            int s = sm / max(M1, 1), m1 = sm - s * max(M1, 1);
-            float v = 0.f;
-            if (n < N && j < N && vq[s]) v = p.P[(((size_t)bq[s] * M1 + m1) * N + n) * N + j];
-            PT[idx] = v;
-        }
-        for (int idx = tid; idx < 2 * NP * ncz; idx += NT) {
-            int ccl = idx % ncz, j = (idx / ncz) % NP, s = idx / (ncz * NP);
-            float v = 0.f;
-            if (j < N && vq[s]) {
-                const int t = tq[s], b = bq[s];
-                const int c = c_lo + ccl - zoff;                    // column within x or within h
-                const size_t ro = (size_t)b * N + j;
-                if (job.type == 0) {
-                    const float* xs; long long xsb;
-                    if (p.mode == 0) { xs = p.x + (size_t)t * p.xs_t; xsb = p.xs_b; }
-                    else {
-                        if (p.layer == 0) {
-                            xsb = (long long)N * p.Fo;
-                            if (t == 0) xs = nullptr;
-                            else if ((p.teacher_mask >> (t - 1)) & 1ull) xs = p.targets + (size_t)(t - 1) * B * N * p.Fo;
-                            else xs = p.out + (size_t)(t - 1) * B * N * p.Fo;
-                        } else { xsb = (long long)NH; xs = p.hseq + ((size_t)t * p.ncell + (p.layer - 1)) * B * NH; }
-                    }
-                    if (xs != nullptr) v = xs[(size_t)b * xsb + j * p.fin + c];
-                } else {
-                    const float* hp = (p.mode == 0)
-                        ? ((t == 0) ? p.h0 : p.hseq + (size_t)(t - 1) * B * NH)
-                        : ((t == 0) ? p.h0 + (size_t)p.layer * B * NH
-                                    : p.hseq + ((size_t)(t - 1) * p.ncell + p.layer) * B * NH);
-                    v = hp[ro * H + c];
-                    if (job.type == 2) {
-                        const float* rc = (p.mode == 0) ? p.ruc + (size_t)t * B * NH * 3
-                                                        : p.ruc + ((size_t)t * p.ncell + p.layer) * B * NH * 3;
-                        v *= rc[ro * H3 + c];
-                    }
-                }
+#pragma unroll
+        for (int k = 0; k < BS; ++k) {                                // B tile: dA^T
+            if (b_off[k] >= 0) {
+                float4 h, l;
+                split4(breg[k], h, l);
+                b_hi[b_off[k]] = h;
+                b_lo[b_off[k]] = l;
             }
-            Zc[(s * NP + j) * TZC + ccl] = v;
+        }
+        if (ones_row && tid < TKG) {                                 // db row: 1 for every real (sample, node)
+            int s = tid / 5, q5 = tid % 5;
+            bool v = s ? v1 : v0;
+            float4 o;
+            o.x = (v && 4 * q5 + 0 < N) ? 1.f : 0.f;
+            o.y = (v && 4 * q5 + 1 < N) ? 1.f : 0.f;
+            o.z = (v && 4 * q5 + 2 < N) ? 1.f : 0.f;
+            o.w = (v && 4 * q5 + 3 < N) ? 1.f : 0.f;
+            a_hi[tid * 128 + 127] = o;
         }
         __syncthreads();
-        // ---- A tile: G^T, one task = (sample, source column, node quad) ---------------------------------
-        for (int id = tid; id < 2 * ncz * 5; id += NT) {
-            int ccl = id % ncz, t1 = id / ncz;
-            int q5 = t1 % 5, s = t1 / 5;
-            const float* zp = Zc + (s * NP) * TZC + ccl;
-            const int kg = s * 5 + q5;
-            const int kbase = (c_lo + ccl) * M - kk0;                // local row of the m = 0 term
-            {   // m = 0: identity
-                if (kbase >= 0 && kbase < nkk) {
-                    float4 v = make_float4(zp[(4 * q5) * TZC], zp[(4 * q5 + 1) * TZC], zp[(4 * q5 + 2) * TZC],
-                                           zp[(4 * q5 + 3) * TZC]);
-                    float4 h, l;
-                    split4(v, h, l);
-                    a_hi[kg * 128 + kbase] = h;
-                    a_lo[kg * 128 + kbase] = l;
-                }
+        // ---- global loads of the next chunk (latency hidden behind the A production below) ---------------------
+        if (ch + gridDim.y < nchunk) prefetch(ch + gridDim.y);
+        // ---- A tile: G^T ------------------------------------------------------------------------------------------
+        if (tid < a_cnt) {
+            const float* zp = Zc + (a_s * NP) * ZLD + a_ccl;
+            const int kg = a_s * 5 + a_q5;
+            const int kbase = (c_lo + a_ccl) * M - kk0;              // local row of the m = 0 term
+            if (kbase >= 0 && kbase < nkk) {
+                float4 v = make_float4(zp[(4 * a_q5) * ZLD], zp[(4 * a_q5 + 1) * ZLD], zp[(4 * a_q5 + 2) * ZLD],
+                                       zp[(4 * a_q5 + 3) * ZLD]);     // (dynamic quad index: read from smem, not zc[])
+                float4 h, l;
+                split4(v, h, l);
+                a_hi[kg * 128 + kbase] = h;
+                a_lo[kg * 128 + kbase] = l;
             }
+            float zc[NP];                                             // the source column (rows >= N are zero)
+#pragma unroll
+            for (int j = 0; j < NP; ++j) zc[j] = zp[j * ZLD];
             for (int m1 = 0; m1 < M1; ++m1) {
                 const int kl = kbase + m1 + 1;
                 if (kl < 0 || kl >= nkk) continue;
-                const float* pp = PT + ((size_t)(s * M1 + m1) * NP) * NP + 4 * q5;
+                const float* pp = PT + (size_t)(a_s * M1 + m1) * PTS + 4 * a_q5;
                 float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int j = 0; j < N; ++j) {
-                    float z = zp[j * TZC];
+#pragma unroll
+                for (int j = 0; j < NP; ++j) {                        // PT rows j >= N are zero
                     float4 pv = *reinterpret_cast<const float4*>(pp + j * NP);
-                    a.x = fmaf(pv.x, z, a.x); a.y = fmaf(pv.y, z, a.y);
-                    a.z = fmaf(pv.z, z, a.z); a.w = fmaf(pv.w, z, a.w);
+                    a.x = fmaf(pv.x, zc[j], a.x); a.y = fmaf(pv.y, zc[j], a.y);
+                    a.z = fmaf(pv.z, zc[j], a.z); a.w = fmaf(pv.w, zc[j], a.w);
                 }
                 float4 h, l;
                 split4(a, h, l);
@@ -161,81 +317,29 @@ __global__ void __launch_bounds__(NT, 1) dw_tc_kernel(const DwParams p) {
                 a_lo[kg * 128 + kl] = l;
             }
         }
-        if (ones_row && tid < TKG) {                                 // db row: 1 for every real (sample, node)
-            int s = tid / 5, q5 = tid % 5;
-            float4 v;
-            v.x = (vq[s] && 4 * q5 + 0 < N) ? 1.f : 0.f;
-            v.y = (vq[s] && 4 * q5 + 1 < N) ? 1.f : 0.f;
-            v.z = (vq[s] && 4 * q5 + 2 < N) ? 1.f : 0.f;
-            v.w = (vq[s] && 4 * q5 + 3 < N) ? 1.f : 0.f;
-            a_hi[tid * 128 + 127] = v;
-        }
-        // ---- B tile: dA^T, one task = (K group, 4 output columns) ------------------------------------------
-        {
-            const int noq = nco >> 2;
-            for (int id = tid; id < TKG * noq; id += NT) {
-                int oq = id % noq, kg = id / noq;
-                int s = kg / 5, q5 = kg - s * 5;
-                float4 r[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    int n = 4 * q5 + i;
-                    r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (vq[s] && n < N) {
-                        const float* da = (p.mode == 0) ? p.dA + (size_t)tq[s] * B * NH * 3
-                                                        : p.dA + ((size_t)tq[s] * p.ncell + p.layer) * B * NH * 3;
-                        r[i] = *reinterpret_cast<const float4*>(da + ((size_t)bq[s] * N + n) * H3 + job.o0 + 4 * oq);
-                    }
-                }
-                float4 c0 = make_float4(r[0].x, r[1].x, r[2].x, r[3].x);
-                float4 c1 = make_float4(r[0].y, r[1].y, r[2].y, r[3].y);
-                float4 c2 = make_float4(r[0].z, r[1].z, r[2].z, r[3].z);
-                float4 c3 = make_float4(r[0].w, r[1].w, r[2].w, r[3].w);
-                float4 h, l;
-                float4* bh = b_hi + kg * nco + 4 * oq;
-                float4* bl = b_lo + kg * nco + 4 * oq;
-                split4(c0, h, l); bh[0] = h; bl[0] = l;
-                split4(c1, h, l); bh[1] = h; bl[1] = l;
-                split4(c2, h, l); bh[2] = h; bl[2] = l;
-                split4(c3, h, l); bh[3] = h; bl[3] = l;
-            }
-        }
         fence_async_smem();
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
             issue_3xtf32(taddr, smem_u32(a_hi), smem_u32(a_lo), 128, smem_u32(b_hi), smem_u32(b_lo), nco,
-                         TKR / 8, idesc, it > 0);
+                         TKR / 8, idesc, since_flush > 0);
             umma_commit(&mbar[s_]);
         }
-    }
-    // ---- epilogue: TMEM -> split-K partial -----------------------------------------------------------------
-    const bool any = it > 0;
-    if (any) mbar_wait(&mbar[(it - 1) & 1], ((it - 1) >> 1) & 1);
-    tc_fence_after();
-    {
-        const int row = 32 * (warp & 3) + lane;
-        const int half = warp >> 2, ncol = nco / 2;
-        const size_t psz = (size_t)(p.fin + H) * M * H3;
-        float* part = p.part + (size_t)blockIdx.y * psz;
-        for (int cb = half * ncol; cb < (half + 1) * ncol; cb += 32) {
-            float v[32];
-            if (any) tmem_ld32(taddr + ((uint32_t)(32 * (warp & 3)) << 16) + cb, v);
-            else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = 0.f;
-            }
-            if (row < nkk) {
-                float4* dst = reinterpret_cast<float4*>(part + (size_t)(kk0 + row) * H3 + job.o0 + cb);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-            if (ones_row && row == 127) {
-                float* pb = p.partb + (size_t)blockIdx.y * H3 + job.o0 + cb;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) pb[j] = v[j];
-            }
+        ++since_flush;
+        if (since_flush == TFLUSH) {
+            mbar_wait(&mbar[s_], (it >> 1) & 1);                      // this chunk's MMAs (hence all earlier) done
+            flush();
+            since_flush = 0;
         }
+    }
+    if (since_flush > 0) {
+        mbar_wait(&mbar[(it - 1) & 1], ((it - 1) >> 1) & 1);
+        flush();
+    } else if (!flushed) {                                            // CTA had no chunk at all: zero partial
+        const int row = tid & 127, q = tid >> 7;
+        if (row < nkk)
+            for (int c = q * (nco / 4); c < (q + 1) * (nco / 4); ++c) part[(size_t)(kk0 + row) * H3 + job.o0 + c] = 0.f;
+        if (ones_row && tid < nco) p.partb[(size_t)blockIdx.y * H3 + job.o0 + tid] = 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -243,13 +347,21 @@ __global__ void __launch_bounds__(NT, 1) dw_tc_kernel(const DwParams p) {
 }
 
 int dw_tc_smem_bytes(int M, int nco_max) { return dwtc_smem(M, nco_max).total; }
+size_t dw_tc_pt_floats(int B, int M) { return (size_t)B * (M - 1) * PTS; }
+
+cudaError_t launch_make_pt(const float* P, int B, int M, int N, float* PT, cudaStream_t st) {
+    size_t total = (size_t)B * (M - 1) * PTS;
+    if (total == 0) return cudaSuccess;
+    make_pt_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(P, B, M - 1, N, PT);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_dw_tc(const DwParams& p, int njobs, int nco_max, cudaStream_t st) {
     int smem = dw_tc_smem_bytes(p.M, nco_max);
     cudaError_t e = cudaFuncSetAttribute(dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     dim3 grid(njobs, p.nsplit);
-    dw_tc_kernel<<<grid, NT, smem, st>>>(p);
+    dw_tc_kernel<<<grid, TNT, smem, st>>>(p);
     return cudaGetLastError();
 }
 

@@ -82,6 +82,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 }
 
+// 32 lanes x 16 consecutive columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+}
+
 // ---- mbarrier -----------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -104,14 +118,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // ---- 3xTF32 split ---------------------------------------------------------------------------------------
 // round-to-nearest on both parts keeps the representation error unbiased (a truncating split showed a
 // systematic ~3e-6 relative error at K=320 on hardware; with rounding it is random-walk ~1e-7)
+// The rounding is done with two integer ALU ops on the bit pattern (add half an ulp of TF32, clear the low
+// 13 bits = round-half-away on the magnitude): cvt.rna.tf32.f32 would do the same but issues on the XU
+// pipe (16 lanes/clk/SM), which ncu showed saturated (192 % of peak) in the first dw_tc version.
+// lo = x - hi is exact and has a random sign, so the tensor core truncating it to TF32 adds no bias.
 __device__ __forceinline__ float rna_tf32(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     hi = rna_tf32(x);
-    lo = rna_tf32(x - hi);
+    lo = x - hi;
 }
 __device__ __forceinline__ void split4(const float4& v, float4& hi, float4& lo) {
     split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y);

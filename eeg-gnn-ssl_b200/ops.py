@@ -115,8 +115,12 @@ class _EncoderLayerFn(torch.autograd.Function):
                           dtype=torch.float32) if need else None
         wg, bg, wc, bc = wg.contiguous(), bg.contiguous(), wc.contiguous(), bc.contiguous()
         ws = _params([(wg, bg, wc, bc)])
-        check(_lib.lib().dcgru_encoder_layer_fwd(C.byref(desc), b, t_len, _ptr(x), st, sb, _ptr(h0), _ptr(p),
-                                                 ws, _ptr(h_seq), _ptr(ruc), _stream()), "encoder_layer_fwd")
+        L = _lib.lib()
+        nbytes = L.dcgru_encoder_layer_fwd_workspace(C.byref(desc), b, t_len)
+        ws_buf = torch.empty(max(nbytes, 16), device=x.device, dtype=torch.uint8)
+        check(L.dcgru_encoder_layer_fwd(C.byref(desc), b, t_len, _ptr(x), st, sb, _ptr(h0), _ptr(p), ws,
+                                        _ptr(h_seq), _ptr(ruc), _ptr(ws_buf), nbytes, _stream()),
+              "encoder_layer_fwd")
         ctx.desc = desc
         ctx.strides = (st, sb)
         ctx.save_for_backward(x, h0, p, wg, bg, wc, bc, h_seq, ruc)

@@ -94,11 +94,15 @@ int dcgru_corr_supports(int32_t batch, int32_t seq_len, int32_t num_nodes, int32
  * h0:    (B, N*H)
  * P:     (B, M-1, N, N) from dcgru_graph_poly
  * h_seq: (T, B, N*H) out -- every step's hidden state (the layer's output sequence)
- * ruc:   (T, B, N, 3H) out -- r | u | c per node, saved for backward (NULL: inference)       */
+ * ruc:   (T, B, N, 3H) out -- r | u | c per node, saved for backward (NULL: inference)
+ * workspace: scratch for the pre-tiled weight image of the tensor-core kernel (may be NULL:
+ *        the fp32 FMA kernel is used then)                                                    */
+size_t dcgru_encoder_layer_fwd_workspace(const dcgru_cell_desc *d, int32_t batch, int32_t seq_len);
 int dcgru_encoder_layer_fwd(const dcgru_cell_desc *d, int32_t batch, int32_t seq_len,
                             const float *x, int64_t x_stride_t, int64_t x_stride_b,
                             const float *h0, const float *P, const dcgru_cell_params *w,
-                            float *h_seq, float *ruc, void *stream);
+                            float *h_seq, float *ruc,
+                            void *workspace, size_t workspace_bytes, void *stream);
 
 size_t dcgru_encoder_layer_bwd_workspace(const dcgru_cell_desc *d, int32_t batch,
                                          int32_t seq_len);

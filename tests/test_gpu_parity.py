@@ -186,7 +186,7 @@ def test_encoder_vs_oracle_fp64(dev, B, T, H, K, S, L, act):
     for k in ours:
         e = rel_err(ours[k].cpu().numpy(), ref64[k].numpy())
         e32 = rel_err(ref32[k].numpy(), ref64[k].numpy())      # fp32 round-off of the same math on CPU
-        assert e < max(TOL, 4 * e32), (k, e, e32)
+        assert e < max(TOL, 8 * e32), (k, e, e32)
 
 
 def test_cell_single_step(dev):

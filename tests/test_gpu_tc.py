@@ -15,7 +15,7 @@ def dev():
     return torch.device("cuda:0")
 
 
-@pytest.mark.parametrize("N,K", [(64, 32), (128, 64), (192, 320), (256, 96)])
+@pytest.mark.parametrize("N,K", [(64, 32), (128, 64), (192, 320), (256, 96), (64, 2048), (64, 16384)])
 def test_tcgen05_3xtf32_gemm(dev, N, K):
     from eeg_gnn_ssl_b200 import _lib
     g = torch.Generator().manual_seed(N + K)
@@ -33,7 +33,9 @@ def test_tcgen05_3xtf32_gemm(dev, N, K):
     tf32 = float(((A.to(dev) @ B.to(dev).t()).cpu().double() - ref).abs().max() / ref.abs().max())
     print(f"N={N} K={K}: 3xTF32 rel err {err:.3e} (fp32 matmul on device: {tf32:.3e})")
     assert np.isfinite(got.numpy()).all()
-    assert err < 2e-6, err
+    # the tensor core truncates when adding into the fp32 accumulator: the bias grows with the number of
+    # accumulation steps (K/8*3), which is why dw_tc flushes TMEM every 32 chunks
+    assert err < 2e-6 + 1.5e-8 * K, err
 
 
 def _grads(dev, B, T, H, K, S, L, seed=0):
@@ -61,3 +63,31 @@ def test_tc_weight_gradients_match_simt(dev, monkeypatch, B, T, H, K, S, L):
     for n in ref:
         e = float((got[n] - ref[n]).abs().max() / ref[n].abs().max())
         assert e < 1e-5, (n, e)
+
+
+@pytest.mark.parametrize("B,T,L", [(13, 5, 2), (6, 3, 1), (150, 4, 2)])
+def test_tc_forward_matches_simt(dev, monkeypatch, B, T, L):
+    """seq_fwd_tc_kernel (tcgen05) against the fp32 FMA kernel: hidden-state sequences and input grads"""
+    from eeg_gnn_ssl_b200.model.model import DCRNNEncoder
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("DCGRU_DISABLE_TC", flag)
+        g = torch.Generator().manual_seed(7)
+        torch.manual_seed(7)
+        enc = DCRNNEncoder(100, 2, 64, 19, L, dcgru_activation="tanh").to(dev)
+        with torch.no_grad():
+            for p in enc.parameters():
+                if p.dim() == 1:
+                    p.add_(0.1 * torch.randn(p.shape, generator=g).to(dev))
+        x = torch.randn(T, B, 19, 100, generator=g).to(dev)
+        # row-stochastic supports (what the loaders produce); dense Gaussian ones make 2S^2-I ill conditioned
+        sup = [torch.softmax(2 * torch.randn(B, 19, 19, generator=g), -1).to(dev)]
+        h0 = (0.3 * torch.randn(L, B, 19 * 64, generator=g)).to(dev).requires_grad_(True)
+        w = torch.randn(T, B, 19 * 64, generator=g).to(dev)
+        oh, top = enc(x, h0, sup)
+        (top * w).sum().backward()
+        outs[flag] = (top.detach().cpu().double(), oh.detach().cpu().double(), h0.grad.cpu().double(),
+                      enc.encoding_cells[0].dconv_gate.weight.grad.cpu().double())
+    for a, b in zip(outs["0"], outs["1"]):
+        e = float((a - b).abs().max() / b.abs().max())
+        assert e < 2e-5, e

@@ -321,7 +321,7 @@ int dcgru_corr_supports(int32_t batch, int32_t seq_len, int32_t num_nodes, int32
 
 size_t dcgru_encoder_layer_fwd_workspace(const dcgru_cell_desc* d, int32_t batch, int32_t seq_len) {
     if (check_desc(d) || batch < 1 || seq_len < 1) return 0;
-    return align_up(seq_fwd_tc_wimg_bytes(d->input_dim)) + 256;
+    return align_up(seq_fwd_tc_wimg_bytes(d->input_dim)) + 256 + 16384;   // + debug stamps (DCGRU_DBG & 4)
 }
 
 int dcgru_encoder_layer_fwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq_len, const float* x,
@@ -339,7 +339,7 @@ int dcgru_encoder_layer_fwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
     cudaStream_t st = (cudaStream_t)stream;
     // tensor-core path (tcgen05, 3xTF32): K=2 / one support / 64 units -- the reference's default cell
     if (tc_enabled() && ruc && workspace && aligned16(workspace) &&
-        workspace_bytes >= seq_fwd_tc_wimg_bytes(d->input_dim) &&
+        workspace_bytes >= align_up(seq_fwd_tc_wimg_bytes(d->input_dim)) + 16384 &&
         seq_fwd_tc_supported(d->num_nodes, d->input_dim, d->hid_dim, M, devinfo().smem)) {
         LAUNCH("seq_fwd_tc", launch_seq_fwd_tc(batch, seq_len, d->num_nodes, d->input_dim, d->activation, x,
                                                x_stride_t, x_stride_b, h0, P, w->Wg, w->bg, w->Wc, w->bc,

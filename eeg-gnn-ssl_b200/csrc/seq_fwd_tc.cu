@@ -17,6 +17,8 @@
 // (two chunks ahead); only the hidden state stays resident in shared memory.
 // The epilogues read the accumulator with tcgen05.ld (thread = row) and fuse bias, sigmoid/tanh, r*h and
 // the GRU update.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "dw.cuh"
 #include "tc_common.cuh"
@@ -43,7 +45,8 @@ constexpr int FT_XSLOT = FT_ROWS * FT_XLD * 4;             // one x chunk: [128 
 constexpr int FT_OFF_A = 0;                                // 2 stages
 constexpr int FT_OFF_B = FT_OFF_A + 2 * FT_A_STAGE;        // 3 slots
 constexpr int FT_OFF_X = FT_OFF_B + 3 * FT_BX_BYTES;       // 3 slots
-constexpr int FT_OFF_ZH = FT_OFF_X + 3 * FT_XSLOT;         // [128][64] hidden state (or r*h)
+constexpr int FT_XRING = 4;                                // x chunk ring slots (prefetch distance 2, race-free)
+constexpr int FT_OFF_ZH = FT_OFF_X + FT_XRING * FT_XSLOT;  // [128][64] hidden state (or r*h)
 constexpr int FT_SMEM = FT_OFF_ZH + FT_ROWS * FT_ZLD * 4;
 
 __host__ __device__ inline int ft_nxc(int fin) { return (fin + FT_CC - 1) / FT_CC; }
@@ -97,7 +100,7 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
 }
 
 struct FwdTcParams {
-    int B, T, N, fin, act;
+    int B, T, N, fin, act, dbg;
     const float* x; long long xs_t, xs_b;
     const float* h0;
     const float* P;
@@ -105,49 +108,59 @@ struct FwdTcParams {
     const float* wimg;
     float* hseq;
     float* ruc;
+    long long* dbgbuf;          // timing experiment (DCGRU_DBG & 4): clock64 stamps of CTA 0
 };
 
-__global__ void __launch_bounds__(NT, 1) seq_fwd_tc_kernel(const FwdTcParams p) {
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void producer_barrier() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+// fast gates for the tensor-core path: ex2.approx based, ~1e-6 absolute error (the fp32 FMA path keeps expf/tanhf)
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+
+constexpr int FT_NPROD = 256;            // producer / epilogue threads (warps 0-7)
+constexpr int FT_THREADS = 320;          // + warp 8: MMA issue, warp 9: TMA weight loads
+
+// Warp-specialised: warps 0-7 build the A tiles and run the epilogues, warp 8 streams weights and x with TMA
+// and issues the MMAs; the only synchronisation inside a step is through mbarriers (no CTA-wide barrier).
+__global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bar_full[3], bar_done[2];
+    __shared__ uint64_t bar_bfull[3], bar_xfull[FT_XRING], bar_afull[2], bar_done[2], bar_epi;
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float sbias[3 * FT_H];                      // bg (r | u) | bc
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = p.N, fin = p.fin;
     const int b0 = blockIdx.x * FT_SB;
     if (tid < 3 * FT_H) sbias[tid] = (tid < 2 * FT_H) ? p.bg[tid] : p.bc[tid - 2 * FT_H];
-    float* ZH = reinterpret_cast<float*>(smem + FT_OFF_ZH);              // [128][64]
-    const int row = tid & 127, half = tid >> 7;
-    const int s_ = row / NP, n_ = row - s_ * NP;
-    const int b_ = b0 + s_;
-    const bool rvalid = (s_ < FT_SB) && (n_ < N) && (b_ < p.B);
+    float* ZH = reinterpret_cast<float*>(smem + FT_OFF_ZH);              // [128][FT_ZLD]
 
     if (warp == 0) tmem_alloc<256>(&tmem_slot);
     if (tid == 0) {
-        mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1); mbar_init(&bar_full[2], 1);
-        mbar_init(&bar_done[0], 1); mbar_init(&bar_done[1], 1);
+        for (int i = 0; i < 3; ++i) mbar_init(&bar_bfull[i], 1);
+        for (int i = 0; i < FT_XRING; ++i) mbar_init(&bar_xfull[i], FT_NPROD);
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_afull[i], FT_NPROD / 32); mbar_init(&bar_done[i], 1); }
+        mbar_init(&bar_epi, FT_NPROD / 32);
         mbar_fence_init();
     }
-    // this row of the diffusion polynomials, kept in registers for the whole sequence
-    float P1[NP], P2[NP];
-#pragma unroll
-    for (int j = 0; j < NP; ++j) {
-        P1[j] = 0.f; P2[j] = 0.f;
-        if (rvalid && j < N) {
-            P1[j] = p.P[(((size_t)b_ * 2 + 0) * N + n_) * N + j];
-            P2[j] = p.P[(((size_t)b_ * 2 + 1) * N + n_) * N + j];
-        }
-    }
     // hidden state <- h0, x ring <- 0 (rows of pad nodes / missing samples stay zero for ever)
-    for (int idx = tid; idx < FT_ROWS * (FT_H / 4); idx += NT) {
+    for (int idx = tid; idx < FT_ROWS * (FT_H / 4); idx += FT_THREADS) {
         const int r = idx / (FT_H / 4), c4 = (idx - r * (FT_H / 4)) * 4;
         const int s = r / NP, n = r - s * NP, b = b0 + s;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (s < FT_SB && n < N && b < p.B) v = *reinterpret_cast<const float4*>(p.h0 + ((size_t)b * N + n) * FT_H + c4);
         *reinterpret_cast<float4*>(ZH + r * FT_ZLD + c4) = v;
     }
-    for (int idx = tid; idx < 3 * FT_XSLOT / 16; idx += NT)
+    for (int idx = tid; idx < FT_XRING * FT_XSLOT / 16; idx += FT_THREADS)
         reinterpret_cast<float4*>(smem + FT_OFF_X)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    fence_async_smem();                      // the zeros must be ordered before the TMA writes into the ring
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -156,56 +169,142 @@ __global__ void __launch_bounds__(NT, 1) seq_fwd_tc_kernel(const FwdTcParams p) 
     const int nxc = ft_nxc(fin), nhc = FT_H / FT_CC;
     const int per_step = nxc + 2 * nhc;
     const unsigned total_chunks = (unsigned)p.T * per_step;
+    const unsigned total_x = (unsigned)p.T * nxc;
     const uint8_t* wimg = reinterpret_cast<const uint8_t*>(p.wimg);
     const size_t NH = (size_t)N * FT_H;
 
-    // weight block of chunk index q within a step
-    auto wblock = [&](int q, const uint8_t*& src, uint32_t& bytes) {
-        if (q < nxc) { src = wimg + (size_t)q * FT_BX_BYTES; bytes = FT_BX_BYTES; }
-        else if (q < nxc + nhc) { src = wimg + (size_t)nxc * FT_BX_BYTES + (size_t)(q - nxc) * FT_BG_BYTES; bytes = FT_BG_BYTES; }
-        else { src = wimg + (size_t)nxc * FT_BX_BYTES + (size_t)nhc * FT_BG_BYTES + (size_t)(q - nxc - nhc) * FT_BC_BYTES;
-               bytes = FT_BC_BYTES; }
-    };
-    // x chunk xq (= t*nxc + i) -> ring slot xq % 3 ; one 16-byte piece per thread
-    const unsigned total_x = (unsigned)p.T * nxc;
-    auto issue_x = [&](unsigned xq) {
-        if (xq < total_x) {
-            const int t = xq / nxc, i = xq - t * nxc;
+    if (warp == 8) {
+        // =================================== TMA + MMA issuer ===================================================
+        // One thread issues every MMA, so its instruction stream is the pipeline's clock: all shared-memory
+        // descriptors are precomputed (a first version rebuilt them per MMA and, with integer divisions for the
+        // chunk bookkeeping, spent ~2500 cycles per chunk here -- measured with clock64 stamps).
+        __shared__ uint64_t dA[2][3][2];                  // [stage][k-step][hi, lo]
+        __shared__ uint64_t dB[3][3][3][2];               // [slot][kind: X, Hg, Hc][k-step][hi, lo]
+        if (lane == 0) {
+            for (int st = 0; st < 2; ++st)
+                for (int k = 0; k < 3; ++k) {
+                    const uint32_t hi = smem_u32(smem + FT_OFF_A + st * FT_A_STAGE) + 2 * k * FT_ROWS * 16;
+                    dA[st][k][0] = make_smem_desc(hi, FT_ROWS * 16, 128);
+                    dA[st][k][1] = make_smem_desc(hi + FT_A_BYTES, FT_ROWS * 16, 128);
+                }
+            for (int sl = 0; sl < 3; ++sl)
+                for (int kind = 0; kind < 3; ++kind) {
+                    const int ncols = kind == 0 ? 192 : (kind == 1 ? 128 : 64);
+                    for (int k = 0; k < 3; ++k) {
+                        const uint32_t hi = smem_u32(smem + FT_OFF_B + sl * FT_BX_BYTES) + 2 * k * ncols * 16;
+                        dB[sl][kind][k][0] = make_smem_desc(hi, ncols * 16, 128);
+                        dB[sl][kind][k][1] = make_smem_desc(hi + FT_KG * ncols * 16, ncols * 16, 128);
+                    }
+                }
+        }
+        __syncwarp();
+        const uint32_t idesc[3] = {make_idesc_tf32(128, 192), make_idesc_tf32(128, 128), make_idesc_tf32(128, 64)};
+        if (lane == 0) {
+            int q = 0, t = 0;                 // chunk within step / step
+            int sb = 0, kb = 0;               // weight slot of chunk g and its use count parity
+            for (unsigned g = 0; g < total_chunks; ++g) {
+                const int sa = g & 1;
+                const bool rec = (p.dbg & 4) && blockIdx.x == 0 && g < 128;
+                if (rec) p.dbgbuf[g * 8 + 0] = clock64();
+                mbar_wait(&bar_bfull[sb], kb);
+                if (rec) p.dbgbuf[g * 8 + 1] = clock64();
+                mbar_wait(&bar_afull[sa], (g >> 1) & 1);
+                if (rec) p.dbgbuf[g * 8 + 2] = clock64();
+                if (q == 0 && t > 0) mbar_wait(&bar_epi, (t - 1) & 1);   // the previous step's TMEM reads are done
+                tc_fence_after();
+                const int kind = (q < nxc) ? 0 : (q < nxc + nhc ? 1 : 2);
+                const uint32_t d = taddr + (kind == 2 ? 128u : 0u);
+                const uint32_t id = idesc[kind];
+                uint32_t acc = (q != 0) ? 1u : 0u;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const uint64_t ah = dA[sa][k][0], al = dA[sa][k][1];
+                    const uint64_t bh = dB[sb][kind][k][0], bl = dB[sb][kind][k][1];
+                    umma_tf32(d, al, bh, id, acc);      // small terms first
+                    umma_tf32(d, ah, bl, id, 1u);
+                    umma_tf32(d, ah, bh, id, 1u);
+                    acc = 1u;
+                }
+                umma_commit(&bar_done[sa]);
+                if (rec) p.dbgbuf[g * 8 + 3] = clock64();
+                // advance the bookkeeping without divisions
+                if (++q == per_step) { q = 0; ++t; }
+                if (++sb == 3) { sb = 0; kb ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 9) {
+        // =================================== TMA weight loader ==================================================
+        // chunk g+2's weights go into the ring slot chunk g-1 used, as soon as that chunk's MMAs have completed
+        const uint8_t* wg_base = wimg + (size_t)nxc * FT_BX_BYTES;
+        const uint8_t* wc_base = wg_base + (size_t)nhc * FT_BG_BYTES;
+        auto load_w = [&](int q, int slot) {                              // q = chunk index within a step
+            const uint8_t* src; uint32_t bytes;
+            if (q < nxc) { src = wimg + (size_t)q * FT_BX_BYTES; bytes = FT_BX_BYTES; }
+            else if (q < nxc + nhc) { src = wg_base + (size_t)(q - nxc) * FT_BG_BYTES; bytes = FT_BG_BYTES; }
+            else { src = wc_base + (size_t)(q - nxc - nhc) * FT_BC_BYTES; bytes = FT_BC_BYTES; }
+            mbar_expect_tx(&bar_bfull[slot], bytes);
+            bulk_copy(smem + FT_OFF_B + slot * FT_BX_BYTES, src, bytes, &bar_bfull[slot]);
+        };
+        if (lane == 0) {
+            load_w(0, 0);
+            if (total_chunks > 1) load_w(1 % per_step, 1);
+            int q2 = 2 % per_step, sb2 = 2;   // chunk g+2: index within step, slot
+            for (unsigned g = 0; g + 2 < total_chunks; ++g) {
+                if (g >= 1) mbar_wait(&bar_done[(g - 1) & 1], ((g - 1) >> 1) & 1);       // frees weight slot sb2
+                load_w(q2, sb2);
+                if (++q2 == per_step) q2 = 0;
+                if (++sb2 == 3) sb2 = 0;
+            }
+        }
+        __syncwarp();
+    } else {
+        // =================================== producers / epilogue ================================================
+        const int row = tid & 127, half = tid >> 7;
+        const int s_ = row / NP, n_ = row - s_ * NP;
+        const int b_ = b0 + s_;
+        const bool rvalid = (s_ < FT_SB) && (n_ < N) && (b_ < p.B);
+        // this row of the diffusion polynomials, kept in registers for the whole sequence
+        float P1[NP], P2[NP];
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            P1[j] = 0.f; P2[j] = 0.f;
+            if (rvalid && j < N) {
+                P1[j] = p.P[(((size_t)b_ * 2 + 0) * N + n_) * N + j];
+                P2[j] = p.P[(((size_t)b_ * 2 + 1) * N + n_) * N + j];
+            }
+        }
+        unsigned g = 0, xq = 0;
+        // x chunk xq (= t*nxc + i) -> ring slot xq % 3: one 16-byte cp.async per thread; the slot's mbarrier
+        // completes when every producer thread's copy has landed (cp.async.mbarrier.arrive.noinc)
+        auto issue_x = [&](unsigned q_) {
+            if (q_ >= total_x) return;
+            const int t = q_ / nxc, i = q_ - t * nxc;
             const int r = tid >> 1, q4 = (tid & 1) * 4;
             const int s = r / NP, n = r - s * NP, b = b0 + s;
             const int c = i * FT_CC + q4;
             if (s < FT_SB && n < N && b < p.B && c < fin) {
-                float* dst = reinterpret_cast<float*>(smem + FT_OFF_X + (xq % 3) * FT_XSLOT) + r * FT_XLD + q4;
+                float* dst = reinterpret_cast<float*>(smem + FT_OFF_X + (q_ % FT_XRING) * FT_XSLOT) + r * FT_XLD + q4;
                 cp_async16(dst, p.x + (size_t)t * p.xs_t + (size_t)b * p.xs_b + n * fin + c);
             }
-        }
-        cp_async_commit();
-    };
-
-    unsigned g = 0;                                                      // global chunk counter
-    unsigned xq = 0;                                                     // x chunk counter
-    // prologue: weights of chunk 0, x chunks 0 and 1
-    if (tid == 0) { const uint8_t* src; uint32_t bytes; wblock(0, src, bytes); bulk_load(smem + FT_OFF_B, src, bytes, &bar_full[0]); }
-    issue_x(0);
-    issue_x(1);
-    cp_async_wait<1>();
-    __syncthreads();
-
-    // one chunk: prefetch the next weight block, build the A tile from 8 source columns, issue the MMAs
-    // zsrc: base of the [rows][zld] source (x ring slot or hidden state), c0 = first column inside it
-    auto chunk = [&](const float* zsrc, int zld, int c0, int cvalid, int ncols, uint32_t dcol, bool fresh, bool is_x) {
-        const int sa = g & 1, sb = g % 3;
-        if (g >= 2) mbar_wait(&bar_done[sa], ((g >> 1) - 1) & 1);          // frees A stage sa and B slot (g+1)%3
-        if (tid == 0 && g + 1 < total_chunks) {
-            const uint8_t* src; uint32_t bytes;
-            wblock((int)((g + 1) % per_step), src, bytes);
-            bulk_load(smem + FT_OFF_B + ((g + 1) % 3) * FT_BX_BYTES, src, bytes, &bar_full[(g + 1) % 3]);
-        }
-        if (is_x) issue_x(xq + 2);
-        float4* a_hi = reinterpret_cast<float4*>(smem + FT_OFF_A + sa * FT_A_STAGE);
-        float4* a_lo = reinterpret_cast<float4*>(smem + FT_OFF_A + sa * FT_A_STAGE + FT_A_BYTES);
-        // ---- A tile: this thread's row, 4 source columns --------------------------------------------------
-        {
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&bar_xfull[q_ % FT_XRING])) : "memory");
+        };
+        issue_x(0);
+        issue_x(1);
+        // A tile of one chunk from 8 source columns; zsrc = [rows][zld] source, c0 = first column inside it
+        auto produce = [&](const float* zsrc, int zld, int c0, int cvalid, bool is_x) {
+            const int sa = g & 1;
+            const bool rec = (p.dbg & 4) && blockIdx.x == 0 && tid == 0 && g < 128;
+            if (rec) p.dbgbuf[g * 8 + 4] = clock64();
+            if (g >= 2) mbar_wait(&bar_done[sa], ((g >> 1) - 1) & 1);    // the MMAs that read this stage are done
+            if (rec) p.dbgbuf[g * 8 + 5] = clock64();
+            if (is_x) {
+                // every producer is past chunk g-2, so the slot x chunk xq-2 lived in can be refilled
+                issue_x(xq + 2);
+                mbar_wait(&bar_xfull[xq % FT_XRING], (xq / FT_XRING) & 1);
+            }
+            float4* a_hi = reinterpret_cast<float4*>(smem + FT_OFF_A + sa * FT_A_STAGE);
+            float4* a_lo = reinterpret_cast<float4*>(smem + FT_OFF_A + sa * FT_A_STAGE + FT_A_BYTES);
             const int c = c0 + 4 * half;
             float v0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
             if (4 * half < cvalid && row < FT_SB * NP) {
@@ -213,12 +312,17 @@ __global__ void __launch_bounds__(NT, 1) seq_fwd_tc_kernel(const FwdTcParams p) 
                 v0[0] = own.x; v0[1] = own.y; v0[2] = own.z; v0[3] = own.w;
                 const float* zq = zsrc + (s_ * NP) * zld + c;
 #pragma unroll
-                for (int j = 0; j < NP; ++j) {                            // rows j >= N are zero, so are P1/P2 there
-                    const float4 z = *reinterpret_cast<const float4*>(zq + j * zld);
-                    a1[0] = fmaf(P1[j], z.x, a1[0]); a1[1] = fmaf(P1[j], z.y, a1[1]);
-                    a1[2] = fmaf(P1[j], z.z, a1[2]); a1[3] = fmaf(P1[j], z.w, a1[3]);
-                    a2[0] = fmaf(P2[j], z.x, a2[0]); a2[1] = fmaf(P2[j], z.y, a2[1]);
-                    a2[2] = fmaf(P2[j], z.z, a2[2]); a2[3] = fmaf(P2[j], z.w, a2[3]);
+                for (int jb = 0; jb < NP; jb += 10) {                     // rows j >= N are zero, so are P1/P2 there
+                    float4 z[10];
+#pragma unroll
+                    for (int j = 0; j < 10; ++j) z[j] = *reinterpret_cast<const float4*>(zq + (jb + j) * zld);
+#pragma unroll
+                    for (int j = 0; j < 10; ++j) {
+                        a1[0] = fmaf(P1[jb + j], z[j].x, a1[0]); a1[1] = fmaf(P1[jb + j], z[j].y, a1[1]);
+                        a1[2] = fmaf(P1[jb + j], z[j].z, a1[2]); a1[3] = fmaf(P1[jb + j], z[j].w, a1[3]);
+                        a2[0] = fmaf(P2[jb + j], z[j].x, a2[0]); a2[1] = fmaf(P2[jb + j], z[j].y, a2[1]);
+                        a2[2] = fmaf(P2[jb + j], z[j].z, a2[2]); a2[3] = fmaf(P2[jb + j], z[j].w, a2[3]);
+                    }
                 }
             }
             // kk order inside the quad: (c, m0) (c, m1) (c, m2) (c+1, m0) ...
@@ -230,52 +334,85 @@ __global__ void __launch_bounds__(NT, 1) seq_fwd_tc_kernel(const FwdTcParams p) 
             split4(f0, h, l); a_hi[(kg0 + 0) * FT_ROWS + row] = h; a_lo[(kg0 + 0) * FT_ROWS + row] = l;
             split4(f1, h, l); a_hi[(kg0 + 1) * FT_ROWS + row] = h; a_lo[(kg0 + 1) * FT_ROWS + row] = l;
             split4(f2, h, l); a_hi[(kg0 + 2) * FT_ROWS + row] = h; a_lo[(kg0 + 2) * FT_ROWS + row] = l;
-        }
-        if (is_x) { cp_async_wait<1>(); ++xq; }                           // the next x chunk has landed (this thread's part)
-        fence_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            mbar_wait(&bar_full[sb], (g / 3) & 1);
+            if (rec) p.dbgbuf[g * 8 + 6] = clock64();
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_afull[sa]);
+            if (rec) p.dbgbuf[g * 8 + 7] = clock64();
+            ++g;
+        };
+        auto wait_all_mma = [&]() {                                       // MMAs of the last produced chunk (hence all)
+            const unsigned gl = g - 1;
+            mbar_wait(&bar_done[gl & 1], (gl >> 1) & 1);
             tc_fence_after();
-            const uint32_t b_hi = smem_u32(smem + FT_OFF_B + sb * FT_BX_BYTES), b_lo = b_hi + FT_KG * ncols * 16;
-            issue_3xtf32(taddr + dcol, smem_u32(a_hi), smem_u32(a_lo), FT_ROWS, b_hi, b_lo, ncols, FT_KK / 8,
-                         make_idesc_tf32(128, ncols), !fresh);
-            umma_commit(&bar_done[sa]);
-        }
-        ++g;
-    };
-    auto wait_all_mma = [&]() {                                           // MMAs of the last issued chunk (hence all)
-        const unsigned gl = g - 1;
-        mbar_wait(&bar_done[gl & 1], (gl >> 1) & 1);
-        tc_fence_after();
-    };
-
-    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
-    const int hf = warp >> 2;                                            // which column half this warp reads
-    const size_t ro = ((size_t)b_ * N + n_);
-    for (int t = 0; t < p.T; ++t) {
-        const float* hprev = (t == 0) ? p.h0 : p.hseq + (size_t)(t - 1) * p.B * NH;
-        float* hout = p.hseq + (size_t)t * p.B * NH;
-        float* ruc = p.ruc + (size_t)t * p.B * NH * 3;
-        // ---- X phase -----------------------------------------------------------------------------------------
-        for (int i = 0; i < nxc; ++i) {
-            const float* xs = reinterpret_cast<const float*>(smem + FT_OFF_X + (xq % 3) * FT_XSLOT);
-            chunk(xs, FT_XLD, 0, min(FT_CC, fin - i * FT_CC), 192, 0, i == 0, true);
-        }
-        // ---- gate: recurrent part -------------------------------------------------------------------------------
-        for (int i = 0; i < nhc; ++i) chunk(ZH, FT_ZLD, i * FT_CC, FT_CC, 128, 0, false, false);
-        wait_all_mma();
-        // epilogue 1: warps 0-3 -> r (cols 0..63), warps 4-7 -> u (cols 64..127); thread = row
-        for (int cb = 0; cb < FT_H; cb += 32) {
-            float v[32];
-            tmem_ld32(taddr + lane_base + hf * FT_H + cb, v);
-            if (rvalid) {
+        };
+        const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
+        const int hf = warp >> 2;                                        // which column half this warp reads
+        // ---- warp-private staging tile (lives in the A stages, which are idle during the epilogues) -------------
+        // [32 rows][36 floats]; lane l owns row l when it exchanges with registers, and rows (l>>3)+4i, float4 l&7
+        // when it exchanges with global memory
+        float* stg = reinterpret_cast<float*>(smem + FT_OFF_A) + warp * (32 * 36);
+        const int rq = lane >> 3, f4 = lane & 7;
+        size_t grow[8];                                                   // (b*N + n) of the rows this lane moves, or ~0
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = sigmoidf_(v[j] + sbias[hf * FT_H + cb + j]);
-                float4* q = reinterpret_cast<float4*>(ruc + ro * 3 * FT_H + hf * FT_H + cb);
+        for (int i = 0; i < 8; ++i) {
+            const int r = 32 * (warp & 3) + rq + 4 * i;
+            const int s = r / NP, n = r - s * NP, b = b0 + s;
+            grow[i] = (s < FT_SB && n < N && b < p.B) ? ((size_t)b * N + n) : ~(size_t)0;
+        }
+        auto stage_put = [&](const float (&v)[32]) {
+            __syncwarp();
+            float4* d = reinterpret_cast<float4*>(stg + lane * 36);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) q[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                if (hf == 0) {                                            // ZH <- r * h
+            for (int j = 0; j < 8; ++j) d[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            __syncwarp();
+        };
+        auto stage_get = [&](float (&v)[32]) {
+            __syncwarp();
+            const float4* d = reinterpret_cast<const float4*>(stg + lane * 36);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float4 q = d[j]; v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w; }
+            __syncwarp();
+        };
+        auto stage_to_global = [&](float* base, int ld, int col0) {      // rows x 32 columns -> base[(b*N+n)*ld + col0 ..]
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (grow[i] != ~(size_t)0)
+                    *reinterpret_cast<float4*>(base + grow[i] * ld + col0 + 4 * f4) =
+                        *reinterpret_cast<const float4*>(stg + (rq + 4 * i) * 36 + 4 * f4);
+        };
+        auto global_to_stage = [&](const float* base, int ld, int col0) {
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (grow[i] != ~(size_t)0) q = __ldcg(reinterpret_cast<const float4*>(base + grow[i] * ld + col0 + 4 * f4));
+                *reinterpret_cast<float4*>(stg + (rq + 4 * i) * 36 + 4 * f4) = q;
+            }
+        };
+        const size_t ro = ((size_t)b_ * N + n_);
+        for (int t = 0; t < p.T; ++t) {
+            const float* hprev = (t == 0) ? p.h0 : p.hseq + (size_t)(t - 1) * p.B * NH;
+            float* hout = p.hseq + (size_t)t * p.B * NH;
+            float* ruc = p.ruc + (size_t)t * p.B * NH * 3;
+            // ---- X phase -------------------------------------------------------------------------------------
+            for (int i = 0; i < nxc; ++i, ++xq) {
+                produce(reinterpret_cast<const float*>(smem + FT_OFF_X + (xq % FT_XRING) * FT_XSLOT), FT_XLD, 0,
+                        min(FT_CC, fin - i * FT_CC), true);
+            }
+            // ---- gate: recurrent part ---------------------------------------------------------------------------
+            for (int i = 0; i < nhc; ++i) produce(ZH, FT_ZLD, i * FT_CC, FT_CC, false);
+            wait_all_mma();
+            // epilogue 1: warps 0-3 -> r (cols 0..63), warps 4-7 -> u (cols 64..127); thread = row.
+            // Global traffic goes through a warp-private staging tile so that every warp instruction moves
+            // whole 128-byte lines (4 rows x 8 float4) instead of 32 scattered 16-byte pieces.
+            for (int cb = 0; cb < FT_H; cb += 32) {
+                float v[32];
+                tmem_ld32(taddr + lane_base + hf * FT_H + cb, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fast_sigmoid(v[j] + sbias[hf * FT_H + cb + j]);
+                stage_put(v);
+                if (rvalid && hf == 0) {                                  // ZH <- r * h
                     float4* z4 = reinterpret_cast<float4*>(ZH + row * FT_ZLD + cb);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -284,56 +421,51 @@ __global__ void __launch_bounds__(NT, 1) seq_fwd_tc_kernel(const FwdTcParams p) 
                         z4[j] = z;
                     }
                 }
+                stage_to_global(ruc, 3 * FT_H, hf * FT_H + cb);
             }
-        }
-        tc_fence_before();
-        __syncthreads();
-        // ---- candidate: recurrent part ----------------------------------------------------------------------------
-        for (int i = 0; i < nhc; ++i) chunk(ZH, FT_ZLD, i * FT_CC, FT_CC, 64, 128, false, false);
-        wait_all_mma();
-        {   // epilogue 2: 64 columns, each warp half takes 32; all global loads first, then math, then stores
-            float v[32], u[32], hp[32];
-            if (rvalid) {
-                const float4* uq = reinterpret_cast<const float4*>(ruc + ro * 3 * FT_H + FT_H + hf * 32);
-                const float4* hq = reinterpret_cast<const float4*>(hprev + ro * FT_H + hf * 32);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 a = __ldcg(uq + j), b = __ldcg(hq + j);
-                    u[4 * j] = a.x; u[4 * j + 1] = a.y; u[4 * j + 2] = a.z; u[4 * j + 3] = a.w;
-                    hp[4 * j] = b.x; hp[4 * j + 1] = b.y; hp[4 * j + 2] = b.z; hp[4 * j + 3] = b.w;
-                }
-            }
-            tmem_ld32(taddr + lane_base + 128 + hf * 32, v);
-            if (rvalid) {
+            tc_fence_before();
+            producer_barrier();                                           // r*h of every row is visible
+            // ---- candidate: recurrent part ------------------------------------------------------------------------
+            for (int i = 0; i < nhc; ++i) produce(ZH, FT_ZLD, i * FT_CC, FT_CC, false);
+            wait_all_mma();
+            {   // epilogue 2: 64 columns, each warp half takes 32 (same staged, line-sized global traffic)
+                float v[32], u[32], hp[32];
+                global_to_stage(ruc, 3 * FT_H, FT_H + hf * 32);
+                stage_get(u);
+                global_to_stage(hprev, FT_H, hf * 32);
+                stage_get(hp);
+                tmem_ld32(taddr + lane_base + 128 + hf * 32, v);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_epi);                     // TMEM is free for the next step's MMAs
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float pre = v[j] + sbias[2 * FT_H + hf * 32 + j];
-                    const float cv = (p.act == 0) ? tanhf(pre) : fmaxf(pre, 0.f);
+                    const float cv = (p.act == 0) ? fast_tanh(pre) : fmaxf(pre, 0.f);
                     v[j] = cv;
                     u[j] = u[j] * hp[j] + (1.f - u[j]) * cv;               // h_new
                 }
-                float4* cq = reinterpret_cast<float4*>(ruc + ro * 3 * FT_H + 2 * FT_H + hf * 32);
-                float4* ho = reinterpret_cast<float4*>(hout + ro * FT_H + hf * 32);
-                float4* z4 = reinterpret_cast<float4*>(ZH + row * FT_ZLD + hf * 32);
+                stage_put(v);
+                stage_to_global(ruc, 3 * FT_H, 2 * FT_H + hf * 32);
+                stage_put(u);
+                if (rvalid) {
+                    float4* z4 = reinterpret_cast<float4*>(ZH + row * FT_ZLD + hf * 32);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    cq[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                    const float4 hn = make_float4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
-                    ho[j] = hn;
-                    z4[j] = hn;
+                    for (int j = 0; j < 8; ++j) z4[j] = make_float4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
                 }
+                stage_to_global(hout, FT_H, hf * 32);
             }
+            producer_barrier();                                           // h_t of every row is visible
         }
-        tc_fence_before();
-        __syncthreads();
     }
-    cp_async_wait<0>();
+    tc_fence_before();
+    __syncthreads();
     if (warp == 0) tmem_dealloc<256>(taddr);
 }
 
 size_t seq_fwd_tc_wimg_bytes(int fin) { return ft_wimg_bytes(fin); }
 bool seq_fwd_tc_supported(int N, int fin, int H, int M, int smem_limit) {
-    return H == FT_H && M == FT_M && N <= NP && fin % 4 == 0 && FT_SMEM + 1088 <= smem_limit;
+    return H == FT_H && M == FT_M && N <= NP && fin % 4 == 0 && FT_SMEM + 2304 <= smem_limit;
 }
 
 cudaError_t launch_seq_fwd_tc(int B, int T, int N, int fin, int act, const float* x, long long xs_t,
@@ -345,11 +477,13 @@ cudaError_t launch_seq_fwd_tc(int B, int T, int N, int fin, int act, const float
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     FwdTcParams p;
+    { const char* e = getenv("DCGRU_DBG"); p.dbg = e ? atoi(e) : 0; }
     p.B = B; p.T = T; p.N = N; p.fin = fin; p.act = act; p.x = x; p.xs_t = xs_t; p.xs_b = xs_b; p.h0 = h0; p.P = P;
     p.bg = bg; p.bc = bc; p.wimg = wimg; p.hseq = hseq; p.ruc = ruc;
+    p.dbgbuf = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(wimg) + ((ft_wimg_bytes(fin) + 255) / 256) * 256);
     e = cudaFuncSetAttribute(seq_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
     if (e != cudaSuccess) return e;
-    seq_fwd_tc_kernel<<<(B + FT_SB - 1) / FT_SB, NT, FT_SMEM, st>>>(p);
+    seq_fwd_tc_kernel<<<(B + FT_SB - 1) / FT_SB, FT_THREADS, FT_SMEM, st>>>(p);
     return cudaGetLastError();
 }
 

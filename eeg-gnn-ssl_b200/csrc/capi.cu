@@ -371,7 +371,7 @@ static size_t enc_bwd_ws(const dcgru_cell_desc* d, int B, int T, bool carve, voi
     float* e = c.take((size_t)T * B * d->num_nodes * 3 * H);
     float* f = c.take((size_t)ns * CM * 3 * H);
     float* g = c.take((size_t)ns * 3 * H);
-    float* pt = c.take(dw_tc_pt_floats(B, M));
+    float* pt = c.take(((dw_tc_pt_floats(B, M) + 63) / 64) * 64 + seq_bwd_tc_wimg_bytes() / 4 + 64);   // P^T + bwd weight image
     if (carve) { *WgT = a; *WcT = b; *dA = e; *part = f; *partb = g; *nsplit = ns; *njobs = nj; *ptbuf = pt; }
     return c.off;
 }
@@ -411,7 +411,18 @@ int dcgru_encoder_layer_bwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
     p.cell[0] = CellWT{WgT, WcT, fin};
     p.P = P; p.h0 = h0; p.hseq = h_seq; p.ruc = ruc; p.d_hseq = d_hseq; p.d_hlast = d_hlast;
     p.dx = dx; p.dh0 = dh0; p.dA = dA;
-    LAUNCH("seq_bwd", launch_seq_bwd(p, pl.SB, pl.smem, st));
+    if (tc_enabled() && seq_bwd_tc_supported(d->num_nodes, H, M, devinfo().smem)) {
+        // recurrent part on the tensor cores; the input gradient is not recurrent -> bulk pass over all steps
+        float* wimg_b = ptbuf + ((dw_tc_pt_floats(batch, M) + 63) / 64) * 64;
+        LAUNCH("seq_bwd_tc", launch_seq_bwd_tc(batch, seq_len, d->num_nodes, fin, d->activation, h0, h_seq, ruc, P,
+                                               w->Wg, w->Wc, d_hseq, d_hlast, wimg_b, dh0, dA, st));
+        if (dx) {
+            p.mode = 2;
+            LAUNCH("dx", launch_seq_bwd(p, pl.SB, pl.smem, st));
+        }
+    } else {
+        LAUNCH("seq_bwd", launch_seq_bwd(p, pl.SB, pl.smem, st));
+    }
     // bulk weight gradients
     q.B = batch; q.T = seq_len; q.N = d->num_nodes; q.H = H; q.M = M; q.nsplit = nsplit; q.mode = 0;
     q.layer = 0; q.ncell = 1; q.fin = fin; q.Fo = 0;

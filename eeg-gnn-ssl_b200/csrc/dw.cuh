@@ -58,5 +58,10 @@ bool seq_fwd_tc_supported(int N, int fin, int H, int M, int smem_limit);
 cudaError_t launch_seq_fwd_tc(int B, int T, int N, int fin, int act, const float* x, long long xs_t, long long xs_b,
                               const float* h0, const float* P, const float* Wg, const float* bg, const float* Wc,
                               const float* bc, float* wimg, float* hseq, float* ruc, cudaStream_t st);
+size_t seq_bwd_tc_wimg_bytes();
+bool seq_bwd_tc_supported(int N, int H, int M, int smem_limit);
+cudaError_t launch_seq_bwd_tc(int B, int T, int N, int fin, int act, const float* h0, const float* hseq, const float* ruc,
+                              const float* P, const float* Wg, const float* Wc, const float* d_hseq, const float* d_hlast,
+                              float* wimg, float* dh0, float* dA, cudaStream_t st);
 cudaError_t launch_tc_selftest(const float* A, const float* B, float* C, int N, int K, cudaStream_t st);
 }  // namespace dcgru

@@ -259,7 +259,26 @@ __global__ void __launch_bounds__(NT, 1) seq_bwd_kernel(const BwdParams p) {
     __syncthreads();
 
     const size_t NH = (size_t)N * H;
-    if (p.mode == 0) {
+    if (p.mode == 2) {
+        // bulk input gradient (not recurrent): grid.y = step.  dX[t] = diffT(dA[t] @ [Wg_x | Wc_x]^T) with the
+        // dA the recurrent kernel (tensor-core or this one) stored.
+        const int t = blockIdx.y;
+        const int fin = p.cell[0].fin, M = p.M, CM = (fin + H) * M, H3 = 3 * H;
+        const float* dA = p.dA + (size_t)t * p.B * NH * 3;
+        for (int idx = threadIdx.x; idx < R * H3; idx += NT) {
+            int row = idx / H3, o = idx - row * H3;
+            int s = row / NP, n = row - s * NP, b = c.b0 + s;
+            c.DA[o * RLD + row] = (n < N && b < p.B) ? dA[((size_t)b * N + n) * H3 + o] : 0.f;
+        }
+        __syncthreads();
+        WTSrc ws{p.cell[0].WgT, 2 * H, p.cell[0].WcT, CM};
+        float* dx = p.dx + (size_t)t * p.B * N * fin;
+        for (int z0 = 0; z0 < fin; z0 += c.zcb) {
+            int ncolz = min(c.zcb, fin - z0);
+            gemm_bwd<SB>(c, c.DA, 3 * H, ws, z0 * M, ncolz * M);
+            diff_t<SB, 2>(c, ncolz, dx, fin, z0);
+        }
+    } else if (p.mode == 0) {
         const int fin = p.cell[0].fin;
         for (int t = p.T - 1; t >= 0; --t) {
             if (t == p.T - 1) dh_load<SB>(c, p.d_hlast, false);
@@ -338,7 +357,7 @@ __global__ void __launch_bounds__(NT, 1) seq_bwd_kernel(const BwdParams p) {
 }
 
 cudaError_t launch_seq_bwd(const BwdParams& p, int SB, int smem_bytes, cudaStream_t st) {
-    int grid = (p.B + SB - 1) / SB;
+    dim3 grid((p.B + SB - 1) / SB, p.mode == 2 ? p.T : 1);
 #define CASE(sb)                                                                                    \
     if (SB == sb) {                                                                                 \
         auto k = seq_bwd_kernel<sb>;                                                                \

@@ -91,3 +91,26 @@ def test_tc_forward_matches_simt(dev, monkeypatch, B, T, L):
     for a, b in zip(outs["0"], outs["1"]):
         e = float((a - b).abs().max() / b.abs().max())
         assert e < 2e-5, e
+
+
+@pytest.mark.parametrize("B,T,L", [(13, 5, 2), (6, 2, 1), (150, 3, 2)])
+def test_tc_backward_matches_simt(dev, monkeypatch, B, T, L):
+    """seq_bwd_tc_kernel + bulk dX against the fp32 FMA BPTT kernel (all gradients)"""
+    from eeg_gnn_ssl_b200.model.model import DCRNNEncoder
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("DCGRU_DISABLE_TC", flag)
+        g = torch.Generator().manual_seed(11)
+        torch.manual_seed(11)
+        enc = DCRNNEncoder(100, 2, 64, 19, L, dcgru_activation="tanh").to(dev)
+        x = torch.randn(T, B, 19, 100, generator=g).to(dev)
+        sup = [torch.softmax(2 * torch.randn(B, 19, 19, generator=g), -1).to(dev)]
+        h0 = (0.3 * torch.randn(L, B, 19 * 64, generator=g)).to(dev).requires_grad_(True)
+        w = torch.randn(T, B, 19 * 64, generator=g).to(dev)
+        wl = torch.randn(L, B, 19 * 64, generator=g).to(dev)
+        oh, top = enc(x, h0, sup)
+        ((top * w).sum() + (oh * wl).sum()).backward()
+        outs[flag] = [h0.grad.cpu().double()] + [p.grad.cpu().double() for p in enc.parameters()]
+    for i, (a, b) in enumerate(zip(outs["0"], outs["1"])):
+        e = float((a - b).abs().max() / b.abs().max())
+        assert e < 3e-5, (i, e)

@@ -371,7 +371,7 @@ static size_t enc_bwd_ws(const dcgru_cell_desc* d, int B, int T, bool carve, voi
     float* e = c.take((size_t)T * B * d->num_nodes * 3 * H);
     float* f = c.take((size_t)ns * CM * 3 * H);
     float* g = c.take((size_t)ns * 3 * H);
-    float* pt = c.take(((dw_tc_pt_floats(B, M) + 63) / 64) * 64 + seq_bwd_tc_wimg_bytes() / 4 + 64);   // P^T + bwd weight image
+    float* pt = c.take(((dw_tc_pt_floats(B, M) + 63) / 64) * 64 + 2 * (seq_bwd_tc_wimg_bytes() / 4 + 64));   // P^T + BPTT weight image + dX weight image
     if (carve) { *WgT = a; *WcT = b; *dA = e; *part = f; *partb = g; *nsplit = ns; *njobs = nj; *ptbuf = pt; }
     return c.off;
 }
@@ -417,8 +417,13 @@ int dcgru_encoder_layer_bwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
         LAUNCH("seq_bwd_tc", launch_seq_bwd_tc(batch, seq_len, d->num_nodes, fin, d->activation, h0, h_seq, ruc, P,
                                                w->Wg, w->Wc, d_hseq, d_hlast, wimg_b, dh0, dA, st));
         if (dx) {
-            p.mode = 2;
-            LAUNCH("dx", launch_seq_bwd(p, pl.SB, pl.smem, st));
+            if (fin == 64) {
+                float* wimg_x = wimg_b + seq_bwd_tc_wimg_bytes() / 4 + 64;
+                LAUNCH("dx_tc", launch_dx_tc(batch, seq_len, d->num_nodes, P, w->Wg, w->Wc, dA, wimg_x, dx, st));
+            } else {
+                p.mode = 2;
+                LAUNCH("dx", launch_seq_bwd(p, pl.SB, pl.smem, st));
+            }
         }
     } else {
         LAUNCH("seq_bwd", launch_seq_bwd(p, pl.SB, pl.smem, st));

@@ -63,5 +63,7 @@ bool seq_bwd_tc_supported(int N, int H, int M, int smem_limit);
 cudaError_t launch_seq_bwd_tc(int B, int T, int N, int fin, int act, const float* h0, const float* hseq, const float* ruc,
                               const float* P, const float* Wg, const float* Wc, const float* d_hseq, const float* d_hlast,
                               float* wimg, float* dh0, float* dA, cudaStream_t st);
+cudaError_t launch_dx_tc(int B, int T, int N, const float* P, const float* Wg, const float* Wc, const float* dA,
+                         float* wimg, float* dx, cudaStream_t st);
 cudaError_t launch_tc_selftest(const float* A, const float* B, float* C, int N, int K, cudaStream_t st);
 }  // namespace dcgru

@@ -15,6 +15,8 @@
 // Roles: warps 0-7 elementwise + A tiles + diffT, warp 8 MMA issue, warp 9 TMA weight loads (12 chunk blocks
 // per step, pre-split / pre-tiled by pack_w_bwd_kernel, 3-slot ring).  Synchronisation is mbarrier-only
 // apart from two 128-thread named barriers around the diffT staging planes.
+#include <cstring>
+
 #include "common.cuh"
 #include "dw.cuh"
 #include "tc_common.cuh"
@@ -69,8 +71,30 @@ __global__ void pack_w_bwd_kernel(const float* Wg, const float* Wc, int fin, flo
     }
 }
 
+// weight image of the input-gradient GEMM (fin == 64): 12 blocks, o = 16*blk .. over [Wg_x | Wc_x] columns
+__global__ void pack_w_dx_kernel(const float* Wg, const float* Wc, float* img) {
+    const int blk = blockIdx.x;
+    float4* hi = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(img) + (size_t)blk * BT_B_SLOT);
+    float4* lo = hi + BT_KG * BT_NCOL;
+    for (int idx = threadIdx.x; idx < BT_KG * BT_NCOL; idx += blockDim.x) {
+        const int kg = idx / BT_NCOL, kk = idx - kg * BT_NCOL;               // kk: x-part rows 0..191 (fin = 64)
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int o = 16 * blk + 4 * kg + e;
+            v[e] = (o < 2 * BT_H) ? Wg[(size_t)kk * 2 * BT_H + o] : Wc[(size_t)kk * BT_H + o - 2 * BT_H];
+        }
+        float4 h, l;
+        split4(make_float4(v[0], v[1], v[2], v[3]), h, l);
+        hi[idx] = h;
+        lo[idx] = l;
+    }
+}
+
 struct BwdTcParams {
     int B, T, N, act;
+    int mode;                   // 0: BPTT (B1, B2), 1: bulk input gradient dX[t] = diffT(dA[t] @ [Wg_x|Wc_x]^T), fin == 64
+    float* dx;                  // mode 1: (T, B, N*64)
     const float* h0;
     const float* hseq;
     const float* ruc;
@@ -150,11 +174,11 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
                 mbar_wait(&bar_afull[sa], (g >> 2) & 1);
                 if (step > 0) {                                           // the previous step's reads of D are done
                     if (q == 0) mbar_wait(&bar_d1free, (step - 1) & 1);
-                    if (q == 4) mbar_wait(&bar_d2free, (step - 1) & 1);
+                    if (q == 4 && p.mode == 0) mbar_wait(&bar_d2free, (step - 1) & 1);
                 }
                 tc_fence_after();
-                const uint32_t d = taddr + (q < 4 ? BT_D1 : BT_D2);
-                uint32_t acc = (q == 0 || q == 4) ? 0u : 1u;
+                const uint32_t d = taddr + ((q < 4 || p.mode == 1) ? BT_D1 : BT_D2);
+                uint32_t acc = (q == 0 || (q == 4 && p.mode == 0)) ? 0u : 1u;
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     const uint64_t ah = dA_desc[sa][k][0], al = dA_desc[sa][k][1];
@@ -332,6 +356,34 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
             }
             __syncwarp();
         }
+        if (p.mode == 1) {
+            // ---- bulk input gradient: one GEMM (K = 192: dA_r | dA_u | dA_c) + diffT per step, steps independent -----
+            for (int t = 0; t < p.T; ++t) {
+                const float* dA = p.dA + (size_t)t * p.B * NH * 3;
+                const unsigned g0 = g;
+                float w0[32];
+#pragma unroll
+                for (int part = 0; part < 3; ++part) {
+                    tile_load(tile0, dA, 3 * BT_H, part * BT_H + 32 * hf);
+                    cp_async_commit();
+                    cp_async_wait<0>();
+                    __syncwarp();
+                    tile_get(tile0, w0);
+                    __syncwarp();
+                    put_chunk(w0, 0, 0); put_chunk(w0, 0, 1); put_chunk(w0, 1, 0); put_chunk(w0, 1, 1);
+                }
+                wait_chunk(g0 + 11);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) w0[j] = 0.f;
+                diff_t(BT_D1, w0);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) bt_arrive(&bar_d1free);
+                prod_barrier();                                           // planes idle: tile 0 may be reused
+                tile_store(tile0, w0, p.dx + (size_t)t * p.B * NH, BT_H, 32 * hf);
+                prod_barrier();
+            }
+        } else
         for (int t = p.T - 1; t >= 0; --t) {
             const float* hprev = (t == 0) ? p.h0 : p.hseq + (size_t)(t - 1) * p.B * NH;
             const float* ruc = p.ruc + (size_t)t * p.B * NH * 3;
@@ -432,7 +484,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
             prod_barrier();                                             // planes idle before the next step's IO tiles
         }
         // ---- dh0 ----------------------------------------------------------------------------------------------------
-        {
+        if (p.mode == 0) {
             float v[32];
             const float4* z4 = reinterpret_cast<const float4*>(DH + row * BT_DLD + 32 * hf);
 #pragma unroll
@@ -458,8 +510,24 @@ cudaError_t launch_seq_bwd_tc(int B, int T, int N, int fin, int act, const float
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     BwdTcParams p;
+    p.mode = 0; p.dx = nullptr;
     p.B = B; p.T = T; p.N = N; p.act = act; p.h0 = h0; p.hseq = hseq; p.ruc = ruc; p.P = P;
     p.d_hseq = d_hseq; p.d_hlast = d_hlast; p.wimg = wimg; p.dh0 = dh0; p.dA = dA;
+    e = cudaFuncSetAttribute(seq_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM);
+    if (e != cudaSuccess) return e;
+    seq_bwd_tc_kernel<<<(B + BT_SB - 1) / BT_SB, BT_THREADS, BT_SMEM, st>>>(p);
+    return cudaGetLastError();
+}
+
+// dX for an encoder layer whose input is the hidden sequence of the layer below (fin == H == 64)
+cudaError_t launch_dx_tc(int B, int T, int N, const float* P, const float* Wg, const float* Wc, const float* dA,
+                         float* wimg, float* dx, cudaStream_t st) {
+    pack_w_dx_kernel<<<BT_CHUNKS, 256, 0, st>>>(Wg, Wc, wimg);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    BwdTcParams p;
+    memset(&p, 0, sizeof p);
+    p.mode = 1; p.B = B; p.T = T; p.N = N; p.P = P; p.wimg = wimg; p.dA = const_cast<float*>(dA); p.dx = dx;
     e = cudaFuncSetAttribute(seq_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM);
     if (e != cudaSuccess) return e;
     seq_bwd_tc_kernel<<<(B + BT_SB - 1) / BT_SB, BT_THREADS, BT_SMEM, st>>>(p);

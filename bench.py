@@ -326,29 +326,57 @@ def main():
         nm, cnt, ms = ln.split()
         kern[nm] = (int(cnt), float(ms))
     launches = sum(c for c, _ in kern.values()) // args.steps
-    per_layer = flops_per_clip_fwd(cfg)
-    fwd_flops = sum(per_layer) * cfg["B"]                    # per rank per step; seq_bwd and dw do as much each
-    dom = max(("seq_fwd", "seq_bwd", "dw"), key=lambda k: kern.get(k, (0, 0.0))[1])
+    # algorithmic FLOPs per launch of each kernel family (as-written count, SURVEY 8(d) / DESIGN.md section 5):
+    #   forward layer l            : T*B*F_cell(C_l)
+    #   BPTT layer l (dH/dA side)  : the recurrent (h) columns of F_cell;  dX kernel: the input (x) columns
+    #   weight gradient layer l    : T*B*F_cell(C_l)
+    s_ = 2 if cfg["filter_type"] == "dual_random_walk" else 1
+    m_ = s_ * cfg["K"] + 1
+    tb = cfg["T"] * cfg["B"]
+    def f_cols(cols):          # diffusion of `cols` columns twice-as-written + projection of cols*M rows onto 3H outputs
+        return 2 * (s_ * cfg["K"] * 2 * N_NODES * N_NODES * cols) + 2 * N_NODES * (cols * m_) * 3 * cfg["H"]
+    fam = {}
+    for l in range(cfg["L"]):
+        fin_l = F_IN if l == 0 else cfg["H"]
+        full, hpart, xpart = tb * f_cols(fin_l + cfg["H"]), tb * f_cols(cfg["H"]), tb * f_cols(fin_l)
+        for nm in ("seq_fwd", "seq_fwd_tc", "dw", "dw_tc"):
+            fam.setdefault(nm, []).append(full)
+        fam.setdefault("seq_bwd", []).append(full if l > 0 else hpart)
+        fam.setdefault("seq_bwd_tc", []).append(hpart)
+        if l > 0:
+            fam.setdefault("dx_tc", []).append(xpart)
+            fam.setdefault("dx", []).append(xpart)
+    big = [k for k in fam if k in kern]
+    dom = max(big, key=lambda k: kern[k][1])
     dcount, dms = kern[dom]
-    # every launch of the dominant kernel handles one layer: average FLOPs per launch = fwd_flops / L
-    achieved = (fwd_flops / cfg["L"]) / (dms / dcount * 1e-3) / 1e12
+    flops_per_launch = sum(fam[dom]) / len(fam[dom])
+    achieved = flops_per_launch / (dms / dcount * 1e-3) / 1e12
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    traffic = None
+    try:                                   # dram bytes per launch of the dominant kernel, from the committed ncu capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))
+        traffic = tr.get(dom)
+    except Exception:
+        pass
+    total_alg = sum(sum(fam[k]) for k in big)
+    total_ms = sum(kern[k][1] for k in big) / args.steps
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback",
-                "note": "generic path computes in fp32 on the FMA pipe (fp32 SIMT peak ~72 TFLOP/s/GPU); "
-                        "FLOPs are the as-written count of SURVEY 8(d) / DESIGN.md",
+                "note": "kernels compute in fp32-equivalent 3xTF32 on tcgen05 (3 TF32 MMAs per product: the attainable "
+                        "peak of this arithmetic is ~1/6 of the bf16 peak); FLOPs are the as-written count of SURVEY 8(d)",
+                "all_kernels_tflops": total_alg / (total_ms * 1e-3) / 1e12,
                 "kernel_ms_per_step": {k: v[1] / args.steps for k, v in kern.items()}}
 
     line = {"metric": "EEG clips/sec (fwd+bwd, T=60, N=19)", "value": value, "unit": "clips/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (3xTF32 on tcgen05, fp32 accumulate)", "data": "synthetic",
             "config": {"workload": cfg["name"], "global_batch": clips, "seq_len": cfg["T"],
                        "parallelism": f"dp{world}", "l2": "inputs larger than L2 (x = 233 MB/rank, saved "
                        "activations ~1.2 GB/rank are rewritten every step)",

@@ -114,3 +114,39 @@ def test_tc_backward_matches_simt(dev, monkeypatch, B, T, L):
     for i, (a, b) in enumerate(zip(outs["0"], outs["1"])):
         e = float((a - b).abs().max() / b.abs().max())
         assert e < 3e-5, (i, e)
+
+
+def test_tc_path_full_size_accuracy(dev, monkeypatch):
+    """BASELINE config 2 size (B=512, T=60, 2 layers): the tensor-core path against the fp32 FMA path.
+    This is where accumulation length matters (dW sums 583 680 rows; TMEM is flushed every 16 chunks)."""
+    from eeg_gnn_ssl_b200.model.model import DCRNNModel_classification
+    import types
+    from oracle.graph_oracle import scaled_laplacian
+    from tests.conftest import load_golden
+    _, a = load_golden("graph_supports")
+    lap = torch.tensor(scaled_laplacian(a["dist_adj"]).astype(np.float32), device=dev)
+    args = types.SimpleNamespace(num_nodes=19, num_rnn_layers=2, rnn_units=64, input_dim=100, output_dim=100,
+                                 max_diffusion_step=2, dcgru_activation="tanh", filter_type="laplacian", dropout=0.0,
+                                 cl_decay_steps=3000, use_curriculum_learning=False)
+    B, T = 512, 60
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("DCGRU_DISABLE_TC", flag)
+        torch.manual_seed(123)
+        model = DCRNNModel_classification(args, 1).to(dev)
+        g = torch.Generator().manual_seed(5)
+        x = torch.randn(B, T, 19, 100, generator=g).to(dev)
+        y = (torch.rand(B, generator=g) > 0.5).float().to(dev)
+        sl = torch.full((B,), T, dtype=torch.long, device=dev)
+        logits = model(x, sl, [lap.unsqueeze(0).expand(B, 19, 19).contiguous()])
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(logits.view(-1), y)
+        loss.backward()
+        res[flag] = (logits.detach().cpu().double(), {n: p.grad.cpu().double() for n, p in model.named_parameters()})
+    e = float((res["0"][0] - res["1"][0]).abs().max() / res["1"][0].abs().max())
+    print(f"logits TC vs fp32: {e:.2e}")
+    assert e < 1e-4
+    for n in res["1"][1]:
+        a_, b_ = res["0"][1][n], res["1"][1][n]
+        e = float((a_ - b_).abs().max() / b_.abs().max())
+        print(f"{n}: {e:.2e}")
+        assert e < 1e-4, (n, e)

@@ -128,7 +128,8 @@ class DCRNNModel_classification(nn.Module):
     def forward(self, input_seq, seq_lengths, supports):
         """input_seq (B,T,N,Fin), seq_lengths (B,) -> pooled logits (B, num_classes)."""
         b = input_seq.shape[0]
-        h0 = self.encoder.init_hidden(b).to(input_seq.device)
+        # zeros created on the device (init_hidden() keeps the reference's CPU-tensor contract for callers that use it)
+        h0 = torch.zeros(self.num_rnn_layers, b, self.num_nodes * self.rnn_units, device=input_seq.device)
         _, top = self.encoder(input_seq.transpose(0, 1), h0, supports)          # (T,B,N*H)
         idx = (seq_lengths.to(top.device).long() - 1).view(1, b, 1).expand(1, b, top.shape[2])
         last = top.gather(0, idx).squeeze(0).view(b, self.num_nodes, self.rnn_units)
@@ -159,7 +160,7 @@ class DCRNNModel_nextTimePred(nn.Module):
     def forward(self, encoder_inputs, decoder_inputs, supports, batches_seen=None):
         """(B,T,N,Fin), (B,To,N,Fo) -> predictions (B,To,N,Fo)."""
         b, to_len, n, _ = decoder_inputs.shape
-        h0 = self.encoder.init_hidden(b).to(encoder_inputs.device)
+        h0 = torch.zeros(self.num_rnn_layers, b, self.num_nodes * self.rnn_units, device=encoder_inputs.device)
         context, _ = self.encoder(encoder_inputs.transpose(0, 1), h0, supports)
         ratio = None
         if self.training and self.use_curriculum_learning and batches_seen is not None:

@@ -377,7 +377,7 @@ def main():
     for l in range(cfg["L"]):
         fin_l = F_IN if l == 0 else cfg["H"]
         full, hpart, xpart = tb * f_cols(fin_l + cfg["H"]), tb * f_cols(cfg["H"]), tb * f_cols(fin_l)
-        for nm in ("seq_fwd", "seq_fwd_tc", "dw", "dw_tc"):
+        for nm in ("seq_fwd", "seq_fwd_tc", "dw", "dw_tc", "dw_mm"):
             fam.setdefault(nm, []).append(full)
         fam.setdefault("seq_bwd", []).append(full if l > 0 else hpart)
         fam.setdefault("seq_bwd_tc", []).append(hpart)

@@ -8,9 +8,9 @@ LIB_PATH = os.path.join(_HERE, "lib", "libdcgru_b200.so")
 
 SYMBOLS = [
     "dcgru_version", "dcgru_last_error", "dcgru_graph_poly", "dcgru_corr_supports",
-    "dcgru_encoder_layer_fwd", "dcgru_encoder_layer_fwd_workspace", "dcgru_encoder_layer_bwd_workspace", "dcgru_encoder_layer_bwd",
+    "dcgru_encoder_layer_fwd", "dcgru_encoder_layer_gsave_bytes", "dcgru_encoder_layer_fwd_workspace", "dcgru_encoder_layer_bwd_workspace", "dcgru_encoder_layer_bwd",
     "dcgru_decoder_fwd_workspace", "dcgru_decoder_fwd", "dcgru_decoder_bwd_workspace", "dcgru_decoder_bwd",
-    "dcgru_timing_enable", "dcgru_timing_collect", "dcgru_tc_selftest",
+    "dcgru_timing_enable", "dcgru_timing_collect", "dcgru_tc_selftest", "dcgru_debug_encoder_bwd_offsets",
 ]
 
 MAX_LAYERS = 4
@@ -48,13 +48,15 @@ def lib():
     L.dcgru_last_error.restype = C.c_char_p
     L.dcgru_graph_poly.argtypes = [i32, i32, i32, i32, C.POINTER(vp), C.POINTER(i64), vp, vp]
     L.dcgru_corr_supports.argtypes = [i32, i32, i32, i32, vp, i64, i64, f32, f32, i32, vp, vp, vp, vp]
-    L.dcgru_encoder_layer_fwd.argtypes = [pd, i32, i32, vp, i64, i64, vp, vp, pp, vp, vp, vp, sz, vp]
+    L.dcgru_encoder_layer_fwd.argtypes = [pd, i32, i32, vp, i64, i64, vp, vp, pp, vp, vp, vp, sz, vp, sz, vp]
+    L.dcgru_encoder_layer_gsave_bytes.argtypes = [pd, i32, i32]
+    L.dcgru_encoder_layer_gsave_bytes.restype = sz
     L.dcgru_encoder_layer_fwd_workspace.argtypes = [pd, i32, i32]
     L.dcgru_encoder_layer_fwd_workspace.restype = sz
     L.dcgru_encoder_layer_bwd_workspace.argtypes = [pd, i32, i32]
     L.dcgru_encoder_layer_bwd_workspace.restype = sz
     L.dcgru_encoder_layer_bwd.argtypes = [pd, i32, i32, vp, i64, i64, vp, vp, pp, vp, vp, vp, vp, vp, vp, pg,
-                                          vp, sz, vp]
+                                          vp, sz, vp, sz, vp]
     L.dcgru_decoder_fwd_workspace.argtypes = [pd, i32, i32, i32]
     L.dcgru_decoder_fwd_workspace.restype = sz
     L.dcgru_decoder_fwd.argtypes = [pd, i32, i32, i32, vp, u64, vp, vp, pp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
@@ -63,10 +65,12 @@ def lib():
     L.dcgru_decoder_bwd.argtypes = [pd, i32, i32, i32, vp, u64, vp, vp, pp, vp, vp, vp, vp, vp, vp, vp, pg,
                                     vp, vp, vp, sz, vp]
     L.dcgru_tc_selftest.argtypes = [vp, vp, vp, i32, i32, vp]
+    L.dcgru_debug_encoder_bwd_offsets.argtypes = [pd, i32, i32, C.POINTER(sz)]
     L.dcgru_timing_enable.argtypes = [C.c_int]
     L.dcgru_timing_collect.argtypes = [C.c_char_p, sz]
     for name in SYMBOLS:
         if name not in ("dcgru_last_error", "dcgru_encoder_layer_bwd_workspace", "dcgru_encoder_layer_fwd_workspace",
+                        "dcgru_encoder_layer_gsave_bytes",
                         "dcgru_decoder_fwd_workspace", "dcgru_decoder_bwd_workspace"):
             getattr(L, name).restype = C.c_int
     _lib = L

@@ -319,6 +319,25 @@ int dcgru_corr_supports(int32_t batch, int32_t seq_len, int32_t num_nodes, int32
     return 0;
 }
 
+// operand image of the tensor-core forward kernel (0: the configuration has no such path)
+static size_t gsave_bytes_for(const dcgru_cell_desc* d, int B, int T) {
+    if (!tc_enabled()) return 0;
+    { const char* e = getenv("DCGRU_DISABLE_GSAVE"); if (e && e[0] == '1') return 0; }
+    const int M = Mof(d);
+    const DevInfo& di = devinfo();
+    if (!seq_fwd_tc_supported(d->num_nodes, d->input_dim, d->hid_dim, M, di.smem)) return 0;
+    if (!seq_bwd_tc_supported(d->num_nodes, d->hid_dim, M, di.smem)) return 0;
+    if (dw_mm_smem_bytes() + 2048 > di.smem) return 0;
+    DwmmParams q;
+    if (!dwmm_plan(d->input_dim, d->hid_dim, M, seq_tc_nslab(B, T), di.sms, &q)) return 0;
+    return seq_fwd_tc_gsave_bytes(B, T, d->input_dim);
+}
+
+size_t dcgru_encoder_layer_gsave_bytes(const dcgru_cell_desc* d, int32_t batch, int32_t seq_len) {
+    if (check_desc(d) || batch < 1 || seq_len < 1) return 0;
+    return gsave_bytes_for(d, batch, seq_len);
+}
+
 size_t dcgru_encoder_layer_fwd_workspace(const dcgru_cell_desc* d, int32_t batch, int32_t seq_len) {
     if (check_desc(d) || batch < 1 || seq_len < 1) return 0;
     return align_up(seq_fwd_tc_wimg_bytes(d->input_dim)) + 256 + 16384;   // + debug stamps (DCGRU_DBG & 4)
@@ -326,8 +345,8 @@ size_t dcgru_encoder_layer_fwd_workspace(const dcgru_cell_desc* d, int32_t batch
 
 int dcgru_encoder_layer_fwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq_len, const float* x,
                             int64_t x_stride_t, int64_t x_stride_b, const float* h0, const float* P,
-                            const dcgru_cell_params* w, float* h_seq, float* ruc, void* workspace,
-                            size_t workspace_bytes, void* stream) {
+                            const dcgru_cell_params* w, float* h_seq, float* ruc, void* gsave,
+                            size_t gsave_bytes, void* workspace, size_t workspace_bytes, void* stream) {
     if (check_desc(d)) return 1;
     if (batch < 1 || seq_len < 1) return fail("empty batch/sequence");
     if (!x || !h0 || !w || !h_seq || !w->Wg || !w->bg || !w->Wc || !w->bc) return fail("null pointer");
@@ -341,11 +360,18 @@ int dcgru_encoder_layer_fwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
     if (tc_enabled() && ruc && workspace && aligned16(workspace) &&
         workspace_bytes >= align_up(seq_fwd_tc_wimg_bytes(d->input_dim)) + 16384 &&
         seq_fwd_tc_supported(d->num_nodes, d->input_dim, d->hid_dim, M, devinfo().smem)) {
+        if (gsave) {
+            const size_t need = gsave_bytes_for(d, batch, seq_len);
+            if (need == 0) return fail("this configuration has no operand image: pass gsave = NULL");
+            if (gsave_bytes < need) return fail("gsave too small (%zu < %zu bytes)", gsave_bytes, need);
+            if (!aligned16(gsave)) return fail("gsave must be 16-byte aligned");
+        }
         LAUNCH("seq_fwd_tc", launch_seq_fwd_tc(batch, seq_len, d->num_nodes, d->input_dim, d->activation, x,
                                                x_stride_t, x_stride_b, h0, P, w->Wg, w->bg, w->Wc, w->bc,
-                                               (float*)workspace, h_seq, ruc, st));
+                                               (float*)workspace, h_seq, ruc, gsave, st));
         return 0;
     }
+    if (gsave) return fail("gsave given but the tensor-core forward path is not available for this call");
     FwdPlan pl;
     if (!plan_fwd(d->hid_dim, d->input_dim + d->hid_dim, M, batch, 0, &pl))
         return fail("no tiling fits shared memory (input_dim=%d hid=%d M=%d)", d->input_dim, d->hid_dim, M);
@@ -361,7 +387,8 @@ int dcgru_encoder_layer_fwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
 
 static size_t enc_bwd_ws(const dcgru_cell_desc* d, int B, int T, bool carve, void* ws, float** WgT, float** WcT,
                          float** dA, float** part, float** partb, int* nsplit, int* njobs, DwJob* jobs,
-                         float** ptbuf = nullptr) {
+                         float** ptbuf = nullptr, float** daimg = nullptr, float** mmpart = nullptr,
+                         float** cspart = nullptr) {
     const int H = d->hid_dim, M = Mof(d), CM = (d->input_dim + H) * M;
     CellDwPlan dp = plan_cell_dw(d->input_dim, H, M, B, T, jobs);
     int nj = dp.njobs, ns = dp.nsplit;
@@ -372,7 +399,17 @@ static size_t enc_bwd_ws(const dcgru_cell_desc* d, int B, int T, bool carve, voi
     float* f = c.take((size_t)ns * CM * 3 * H);
     float* g = c.take((size_t)ns * 3 * H);
     float* pt = c.take(((dw_tc_pt_floats(B, M) + 63) / 64) * 64 + 2 * (seq_bwd_tc_wimg_bytes() / 4 + 64));   // P^T + BPTT weight image + dX weight image
-    if (carve) { *WgT = a; *WcT = b; *dA = e; *part = f; *partb = g; *nsplit = ns; *njobs = nj; *ptbuf = pt; }
+    // operand-image path (dw_mm.cu): dA image, per-CTA partials, column-sum partials
+    float *im = nullptr, *mp = nullptr, *cp = nullptr;
+    if (gsave_bytes_for(d, B, T) > 0) {
+        im = c.take(seq_bwd_tc_daimg_bytes(B, T) / 4);
+        mp = c.take(dwmm_part_floats(devinfo().sms));
+        cp = c.take(colsum_part_floats(H));
+    }
+    if (carve) {
+        *WgT = a; *WcT = b; *dA = e; *part = f; *partb = g; *nsplit = ns; *njobs = nj; *ptbuf = pt;
+        *daimg = im; *mmpart = mp; *cspart = cp;
+    }
     return c.off;
 }
 
@@ -381,11 +418,25 @@ size_t dcgru_encoder_layer_bwd_workspace(const dcgru_cell_desc* d, int32_t batch
     return enc_bwd_ws(d, batch, seq_len, false, nullptr, 0, 0, 0, 0, 0, 0, 0, 0);
 }
 
+int dcgru_debug_encoder_bwd_offsets(const dcgru_cell_desc* d, int32_t batch, int32_t seq_len, size_t* out3) {
+    if (check_desc(d) || batch < 1 || seq_len < 1 || !out3) return fail("bad arguments");
+    float *WgT, *WcT, *dA, *part, *partb, *ptbuf, *daimg, *mmpart, *cspart;
+    int nsplit, njobs;
+    DwJob jobs[DW_MAXJOBS];
+    enc_bwd_ws(d, batch, seq_len, true, nullptr, &WgT, &WcT, &dA, &part, &partb, &nsplit, &njobs, jobs, &ptbuf,
+               &daimg, &mmpart, &cspart);
+    out3[0] = (size_t)((char*)dA - (char*)nullptr);
+    out3[1] = daimg ? (size_t)((char*)daimg - (char*)nullptr) : 0;
+    out3[2] = mmpart ? (size_t)((char*)mmpart - (char*)nullptr) : 0;
+    return 0;
+}
+
 int dcgru_encoder_layer_bwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq_len, const float* x,
                             int64_t x_stride_t, int64_t x_stride_b, const float* h0, const float* P,
                             const dcgru_cell_params* w, const float* h_seq, const float* ruc,
                             const float* d_hseq, const float* d_hlast, float* dx, float* dh0,
-                            const dcgru_cell_grads* g, void* workspace, size_t workspace_bytes, void* stream) {
+                            const dcgru_cell_grads* g, const void* gsave, size_t gsave_bytes,
+                            void* workspace, size_t workspace_bytes, void* stream) {
     if (check_desc(d)) return 1;
     if (batch < 1 || seq_len < 1) return fail("empty batch/sequence");
     if (!x || !h0 || !w || !h_seq || !ruc || !dh0 || !g || !workspace) return fail("null pointer");
@@ -395,11 +446,21 @@ int dcgru_encoder_layer_bwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
     if (!aligned16(workspace) || !aligned16(h_seq) || !aligned16(ruc)) return fail("unaligned pointer");
     if (dcgru_encoder_layer_bwd_workspace(d, batch, seq_len) > workspace_bytes) return fail("workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
-    float *WgT, *WcT, *dA, *part, *partb, *ptbuf;
+    float *WgT, *WcT, *dA, *part, *partb, *ptbuf, *daimg, *mmpart, *cspart;
     int nsplit, njobs;
     DwParams q;
     memset(&q, 0, sizeof q);
-    enc_bwd_ws(d, batch, seq_len, true, workspace, &WgT, &WcT, &dA, &part, &partb, &nsplit, &njobs, q.jobs, &ptbuf);
+    enc_bwd_ws(d, batch, seq_len, true, workspace, &WgT, &WcT, &dA, &part, &partb, &nsplit, &njobs, q.jobs, &ptbuf,
+               &daimg, &mmpart, &cspart);
+    DwmmParams mm;
+    bool use_mm = false;
+    if (gsave) {
+        const size_t need = gsave_bytes_for(d, batch, seq_len);
+        if (need == 0 || !daimg) return fail("this configuration has no operand image: pass gsave = NULL");
+        if (gsave_bytes < need) return fail("gsave too small (%zu < %zu bytes)", gsave_bytes, need);
+        if (!dwmm_plan(fin, H, M, seq_tc_nslab(batch, seq_len), devinfo().sms, &mm)) return fail("dw_mm plan failed");
+        use_mm = true;
+    }
     if (njobs > DW_MAXJOBS) return fail("too many weight-gradient jobs (%d)", njobs);
     LAUNCH("transpose", launch_transpose(w->Wg, CM, 2 * H, WgT, CM, st));
     LAUNCH("transpose", launch_transpose(w->Wc, CM, H, WcT, CM, st));
@@ -415,7 +476,8 @@ int dcgru_encoder_layer_bwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
         // recurrent part on the tensor cores; the input gradient is not recurrent -> bulk pass over all steps
         float* wimg_b = ptbuf + ((dw_tc_pt_floats(batch, M) + 63) / 64) * 64;
         LAUNCH("seq_bwd_tc", launch_seq_bwd_tc(batch, seq_len, d->num_nodes, fin, d->activation, h0, h_seq, ruc, P,
-                                               w->Wg, w->Wc, d_hseq, d_hlast, wimg_b, dh0, dA, st));
+                                               w->Wg, w->Wc, d_hseq, d_hlast, wimg_b, dh0, dA,
+                                               use_mm ? (void*)daimg : nullptr, st));
         if (dx) {
             if (fin == 64) {
                 float* wimg_x = wimg_b + seq_bwd_tc_wimg_bytes() / 4 + 64;
@@ -429,6 +491,15 @@ int dcgru_encoder_layer_bwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
         LAUNCH("seq_bwd", launch_seq_bwd(p, pl.SB, pl.smem, st));
     }
     // bulk weight gradients
+    if (use_mm) {
+        // GEMM over the operand images left by the forward (G) and backward (dA) sequence kernels
+        mm.G = reinterpret_cast<const uint8_t*>(gsave);
+        mm.DA = reinterpret_cast<const uint8_t*>(daimg);
+        mm.part = mmpart;
+        LAUNCH("dw_mm", launch_dw_mm(mm, fin, H, M, g->dWg, g->dWc, st));
+        LAUNCH("colsum", launch_colsum(dA, (long)seq_len * batch * d->num_nodes, H, cspart, g->dbg, g->dbc, st));
+        return 0;
+    }
     q.B = batch; q.T = seq_len; q.N = d->num_nodes; q.H = H; q.M = M; q.nsplit = nsplit; q.mode = 0;
     q.layer = 0; q.ncell = 1; q.fin = fin; q.Fo = 0;
     q.P = P; q.x = x; q.xs_t = x_stride_t; q.xs_b = x_stride_b; q.h0 = h0; q.hseq = h_seq; q.ruc = ruc; q.dA = dA;

@@ -34,6 +34,37 @@ struct DwParams {
     DwJob jobs[DW_MAXJOBS];
 };
 
+// ---- dw_mm.cu: weight gradient as a GEMM over the saved operand images ----------------------------------
+constexpr int DWMM_MAXTILE = 4;
+constexpr int DWMM_MAXSET = 4;
+struct DwmmTile {
+    int kg0, nkg;      // K groups (4 kk each) of the G image this 128-row tile covers / loads
+    int og0, ncol;     // first column quad of the dA image and number of columns (64, 128 or 192)
+    int tcol;          // TMEM column base inside the set
+};
+struct DwmmSet {
+    int ntile, ncoltot, cta0, ncta, ogmin, ogcnt;
+    DwmmTile tile[DWMM_MAXTILE];
+};
+struct DwmmParams {
+    const uint8_t* G;
+    const uint8_t* DA;
+    float* part;       // [cta][512 columns][128 rows]
+    long nkb;          // K blocks (8 rows each) = slabs * 16
+    int KGT, nset, ncta;
+    DwmmSet set[DWMM_MAXSET];
+};
+bool dwmm_plan(int fin, int H, int M, long nslab, int nsms, DwmmParams* out);
+size_t dwmm_part_floats(int nsms);
+size_t colsum_part_floats(int H);
+int dw_mm_smem_bytes();
+cudaError_t launch_dw_mm(const DwmmParams& p, int fin, int H, int M, float* dWg, float* dWc, cudaStream_t st);
+cudaError_t launch_colsum(const float* dA, long rows, int H, float* partial, float* dbg, float* dbc, cudaStream_t st);
+int seq_fwd_tc_kgt(int fin);
+int seq_tc_nslab(int B, int T);
+size_t seq_fwd_tc_gsave_bytes(int B, int T, int fin);
+size_t seq_bwd_tc_daimg_bytes(int B, int T);
+
 int dw_smem_bytes(int M, int nco_max);
 cudaError_t launch_dw(const DwParams& p, int njobs, int nco_max, cudaStream_t st);
 cudaError_t launch_reduce_cell(const float* part, const float* partb, int nsplit, int CM, int H,
@@ -57,12 +88,12 @@ size_t seq_fwd_tc_wimg_bytes(int fin);
 bool seq_fwd_tc_supported(int N, int fin, int H, int M, int smem_limit);
 cudaError_t launch_seq_fwd_tc(int B, int T, int N, int fin, int act, const float* x, long long xs_t, long long xs_b,
                               const float* h0, const float* P, const float* Wg, const float* bg, const float* Wc,
-                              const float* bc, float* wimg, float* hseq, float* ruc, cudaStream_t st);
+                              const float* bc, float* wimg, float* hseq, float* ruc, void* gsave, cudaStream_t st);
 size_t seq_bwd_tc_wimg_bytes();
 bool seq_bwd_tc_supported(int N, int H, int M, int smem_limit);
 cudaError_t launch_seq_bwd_tc(int B, int T, int N, int fin, int act, const float* h0, const float* hseq, const float* ruc,
                               const float* P, const float* Wg, const float* Wc, const float* d_hseq, const float* d_hlast,
-                              float* wimg, float* dh0, float* dA, cudaStream_t st);
+                              float* wimg, float* dh0, float* dA, void* daimg, cudaStream_t st);
 cudaError_t launch_dx_tc(int B, int T, int N, const float* P, const float* Wg, const float* Wc, const float* dA,
                          float* wimg, float* dx, cudaStream_t st);
 cudaError_t launch_tc_selftest(const float* A, const float* B, float* C, int N, int K, cudaStream_t st);

@@ -15,6 +15,9 @@
 // Roles: warps 0-7 elementwise + A tiles + diffT, warp 8 MMA issue, warp 9 TMA weight loads (12 chunk blocks
 // per step, pre-split / pre-tiled by pack_w_bwd_kernel, 3-slot ring).  Synchronisation is mbarrier-only
 // apart from two 128-thread named barriers around the diffT staging planes.
+// A slots are laid out [row group of 8][K group][8 rows x 16 B] (LBO = 128 B, SBO = 512 B).  Optional operand
+// image (daimg): warp 10 copies every finished A slot (hi and lo) to HBM with bulk stores into
+// DA[cta][t][hi|lo][row group][o/4 in r|u|c order][128 B] -- the B operand of the weight-gradient GEMM (dw_mm.cu).
 #include <cstring>
 
 #include "common.cuh"
@@ -43,7 +46,8 @@ constexpr int BT_OFF_S = BT_OFF_B + 3 * BT_B_SLOT;         // 2 planes [128][36]
 constexpr int BT_OFF_DH = BT_OFF_S + 2 * BT_ROWS * BT_PLD * 4;
 constexpr int BT_SMEM = BT_OFF_DH + BT_ROWS * BT_DLD * 4;
 constexpr int BT_NPROD = 256;
-constexpr int BT_THREADS = 320;
+constexpr int BT_THREADS = 352;                            // + warp 10: operand-image dump
+constexpr int BT_RG_F4 = BT_KG * 8;                        // float4s per 8-row group of an A slot (512 B)
 constexpr uint32_t BT_D1 = 0, BT_D2 = 256;                 // TMEM column bases
 
 // weight image: 12 blocks in consumption order, each [hi: kg][n = kk] [lo: kg][n] float4 over 4 consecutive o
@@ -104,6 +108,7 @@ struct BwdTcParams {
     const float* wimg;
     float* dh0;
     float* dA;
+    uint8_t* daimg;             // mode 0: operand image of dA for dw_mm (nullptr: not saved)
 };
 
 __device__ __forceinline__ void bt_arrive(uint64_t* bar) {
@@ -123,7 +128,7 @@ __device__ __forceinline__ void prod_barrier() {             // the 8 producer w
 
 __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bar_bfull[3], bar_afull[4], bar_cdone[4], bar_d1free, bar_d2free;
+    __shared__ uint64_t bar_bfull[3], bar_afull[4], bar_cdone[4], bar_stored[4], bar_d1free, bar_d2free;
     __shared__ uint32_t tmem_slot;
     __shared__ uint64_t dA_desc[4][2][2];                    // [slot][k-step][hi, lo]
     __shared__ uint64_t dB_desc[3][2][2];
@@ -135,15 +140,15 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
     if (warp == 0) tmem_alloc<512>(&tmem_slot);
     if (tid == 0) {
         for (int i = 0; i < 3; ++i) mbar_init(&bar_bfull[i], 1);
-        for (int i = 0; i < 4; ++i) { mbar_init(&bar_afull[i], BT_NPROD / 32); mbar_init(&bar_cdone[i], 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&bar_afull[i], BT_NPROD / 32); mbar_init(&bar_cdone[i], 1); mbar_init(&bar_stored[i], 1); }
         mbar_init(&bar_d1free, BT_NPROD / 32);
         mbar_init(&bar_d2free, BT_NPROD / 32);
         mbar_fence_init();
         for (int sl = 0; sl < 4; ++sl)
             for (int k = 0; k < 2; ++k) {
-                const uint32_t hi = smem_u32(smem + BT_OFF_A + sl * BT_A_SLOT) + 2 * k * BT_ROWS * 16;
-                dA_desc[sl][k][0] = make_smem_desc(hi, BT_ROWS * 16, 128);
-                dA_desc[sl][k][1] = make_smem_desc(hi + BT_A_BYTES, BT_ROWS * 16, 128);
+                const uint32_t hi = smem_u32(smem + BT_OFF_A + sl * BT_A_SLOT) + 2 * k * 128;
+                dA_desc[sl][k][0] = make_smem_desc(hi, 128, BT_RG_F4 * 16);
+                dA_desc[sl][k][1] = make_smem_desc(hi + BT_A_BYTES, 128, BT_RG_F4 * 16);
             }
         for (int sl = 0; sl < 3; ++sl)
             for (int k = 0; k < 2; ++k) {
@@ -162,6 +167,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
     const unsigned total_chunks = (unsigned)p.T * BT_CHUNKS;
     const uint8_t* wimg = reinterpret_cast<const uint8_t*>(p.wimg);
     const size_t NH = (size_t)N * BT_H;
+    const bool dump = (p.daimg != nullptr) && p.mode == 0;
 
     if (warp == 8) {
         // =================================== MMA issuer =========================================================
@@ -210,6 +216,31 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
                 if (++q2 == BT_CHUNKS) q2 = 0;
                 if (++sb2 == 3) sb2 = 0;
             }
+        }
+        __syncwarp();
+    } else if (warp == 10) {
+        // =================================== operand-image dump ==================================================
+        // lane = (hi|lo, row group): one 512-byte bulk store per finished A slot
+        if (dump) {
+            const int part = lane >> 4, rg = lane & 15;
+            const size_t rg_bytes = (size_t)(3 * BT_H / 4) * 128;           // 48 column quads
+            const size_t slab = 2 * 16 * rg_bytes;                          // one (cta, t)
+            uint8_t* gbase = p.daimg + (size_t)blockIdx.x * p.T * slab + ((size_t)part * 16 + rg) * rg_bytes;
+            const uint8_t* src0 = smem + BT_OFF_A + part * BT_A_BYTES + rg * (BT_RG_F4 * 16);
+            int q = 0, t = p.T - 1;
+            for (unsigned g = 0; g < total_chunks; ++g) {
+                const int sa = g & 3;
+                // column quad of the chunk in [r | u | c] order: B1 = c, then u, then r
+                const int og0 = (q < 4) ? 32 + 4 * q : (q < 8 ? 16 + 4 * (q - 4) : 4 * (q - 8));
+                mbar_wait(&bar_afull[sa], (g >> 2) & 1);
+                bulk_s2g(gbase + (size_t)t * slab + (size_t)og0 * 128, src0 + sa * BT_A_SLOT, BT_RG_F4 * 16);
+                bulk_commit();
+                bulk_wait_read();
+                __syncwarp();
+                if (lane == 0) bt_arrive(&bar_stored[sa]);
+                if (++q == BT_CHUNKS) { q = 0; --t; }
+            }
+            bulk_wait_all();
         }
         __syncwarp();
     } else {
@@ -269,7 +300,10 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
         unsigned g = 0;
         auto put_chunk = [&](const float (&v)[32], int owner_hf, int sub) {
             const int sa = g & 3;
-            if (g >= 4) mbar_wait(&bar_cdone[sa], ((g >> 2) - 1) & 1);    // the MMAs that read this slot are done
+            if (g >= 4) {
+                mbar_wait(&bar_cdone[sa], ((g >> 2) - 1) & 1);            // the MMAs that read this slot are done
+                if (dump) mbar_wait(&bar_stored[sa], ((g >> 2) - 1) & 1); // ... and so is its copy to the operand image
+            }
             if (hf == owner_hf) {
                 float4* a_hi = reinterpret_cast<float4*>(smem + BT_OFF_A + sa * BT_A_SLOT);
                 float4* a_lo = reinterpret_cast<float4*>(smem + BT_OFF_A + sa * BT_A_SLOT + BT_A_BYTES);
@@ -278,8 +312,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
                     float4 h, l;
                     split4(make_float4(v[16 * sub + 4 * kg], v[16 * sub + 4 * kg + 1], v[16 * sub + 4 * kg + 2],
                                        v[16 * sub + 4 * kg + 3]), h, l);
-                    a_hi[kg * BT_ROWS + row] = h;
-                    a_lo[kg * BT_ROWS + row] = l;
+                    a_hi[(row >> 3) * BT_RG_F4 + kg * 8 + (row & 7)] = h;
+                    a_lo[(row >> 3) * BT_RG_F4 + kg * 8 + (row & 7)] = l;
                 }
                 fence_async_smem();
             }
@@ -390,6 +424,10 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
             float* dA = p.dA + (size_t)t * p.B * NH * 3;
             const unsigned g0 = g;                                        // first chunk of this step
             float hp[32], dAu[32], w0[32], w1[32];
+            if (dump && g >= 4) {                                         // tile 1 aliases the A ring: its copies must have been read
+#pragma unroll
+                for (unsigned i = 1; i <= 4; ++i) mbar_wait(&bar_stored[(g - i) & 3], ((g - i) >> 2) & 1);
+            }
             // ---- E1 ------------------------------------------------------------------------------------------
             // (all MMAs of the previous step are complete: the A ring and the planes are idle)
             tile_load(tile0, ruc, 3 * BT_H, BT_H + 32 * hf);              // u
@@ -498,6 +536,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
 }
 
 size_t seq_bwd_tc_wimg_bytes() { return (size_t)BT_CHUNKS * BT_B_SLOT; }
+size_t seq_bwd_tc_daimg_bytes(int B, int T) {
+    return (size_t)((B + BT_SB - 1) / BT_SB) * T * 2 * 16 * (3 * BT_H / 4) * 128;
+}
 bool seq_bwd_tc_supported(int N, int H, int M, int smem_limit) {
     return H == BT_H && M == BT_M && N <= NP && BT_SMEM + 2304 <= smem_limit;
 }
@@ -505,7 +546,7 @@ bool seq_bwd_tc_supported(int N, int H, int M, int smem_limit) {
 cudaError_t launch_seq_bwd_tc(int B, int T, int N, int fin, int act, const float* h0, const float* hseq,
                               const float* ruc, const float* P, const float* Wg, const float* Wc,
                               const float* d_hseq, const float* d_hlast, float* wimg, float* dh0, float* dA,
-                              cudaStream_t st) {
+                              void* daimg, cudaStream_t st) {
     pack_w_bwd_kernel<<<BT_CHUNKS, 256, 0, st>>>(Wg, Wc, fin, wimg);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -513,6 +554,7 @@ cudaError_t launch_seq_bwd_tc(int B, int T, int N, int fin, int act, const float
     p.mode = 0; p.dx = nullptr;
     p.B = B; p.T = T; p.N = N; p.act = act; p.h0 = h0; p.hseq = hseq; p.ruc = ruc; p.P = P;
     p.d_hseq = d_hseq; p.d_hlast = d_hlast; p.wimg = wimg; p.dh0 = dh0; p.dA = dA;
+    p.daimg = reinterpret_cast<uint8_t*>(daimg);
     e = cudaFuncSetAttribute(seq_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM);
     if (e != cudaSuccess) return e;
     seq_bwd_tc_kernel<<<(B + BT_SB - 1) / BT_SB, BT_THREADS, BT_SMEM, st>>>(p);

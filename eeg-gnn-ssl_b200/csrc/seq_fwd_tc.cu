@@ -9,7 +9,12 @@
 // A operand: each thread owns one (sample, node) row and keeps that row of the diffusion polynomials P_m
 // in registers for the whole sequence; for every 8-column chunk of [x | h] it forms the M diffusion terms
 // of 4 columns (20 broadcast float4 reads + 40 FMAs per column quad), splits them hi/lo and writes them
-// in kk = c*M + m order into a K-group-major UMMA tile (2 stages).
+// in kk = c*M + m order into a UMMA tile (2 stages) laid out [row group of 8][K group][8 rows x 16 B]
+// (canonical K-major no-swizzle: LBO = 128 B between K groups, SBO = 768 B between row groups).
+// Optional operand image (gsave): a dump warp copies every finished A stage (hi and lo) to HBM with bulk
+// stores, one 768-byte row-group slice per lane, into G[cta][t][hi|lo][row group][kg of the step][128 B].
+// In that layout an 8-row K block of the weight-gradient GEMM (dw_mm.cu) is one contiguous piece that is
+// already a valid MN-major UMMA operand, so dW needs no recomputation of the diffusion at all.
 // B operand: the weights, pre-split and pre-tiled once per launch by pack_w_fwd_kernel, streamed chunk by
 // chunk from L2 with cp.async.bulk (TMA) into a 3-slot ring, each load issued one chunk ahead at the top
 // of the iteration so its latency hides behind two A-tile productions; mbarriers track "weights landed"
@@ -108,15 +113,10 @@ struct FwdTcParams {
     const float* wimg;
     float* hseq;
     float* ruc;
+    uint8_t* gsave;             // operand image for dw_mm (nullptr: not saved)
     long long* dbgbuf;          // timing experiment (DCGRU_DBG & 4): clock64 stamps of CTA 0
 };
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void bulk_copy(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -127,13 +127,15 @@ __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 
 __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
 constexpr int FT_NPROD = 256;            // producer / epilogue threads (warps 0-7)
-constexpr int FT_THREADS = 320;          // + warp 8: MMA issue, warp 9: TMA weight loads
+constexpr int FT_THREADS = 352;          // + warp 8: MMA issue, warp 9: TMA weight loads, warp 10: operand-image dump
+constexpr int FT_RG_F4 = FT_KG * 8;      // float4s per 8-row group of an A tile (768 B)
+__device__ __forceinline__ int ft_a_idx(int kg, int row) { return (row >> 3) * FT_RG_F4 + kg * 8 + (row & 7); }
 
 // Warp-specialised: warps 0-7 build the A tiles and run the epilogues, warp 8 streams weights and x with TMA
 // and issues the MMAs; the only synchronisation inside a step is through mbarriers (no CTA-wide barrier).
 __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bar_bfull[3], bar_xfull[FT_XRING], bar_afull[2], bar_done[2], bar_epi;
+    __shared__ uint64_t bar_bfull[3], bar_xfull[FT_XRING], bar_afull[2], bar_done[2], bar_stored[2], bar_epi;
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float sbias[3 * FT_H];                      // bg (r | u) | bc
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
     if (tid == 0) {
         for (int i = 0; i < 3; ++i) mbar_init(&bar_bfull[i], 1);
         for (int i = 0; i < FT_XRING; ++i) mbar_init(&bar_xfull[i], FT_NPROD);
-        for (int i = 0; i < 2; ++i) { mbar_init(&bar_afull[i], FT_NPROD / 32); mbar_init(&bar_done[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_afull[i], FT_NPROD / 32); mbar_init(&bar_done[i], 1); mbar_init(&bar_stored[i], 1); }
         mbar_init(&bar_epi, FT_NPROD / 32);
         mbar_fence_init();
     }
@@ -172,6 +174,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
     const unsigned total_x = (unsigned)p.T * nxc;
     const uint8_t* wimg = reinterpret_cast<const uint8_t*>(p.wimg);
     const size_t NH = (size_t)N * FT_H;
+    const bool dump = p.gsave != nullptr;
 
     if (warp == 8) {
         // =================================== TMA + MMA issuer ===================================================
@@ -183,9 +186,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
         if (lane == 0) {
             for (int st = 0; st < 2; ++st)
                 for (int k = 0; k < 3; ++k) {
-                    const uint32_t hi = smem_u32(smem + FT_OFF_A + st * FT_A_STAGE) + 2 * k * FT_ROWS * 16;
-                    dA[st][k][0] = make_smem_desc(hi, FT_ROWS * 16, 128);
-                    dA[st][k][1] = make_smem_desc(hi + FT_A_BYTES, FT_ROWS * 16, 128);
+                    const uint32_t hi = smem_u32(smem + FT_OFF_A + st * FT_A_STAGE) + 2 * k * 128;
+                    dA[st][k][0] = make_smem_desc(hi, 128, FT_RG_F4 * 16);
+                    dA[st][k][1] = make_smem_desc(hi + FT_A_BYTES, 128, FT_RG_F4 * 16);
                 }
             for (int sl = 0; sl < 3; ++sl)
                 for (int kind = 0; kind < 3; ++kind) {
@@ -258,6 +261,30 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
             }
         }
         __syncwarp();
+    } else if (warp == 10) {
+        // =================================== operand-image dump ==================================================
+        // lane = (hi|lo, row group): one 768-byte bulk store per finished A stage; the stage is released to the
+        // producers (bar_stored) once every lane's store has read its shared-memory source
+        if (dump) {
+            const int part = lane >> 4, rg = lane & 15;
+            const size_t kgt_bytes = (size_t)per_step * FT_KG * 128;       // one row group of a step
+            const size_t slab = 2 * 16 * kgt_bytes;                         // one (cta, t)
+            uint8_t* gdst = p.gsave + (size_t)blockIdx.x * p.T * slab + ((size_t)part * 16 + rg) * kgt_bytes;
+            const uint8_t* src0 = smem + FT_OFF_A + part * FT_A_BYTES + rg * (FT_RG_F4 * 16);
+            int q = 0;
+            for (unsigned g = 0; g < total_chunks; ++g) {
+                const int sa = g & 1;
+                mbar_wait(&bar_afull[sa], (g >> 1) & 1);
+                bulk_s2g(gdst + (size_t)q * (FT_KG * 128), src0 + sa * FT_A_STAGE, FT_RG_F4 * 16);
+                bulk_commit();
+                bulk_wait_read();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_stored[sa]);
+                if (++q == per_step) { q = 0; gdst += slab; }
+            }
+            bulk_wait_all();
+        }
+        __syncwarp();
     } else {
         // =================================== producers / epilogue ================================================
         const int row = tid & 127, half = tid >> 7;
@@ -296,7 +323,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
             const int sa = g & 1;
             const bool rec = (p.dbg & 4) && blockIdx.x == 0 && tid == 0 && g < 128;
             if (rec) p.dbgbuf[g * 8 + 4] = clock64();
-            if (g >= 2) mbar_wait(&bar_done[sa], ((g >> 1) - 1) & 1);    // the MMAs that read this stage are done
+            if (g >= 2) {
+                mbar_wait(&bar_done[sa], ((g >> 1) - 1) & 1);            // the MMAs that read this stage are done
+                if (dump) mbar_wait(&bar_stored[sa], ((g >> 1) - 1) & 1); // ... and so is its copy to the operand image
+            }
             if (rec) p.dbgbuf[g * 8 + 5] = clock64();
             if (is_x) {
                 // every producer is past chunk g-2, so the slot x chunk xq-2 lived in can be refilled
@@ -331,9 +361,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
             float4 f2 = make_float4(a2[2], v0[3], a1[3], a2[3]);
             float4 h, l;
             const int kg0 = half * 3;
-            split4(f0, h, l); a_hi[(kg0 + 0) * FT_ROWS + row] = h; a_lo[(kg0 + 0) * FT_ROWS + row] = l;
-            split4(f1, h, l); a_hi[(kg0 + 1) * FT_ROWS + row] = h; a_lo[(kg0 + 1) * FT_ROWS + row] = l;
-            split4(f2, h, l); a_hi[(kg0 + 2) * FT_ROWS + row] = h; a_lo[(kg0 + 2) * FT_ROWS + row] = l;
+            const int ai = ft_a_idx(kg0, row);
+            split4(f0, h, l); a_hi[ai] = h; a_lo[ai] = l;
+            split4(f1, h, l); a_hi[ai + 8] = h; a_lo[ai + 8] = l;
+            split4(f2, h, l); a_hi[ai + 16] = h; a_lo[ai + 16] = l;
             if (rec) p.dbgbuf[g * 8 + 6] = clock64();
             fence_async_smem();
             __syncwarp();
@@ -344,6 +375,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
         auto wait_all_mma = [&]() {                                       // MMAs of the last produced chunk (hence all)
             const unsigned gl = g - 1;
             mbar_wait(&bar_done[gl & 1], (gl >> 1) & 1);
+            if (dump) {                                                   // the epilogues stage through the A stages
+                mbar_wait(&bar_stored[gl & 1], (gl >> 1) & 1);
+                if (gl >= 1) mbar_wait(&bar_stored[(gl - 1) & 1], ((gl - 1) >> 1) & 1);
+            }
             tc_fence_after();
         };
         const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
@@ -390,7 +425,6 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
                 *reinterpret_cast<float4*>(stg + (rq + 4 * i) * 36 + 4 * f4) = q;
             }
         };
-        const size_t ro = ((size_t)b_ * N + n_);
         for (int t = 0; t < p.T; ++t) {
             const float* hprev = (t == 0) ? p.h0 : p.hseq + (size_t)(t - 1) * p.B * NH;
             float* hout = p.hseq + (size_t)t * p.B * NH;
@@ -464,6 +498,12 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
 }
 
 size_t seq_fwd_tc_wimg_bytes(int fin) { return ft_wimg_bytes(fin); }
+// operand image geometry shared with dw_mm.cu: K groups per step, CTAs, bytes
+int seq_fwd_tc_kgt(int fin) { return (ft_nxc(fin) + 2 * (FT_H / FT_CC)) * FT_KG; }
+int seq_tc_nslab(int B, int T) { return ((B + FT_SB - 1) / FT_SB) * T; }
+size_t seq_fwd_tc_gsave_bytes(int B, int T, int fin) {
+    return (size_t)seq_tc_nslab(B, T) * 2 * 16 * seq_fwd_tc_kgt(fin) * 128;
+}
 bool seq_fwd_tc_supported(int N, int fin, int H, int M, int smem_limit) {
     return H == FT_H && M == FT_M && N <= NP && fin % 4 == 0 && FT_SMEM + 2304 <= smem_limit;
 }
@@ -471,7 +511,7 @@ bool seq_fwd_tc_supported(int N, int fin, int H, int M, int smem_limit) {
 cudaError_t launch_seq_fwd_tc(int B, int T, int N, int fin, int act, const float* x, long long xs_t,
                               long long xs_b, const float* h0, const float* P, const float* Wg, const float* bg,
                               const float* Wc, const float* bc, float* wimg, float* hseq, float* ruc,
-                              cudaStream_t st) {
+                              void* gsave, cudaStream_t st) {
     const int nblk = ft_nxc(fin) + 2 * (FT_H / FT_CC);
     pack_w_fwd_kernel<<<nblk, 256, 0, st>>>(Wg, Wc, fin, wimg);
     cudaError_t e = cudaGetLastError();
@@ -480,6 +520,7 @@ cudaError_t launch_seq_fwd_tc(int B, int T, int N, int fin, int act, const float
     { const char* e = getenv("DCGRU_DBG"); p.dbg = e ? atoi(e) : 0; }
     p.B = B; p.T = T; p.N = N; p.fin = fin; p.act = act; p.x = x; p.xs_t = xs_t; p.xs_b = xs_b; p.h0 = h0; p.P = P;
     p.bg = bg; p.bc = bc; p.wimg = wimg; p.hseq = hseq; p.ruc = ruc;
+    p.gsave = reinterpret_cast<uint8_t*>(gsave);
     p.dbgbuf = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(wimg) + ((ft_wimg_bytes(fin) + 255) / 256) * 256);
     e = cudaFuncSetAttribute(seq_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
     if (e != cudaSuccess) return e;

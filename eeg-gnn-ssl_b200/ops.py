@@ -118,11 +118,16 @@ class _EncoderLayerFn(torch.autograd.Function):
         L = _lib.lib()
         nbytes = L.dcgru_encoder_layer_fwd_workspace(C.byref(desc), b, t_len)
         ws_buf = torch.empty(max(nbytes, 16), device=x.device, dtype=torch.uint8)
+        # operand image for the weight-gradient GEMM (tensor-core configurations only; 0 bytes otherwise)
+        gbytes = L.dcgru_encoder_layer_gsave_bytes(C.byref(desc), b, t_len) if need else 0
+        gsave = torch.empty(gbytes, device=x.device, dtype=torch.uint8) if gbytes else None
         check(L.dcgru_encoder_layer_fwd(C.byref(desc), b, t_len, _ptr(x), st, sb, _ptr(h0), _ptr(p), ws,
-                                        _ptr(h_seq), _ptr(ruc), _ptr(ws_buf), nbytes, _stream()),
+                                        _ptr(h_seq), _ptr(ruc), _ptr(gsave), gbytes, _ptr(ws_buf), nbytes,
+                                        _stream()),
               "encoder_layer_fwd")
         ctx.desc = desc
         ctx.strides = (st, sb)
+        ctx.gsave = gsave
         ctx.save_for_backward(x, h0, p, wg, bg, wc, bc, h_seq, ruc)
         ctx.set_materialize_grads(False)
         h_last = h_seq[t_len - 1].clone()
@@ -150,8 +155,11 @@ class _EncoderLayerFn(torch.autograd.Function):
         g = CellGrads(dwg.data_ptr(), dbg.data_ptr(), dwc.data_ptr(), dbc.data_ptr())
         check(L.dcgru_encoder_layer_bwd(C.byref(desc), b, t_len, _ptr(x), st, sb, _ptr(h0), _ptr(p), ws,
                                         _ptr(h_seq), _ptr(ruc), _ptr(d_hseq), _ptr(d_hlast), _ptr(dx),
-                                        _ptr(dh0), C.byref(g), _ptr(ws_buf), nbytes, _stream()),
+                                        _ptr(dh0), C.byref(g), _ptr(ctx.gsave),
+                                        ctx.gsave.numel() if ctx.gsave is not None else 0,
+                                        _ptr(ws_buf), nbytes, _stream()),
               "encoder_layer_bwd")
+        ctx.gsave = None
         return dx, dh0, None, dwg, dbg, dwc, dbc, None
 
 

@@ -95,29 +95,43 @@ int dcgru_corr_supports(int32_t batch, int32_t seq_len, int32_t num_nodes, int32
  * P:     (B, M-1, N, N) from dcgru_graph_poly
  * h_seq: (T, B, N*H) out -- every step's hidden state (the layer's output sequence)
  * ruc:   (T, B, N, 3H) out -- r | u | c per node, saved for backward (NULL: inference)
+ * gsave: optional "operand image" saved for backward (NULL: not saved).  When the tensor-core
+ *        kernels serve this configuration, dcgru_encoder_layer_gsave_bytes() is non-zero and the
+ *        forward kernel can leave its diffused GEMM operands [x | h | r*h] (hi/lo split, already
+ *        in tensor-core tile order) in this caller-owned buffer; handing the same buffer to
+ *        dcgru_encoder_layer_bwd turns the weight gradient (the G^T dA of MmBackward for
+ *        model/cell.py:116) into a pure GEMM over saved operands instead of recomputing the
+ *        diffusion.  Costs gsave_bytes of HBM per layer (3.7 GB at B=512, T=60, Fin=100).
  * workspace: scratch for the pre-tiled weight image of the tensor-core kernel (may be NULL:
  *        the fp32 FMA kernel is used then)                                                    */
+size_t dcgru_encoder_layer_gsave_bytes(const dcgru_cell_desc *d, int32_t batch, int32_t seq_len);
 size_t dcgru_encoder_layer_fwd_workspace(const dcgru_cell_desc *d, int32_t batch, int32_t seq_len);
 int dcgru_encoder_layer_fwd(const dcgru_cell_desc *d, int32_t batch, int32_t seq_len,
                             const float *x, int64_t x_stride_t, int64_t x_stride_b,
                             const float *h0, const float *P, const dcgru_cell_params *w,
-                            float *h_seq, float *ruc,
+                            float *h_seq, float *ruc, void *gsave, size_t gsave_bytes,
                             void *workspace, size_t workspace_bytes, void *stream);
 
 size_t dcgru_encoder_layer_bwd_workspace(const dcgru_cell_desc *d, int32_t batch,
                                          int32_t seq_len);
+/* Diagnostics for the tests: byte offsets inside the backward workspace of {row-major dA (T,B,N,3H),
+ * dA operand image, per-CTA partials of the weight-gradient GEMM} (0 = not used by this configuration). */
+int dcgru_debug_encoder_bwd_offsets(const dcgru_cell_desc *d, int32_t batch, int32_t seq_len,
+                                    size_t *out3);
 
 /* Backward of the above (what autograd derives for the reference).
  * d_hseq:  (T,B,N*H) upstream gradient of h_seq (NULL = zeros)
  * d_hlast: (B,N*H)  extra upstream gradient of h_seq[T-1] (the layer's output_hidden; NULL)
  * dx:      (T,B,N*Fin) out, or NULL when the input needs no gradient (layer 0)
- * dh0:     (B,N*H) out                                                                        */
+ * dh0:     (B,N*H) out
+ * gsave:   the operand image the forward call filled, or NULL (the diffusion is recomputed)   */
 int dcgru_encoder_layer_bwd(const dcgru_cell_desc *d, int32_t batch, int32_t seq_len,
                             const float *x, int64_t x_stride_t, int64_t x_stride_b,
                             const float *h0, const float *P, const dcgru_cell_params *w,
                             const float *h_seq, const float *ruc,
                             const float *d_hseq, const float *d_hlast,
                             float *dx, float *dh0, const dcgru_cell_grads *g,
+                            const void *gsave, size_t gsave_bytes,
                             void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- decoder -------------------------------------------------------------------------------

@@ -45,8 +45,11 @@ def test_argument_validation_reports_errors():
     ok = _lib.CellDesc(19, 100, 64, 2, 1, 0)
     assert L.dcgru_encoder_layer_bwd_workspace(C.byref(ok), 512, 60) > 400e6   # dA alone is 448 MB
     assert L.dcgru_decoder_bwd_workspace(C.byref(ok), 3, 4, 65) == 0            # To > 64
-    rc = L.dcgru_encoder_layer_fwd(C.byref(ok), 4, 4, None, 0, 0, None, None, None, None, None, None, 0, None)
+    rc = L.dcgru_encoder_layer_fwd(C.byref(ok), 4, 4, None, 0, 0, None, None, None, None, None, None, 0, None, 0,
+                                   None)
     assert rc != 0 and b"null" in L.dcgru_last_error()
+    # no device here: the tensor-core operand image is not offered (0 bytes), nothing is emulated
+    assert L.dcgru_encoder_layer_gsave_bytes(C.byref(ok), 512, 60) == 0
 
 
 def test_cpu_tensors_are_rejected_not_emulated():

@@ -258,6 +258,21 @@ int dcgru_tc_selftest(const float* A, const float* B, float* C, int32_t N, int32
     return 0;
 }
 
+int dcgru_tc_probe(const float* a_img, int32_t a_bytes, const float* b_img, int32_t b_bytes, uint32_t a_lbo,
+                   uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, int32_t a_mn_major, int32_t b_mn_major,
+                   int32_t a_layout_type, int32_t b_layout_type, float* D, int32_t N, void* stream) {
+    if (!a_img || !b_img || !D) return fail("null pointer");
+    if (a_bytes < 16 || a_bytes > 16384 || b_bytes < 16 || b_bytes > 16384 || a_bytes % 4 || b_bytes % 4)
+        return fail("image sizes must be 16..16384 bytes");
+    if (N < 16 || N > 256 || N % 16) return fail("N=%d unsupported", N);
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | (8u << 24) |
+                           (a_mn_major ? 1u << 15 : 0u) | (b_mn_major ? 1u << 16 : 0u);
+    LAUNCH("tc_probe", launch_tc_probe(a_img, a_bytes, b_img, b_bytes, a_lbo, a_sbo, b_lbo, b_sbo, idesc,
+                                       (uint32_t)a_layout_type & 7u, (uint32_t)b_layout_type & 7u, D, N, st));
+    return 0;
+}
+
 int dcgru_timing_enable(int on) {
     std::lock_guard<std::mutex> lk(g_tmu);
     for (auto& r : g_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -416,6 +431,11 @@ static size_t enc_bwd_ws(const dcgru_cell_desc* d, int B, int T, bool carve, voi
 size_t dcgru_encoder_layer_bwd_workspace(const dcgru_cell_desc* d, int32_t batch, int32_t seq_len) {
     if (check_desc(d) || batch < 1 || seq_len < 1) return 0;
     return enc_bwd_ws(d, batch, seq_len, false, nullptr, 0, 0, 0, 0, 0, 0, 0, 0);
+}
+
+int dcgru_debug_dwmm_stamps(long long* out, int32_t n) {
+    CUDA_TRY(dwmm_read_dbg(out, n));
+    return 0;
 }
 
 int dcgru_debug_encoder_bwd_offsets(const dcgru_cell_desc* d, int32_t batch, int32_t seq_len, size_t* out3) {

@@ -51,9 +51,10 @@ struct DwmmParams {
     const uint8_t* DA;
     float* part;       // [cta][512 columns][128 rows]
     long nkb;          // K blocks (8 rows each) = slabs * 16
-    int KGT, nset, ncta;
+    int KGT, nset, ncta, dbg;
     DwmmSet set[DWMM_MAXSET];
 };
+cudaError_t dwmm_read_dbg(long long* out, int n);
 bool dwmm_plan(int fin, int H, int M, long nslab, int nsms, DwmmParams* out);
 size_t dwmm_part_floats(int nsms);
 size_t colsum_part_floats(int H);
@@ -61,6 +62,7 @@ int dw_mm_smem_bytes();
 cudaError_t launch_dw_mm(const DwmmParams& p, int fin, int H, int M, float* dWg, float* dWc, cudaStream_t st);
 cudaError_t launch_colsum(const float* dA, long rows, int H, float* partial, float* dbg, float* dbc, cudaStream_t st);
 int seq_fwd_tc_kgt(int fin);
+int seq_fwd_tc_kkp(int fin);
 int seq_tc_nslab(int B, int T);
 size_t seq_fwd_tc_gsave_bytes(int B, int T, int fin);
 size_t seq_bwd_tc_daimg_bytes(int B, int T);
@@ -97,4 +99,7 @@ cudaError_t launch_seq_bwd_tc(int B, int T, int N, int fin, int act, const float
 cudaError_t launch_dx_tc(int B, int T, int N, const float* P, const float* Wg, const float* Wc, const float* dA,
                          float* wimg, float* dx, cudaStream_t st);
 cudaError_t launch_tc_selftest(const float* A, const float* B, float* C, int N, int K, cudaStream_t st);
+cudaError_t launch_tc_probe(const float* Aimg, int a_bytes, const float* Bimg, int b_bytes, uint32_t a_lbo, uint32_t a_sbo,
+                            uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc, uint32_t a_type, uint32_t b_type, float* D, int N,
+                            cudaStream_t st);
 }  // namespace dcgru

@@ -1,26 +1,31 @@
 // Weight gradient as a pure TMA-fed tensor-core GEMM (tcgen05, 3xTF32) over the operand images that the
 // forward and backward sequence kernels leave in HBM:
 //     dW[kk][o] = sum over every (cta, t, row) of  G[row][kk] * dA[row][o]
-//   G  image (seq_fwd_tc.cu):  [slab = cta*T + t][hi|lo][row group of 8][kg of the step][8 rows x 16 B]
-//   dA image (seq_bwd_tc.cu):  [slab            ][hi|lo][row group of 8][o/4, r|u|c   ][8 rows x 16 B]
-// One K block = one row group (8 rows) of one slab: for any range of kg / column quads it is ONE contiguous
-// piece of HBM, and once it sits in shared memory it already is a canonical MN-major no-swizzle UMMA operand
-// (4 consecutive kk -- or o -- in 16 bytes, the 8 rows 16 bytes apart, 128 bytes between quads).  So this kernel
-// has no producer threads: one thread issues cp.async.bulk loads into a 4-stage ring, one thread issues the
+//   G  image (seq_fwd_tc.cu):  [slab = cta*T + t][hi|lo][128 rows][KKP floats]   (row-major, kk order of the step)
+//   dA image (seq_bwd_tc.cu):  [slab            ][hi|lo][128 rows][192 floats]   (row-major, columns r|u|c)
+// Both operands of this GEMM are "MN-major" (the GEMM's K index is the image row, the contiguous index is kk / o).
+// For fp32/tf32 the tensor core reads MN-major operands in exactly one layout -- 128-byte rows of 32 values whose
+// 32-byte chunks are XOR-swizzled with the row index (tc_common.cuh) -- and that is what a TMA load with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B produces from a row-major image.  So this kernel has no producer threads:
+// one thread issues tensor-map TMA loads into a 4-stage ring (one K block = 8 image rows), one thread issues the
 // MMAs, eight warps only wake up to flush the TMEM accumulators into the CTA's split-K partial.
 //
-// Work split: the M dimension (kk, in K groups of 4) is cut into 128-row tiles at multiples of 32 kg; a tile
-// that straddles the x / gate-h / candidate-h parts of the image simply takes the union of the dA columns
-// those parts need (rows x columns that mean nothing are never read back).  Tiles are packed into "sets" of
-// at most 512 TMEM columns; a CTA owns one set and a contiguous range of K blocks, so every operand byte is
-// read once per set.  Sets get CTAs in proportion to their MMA cost; all CTAs run in one wave.
+// Work split: the M dimension (kk) is cut into 128-row tiles; a tile that straddles the x / gate-h / candidate-h
+// parts of the image simply takes the union of the dA columns those parts need (rows x columns that mean nothing
+// are never read back).  Tiles are packed into "sets" of at most 512 TMEM columns; a CTA owns one set and a
+// contiguous range of K blocks, so every operand byte is read once per set.  Sets get CTAs in proportion to their
+// MMA cost; all CTAs run in one wave.
 // The tensor core truncates when it adds into the fp32 accumulator (bias ~2e-8 per accumulation), so TMEM is
 // flushed into the partial every DWMM_FLUSH K blocks (640 rows), like dw_tc.cu.  dwmm_reduce_kernel then
 // sums the partials of each set in fixed order (deterministic) straight into dWg / dWc.
 // db is a plain column sum of the row-major dA (colsum kernels below).
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 #include "dw.cuh"
 #include "tc_common.cuh"
+#include "tmap.cuh"
 
 namespace dcgru {
 using namespace tc;
@@ -28,24 +33,30 @@ using namespace tc;
 constexpr int DWMM_NSTAGE = 4;
 constexpr int DWMM_FLUSH = 80;                       // K blocks between flushes (640 rows)
 constexpr int DWMM_THREADS = 320;                    // warp 0: loader, warp 1: MMA issuer, warps 2-9: flush
-constexpr int DWMM_TILE_BYTES = 32 * 128;            // one of hi / lo of a 32-kg tile
-constexpr int DWMM_STAGE_BYTES = DWMM_MAXTILE * 2 * DWMM_TILE_BYTES + 2 * 48 * 128;   // 44 KB
-constexpr int DWMM_SMEM = DWMM_NSTAGE * DWMM_STAGE_BYTES;
+constexpr int DWMM_TILE_BYTES = 4 * 1024;            // one of hi / lo of a 128-kk tile: 4 groups x (8 rows x 128 B)
+constexpr int DWMM_B_BYTES = 6 * 1024;               // one of hi / lo of the dA block: 6 groups of 32 columns
+constexpr int DWMM_STAGE_BYTES = DWMM_MAXTILE * 2 * DWMM_TILE_BYTES + 2 * DWMM_B_BYTES;   // 44 KB
+constexpr int DWMM_SMEM = DWMM_NSTAGE * DWMM_STAGE_BYTES + 1024;                            // + alignment slack
 
-__global__ void __launch_bounds__(DWMM_THREADS, 1) dw_mm_kernel(const DwmmParams p) {
-    extern __shared__ __align__(1024) uint8_t smem[];
+// timing experiment (DCGRU_DBG & 8): clock64 stamps of CTA 0, [K block][loader: top, waited, issued | issuer: top, full, accfree, issued]
+__device__ long long dwmm_dbg[256 * 8];
+
+__global__ void __launch_bounds__(DWMM_THREADS, 1) dw_mm_kernel(const DwmmParams p, const __grid_constant__ CUtensorMap tm_g,
+                                                                const __grid_constant__ CUtensorMap tm_d) {
+    extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_full[DWMM_NSTAGE], bar_empty[DWMM_NSTAGE], bar_accfull, bar_accempty;
     __shared__ uint32_t tmem_slot;
-    __shared__ uint64_t desc[DWMM_NSTAGE][DWMM_MAXTILE][4];          // [stage][tile][A hi, A lo, B hi, B lo]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // the swizzled operand tiles need 1024-byte aligned shared memory
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     // which set / split am I
     int si = 0;
     while (si + 1 < p.nset && (int)blockIdx.x >= p.set[si + 1].cta0) ++si;
     const DwmmSet& S = p.set[si];
+    const int ntile = S.ntile;
     const int split = blockIdx.x - S.cta0;
     const long kb0 = p.nkb * split / S.ncta, kb1 = p.nkb * (split + 1) / S.ncta;
     const int nkb = (int)(kb1 - kb0);
-    const int b_bytes = S.ogcnt * 128;                                // one of hi / lo of the dA block
 
     if (warp == 0) tmem_alloc<512>(&tmem_slot);
     if (tid == 0) {
@@ -53,22 +64,7 @@ __global__ void __launch_bounds__(DWMM_THREADS, 1) dw_mm_kernel(const DwmmParams
         mbar_init(&bar_accfull, 1);
         mbar_init(&bar_accempty, 8);
         mbar_fence_init();
-        for (int st = 0; st < DWMM_NSTAGE; ++st) {
-            const uint32_t base = smem_u32(smem + st * DWMM_STAGE_BYTES);
-            const uint32_t bbase = base + S.ntile * 2 * DWMM_TILE_BYTES;
-            for (int j = 0; j < S.ntile; ++j) {
-                // MN-major, one 8-row K group per MMA: quads are 128 B apart (both offset fields carry it)
-                desc[st][j][0] = make_smem_desc(base + (2 * j) * DWMM_TILE_BYTES, 128, 128);
-                desc[st][j][1] = make_smem_desc(base + (2 * j + 1) * DWMM_TILE_BYTES, 128, 128);
-                const uint32_t bo = (S.tile[j].og0 - S.ogmin) * 128;
-                desc[st][j][2] = make_smem_desc(bbase + bo, 128, 128);
-                desc[st][j][3] = make_smem_desc(bbase + b_bytes + bo, 128, 128);
-            }
-        }
     }
-    for (int idx = tid; idx < DWMM_SMEM / 16; idx += DWMM_THREADS)
-        reinterpret_cast<float4*>(smem)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-    fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -78,61 +74,82 @@ __global__ void __launch_bounds__(DWMM_THREADS, 1) dw_mm_kernel(const DwmmParams
     if (warp == 0) {
         // =================================== loader ================================================================
         if (lane == 0) {
-            const size_t g_rg = (size_t)p.KGT * 128, g_part = 16 * g_rg;            // row group / hi-lo part of G
-            const size_t d_rg = (size_t)48 * 128, d_part = 16 * d_rg;
-            uint32_t tx = 2 * b_bytes;
-            for (int j = 0; j < S.ntile; ++j) tx += 2 * S.tile[j].nkg * 128;
+            tma_prefetch_desc(&tm_g);
+            tma_prefetch_desc(&tm_d);
+            const uint32_t tx = ntile * 2 * DWMM_TILE_BYTES + 2 * DWMM_B_BYTES;     // out-of-bounds groups are zero-filled and counted
+            int grp[DWMM_MAXTILE];
+#pragma unroll
+            for (int j = 0; j < DWMM_MAXTILE; ++j) grp[j] = (j < ntile) ? S.tile[j].kg0 / 8 : 0;
             for (int i = 0; i < nkb; ++i) {
                 const int st = i % DWMM_NSTAGE;
+                const bool rec = p.dbg && blockIdx.x == 0 && i < 256;
+                if (rec) dwmm_dbg[i * 8 + 0] = clock64();
                 if (i >= DWMM_NSTAGE) mbar_wait(&bar_empty[st], ((i / DWMM_NSTAGE) - 1) & 1);
+                if (rec) dwmm_dbg[i * 8 + 1] = clock64();
                 const long kb = kb0 + i;
-                const size_t slab = (size_t)(kb >> 4);
-                const int rg = (int)(kb & 15);
+                // image row of the K block: slab = kb / 16, row group = kb % 16; the lo part is 128 rows further
+                const int row_hi = (int)((kb >> 4) * 256 + (kb & 15) * 8);
                 uint8_t* sbase = smem + st * DWMM_STAGE_BYTES;
                 mbar_expect_tx(&bar_full[st], tx);
-                const uint8_t* g = p.G + slab * 2 * g_part + rg * g_rg;
-                for (int j = 0; j < S.ntile; ++j) {
-                    const uint32_t bytes = S.tile[j].nkg * 128;
-                    bulk_g2s(sbase + (2 * j) * DWMM_TILE_BYTES, g + (size_t)S.tile[j].kg0 * 128, bytes, &bar_full[st]);
-                    bulk_g2s(sbase + (2 * j + 1) * DWMM_TILE_BYTES, g + g_part + (size_t)S.tile[j].kg0 * 128, bytes,
-                             &bar_full[st]);
-                }
-                const uint8_t* d = p.DA + slab * 2 * d_part + rg * d_rg + (size_t)S.ogmin * 128;
-                uint8_t* sb = sbase + S.ntile * 2 * DWMM_TILE_BYTES;
-                bulk_g2s(sb, d, b_bytes, &bar_full[st]);
-                bulk_g2s(sb + b_bytes, d + d_part, b_bytes, &bar_full[st]);
+#pragma unroll
+                for (int j = 0; j < DWMM_MAXTILE; ++j)
+                    if (j < ntile) {
+                        tma_load_3d(sbase + (2 * j) * DWMM_TILE_BYTES, &tm_g, 0, row_hi, grp[j], &bar_full[st]);
+                        tma_load_3d(sbase + (2 * j + 1) * DWMM_TILE_BYTES, &tm_g, 0, row_hi + 128, grp[j], &bar_full[st]);
+                    }
+                uint8_t* sb = sbase + DWMM_MAXTILE * 2 * DWMM_TILE_BYTES;
+                tma_load_3d(sb, &tm_d, 0, row_hi, 0, &bar_full[st]);
+                tma_load_3d(sb + DWMM_B_BYTES, &tm_d, 0, row_hi + 128, 0, &bar_full[st]);
+                if (rec) dwmm_dbg[i * 8 + 2] = clock64();
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         // =================================== MMA issuer ============================================================
+        // one thread issues every MMA: everything it needs per K block lives in registers (descriptors of stage 0;
+        // a stage is an address offset in the low word)
         if (lane == 0) {
+            uint64_t dah[DWMM_MAXTILE], dal[DWMM_MAXTILE], dbh[DWMM_MAXTILE], dbl[DWMM_MAXTILE];
             uint32_t idesc[DWMM_MAXTILE], dcol[DWMM_MAXTILE];
+            const uint32_t base = smem_u32(smem), bbase = base + DWMM_MAXTILE * 2 * DWMM_TILE_BYTES;
+#pragma unroll
             for (int j = 0; j < DWMM_MAXTILE; ++j) {
-                idesc[j] = make_idesc_tf32_mn(128, j < S.ntile ? S.tile[j].ncol : 64);
-                dcol[j] = taddr + (j < S.ntile ? S.tile[j].tcol : 0);
+                const int og0 = (j < ntile) ? S.tile[j].og0 : 0;
+                dah[j] = make_smem_desc_mn(base + (2 * j) * DWMM_TILE_BYTES, 1024, 512);
+                dal[j] = make_smem_desc_mn(base + (2 * j + 1) * DWMM_TILE_BYTES, 1024, 512);
+                dbh[j] = make_smem_desc_mn(bbase + (og0 / 8) * 1024, 1024, 512);
+                dbl[j] = make_smem_desc_mn(bbase + DWMM_B_BYTES + (og0 / 8) * 1024, 1024, 512);
+                idesc[j] = make_idesc_tf32_mn(128, j < ntile ? S.tile[j].ncol : 64);
+                dcol[j] = taddr + (j < ntile ? S.tile[j].tcol : 0);
             }
-            int since = 0, fl = 0;
+            int since = 0, fl = 0, st = 0, ph = 0;
             for (int i = 0; i < nkb; ++i) {
-                const int st = i % DWMM_NSTAGE;
-                mbar_wait(&bar_full[st], (i / DWMM_NSTAGE) & 1);
+                const bool rec = p.dbg && blockIdx.x == 0 && i < 256;
+                if (rec) dwmm_dbg[i * 8 + 3] = clock64();
+                mbar_wait(&bar_full[st], ph);
+                if (rec) dwmm_dbg[i * 8 + 4] = clock64();
                 if (since == 0 && fl > 0) mbar_wait(&bar_accempty, (fl - 1) & 1);   // the flush has read TMEM
+                if (rec) dwmm_dbg[i * 8 + 5] = clock64();
                 tc_fence_after();
                 const uint32_t acc = since > 0 ? 1u : 0u;
-                for (int j = 0; j < S.ntile; ++j) {
-                    const uint64_t ah = desc[st][j][0], al = desc[st][j][1], bh = desc[st][j][2], bl = desc[st][j][3];
-                    umma_tf32(dcol[j], al, bh, idesc[j], acc);      // small terms first
-                    umma_tf32(dcol[j], ah, bl, idesc[j], 1u);
-                    umma_tf32(dcol[j], ah, bh, idesc[j], 1u);
-                }
+                const uint64_t so = (uint64_t)((st * DWMM_STAGE_BYTES) >> 4);
+#pragma unroll
+                for (int j = 0; j < DWMM_MAXTILE; ++j)
+                    if (j < ntile) {
+                        umma_tf32(dcol[j], dal[j] + so, dbh[j] + so, idesc[j], acc);      // small terms first
+                        umma_tf32(dcol[j], dah[j] + so, dbl[j] + so, idesc[j], 1u);
+                        umma_tf32(dcol[j], dah[j] + so, dbh[j] + so, idesc[j], 1u);
+                    }
                 umma_commit(&bar_empty[st]);
+                if (rec) dwmm_dbg[i * 8 + 6] = clock64();
                 if (++since == DWMM_FLUSH || i == nkb - 1) { umma_commit(&bar_accfull); since = 0; ++fl; }
+                if (++st == DWMM_NSTAGE) { st = 0; ph ^= 1; }
             }
         }
         __syncwarp();
     } else {
         // =================================== flush warps ============================================================
-        // TMEM lane = tile row, so thread = row; the partial is stored [column][row]: a warp store is one 128-byte line
+        // TMEM lane = tile row, so thread = row; the partial is stored [column][row]: a warp access is one 128-byte line
         const int quad = warp & 3, half = (warp - 2) >> 2;
         const int row = 32 * quad + lane;
         const int ncolh = S.ncoltot / 2;
@@ -141,13 +158,19 @@ __global__ void __launch_bounds__(DWMM_THREADS, 1) dw_mm_kernel(const DwmmParams
             mbar_wait(&bar_accfull, f & 1);
             tc_fence_after();
             for (int cb = half * ncolh; cb < (half + 1) * ncolh; cb += 16) {
-                float v[16];
-                tmem_ld16(taddr + ((uint32_t)(32 * quad) << 16) + cb, v);
+                float v[16], o[16];
+                float* q = part + (size_t)cb * 128;
+                if (f > 0) {                                          // all 16 loads in flight before the TMEM read returns
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float* q = part + (size_t)(cb + j) * 128;
-                    *q = (f > 0) ? *q + v[j] : v[j];
+                    for (int j = 0; j < 16; ++j) o[j] = __ldcg(q + j * 128);
                 }
+                tmem_ld16(taddr + ((uint32_t)(32 * quad) << 16) + cb, v);
+                if (f > 0) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += o[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) __stcg(q + j * 128, v[j]);
             }
             tc_fence_before();
             __syncwarp();
@@ -159,6 +182,10 @@ __global__ void __launch_bounds__(DWMM_THREADS, 1) dw_mm_kernel(const DwmmParams
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc<512>(taddr);
+}
+
+cudaError_t dwmm_read_dbg(long long* out, int n) {
+    return cudaMemcpyFromSymbol(out, dwmm_dbg, sizeof(long long) * (n < 2048 ? n : 2048));
 }
 
 // dWg / dWc <- fixed-order sum of the partials.  One thread per (W row, column of r|u|c).
@@ -274,10 +301,30 @@ bool dwmm_plan(int fin, int H, int M, long nslab, int nsms, DwmmParams* out) {
 size_t dwmm_part_floats(int nsms) { return (size_t)nsms * 512 * 128; }
 size_t colsum_part_floats(int H) { return (size_t)CS_CTAS * 3 * H; }
 
-cudaError_t launch_dw_mm(const DwmmParams& p, int fin, int H, int M, float* dWg, float* dWc, cudaStream_t st) {
+cudaError_t launch_dw_mm(const DwmmParams& p_, int fin, int H, int M, float* dWg, float* dWc, cudaStream_t st) {
+    DwmmParams p = p_;
+    { const char* e = getenv("DCGRU_DBG"); p.dbg = e ? (atoi(e) & 8) : 0; }
+    // swizzling 3-D views of the row-major images: (32 floats = one 128-byte row piece | image row | 32-float group)
+    CUtensorMap tg, td;
+    const unsigned long long rows = (unsigned long long)(p.nkb / 16) * 256;
+    {
+        const unsigned long long kkp = seq_fwd_tc_kkp(fin);
+        const unsigned long long dims[3] = {32, rows, kkp / 32};
+        const unsigned long long str[3] = {4, kkp * 4, 128};
+        const unsigned box[3] = {32, 8, 4};
+        cudaError_t e = make_tmap_f32(&tg, p.G, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (e != cudaSuccess) return e;
+    }
+    {
+        const unsigned long long dims[3] = {32, rows, (unsigned long long)(3 * H / 32)};
+        const unsigned long long str[3] = {4, (unsigned long long)3 * H * 4, 128};
+        const unsigned box[3] = {32, 8, 6};
+        cudaError_t e = make_tmap_f32(&td, p.DA, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        if (e != cudaSuccess) return e;
+    }
     cudaError_t e = cudaFuncSetAttribute(dw_mm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DWMM_SMEM);
     if (e != cudaSuccess) return e;
-    dw_mm_kernel<<<p.ncta, DWMM_THREADS, DWMM_SMEM, st>>>(p);
+    dw_mm_kernel<<<p.ncta, DWMM_THREADS, DWMM_SMEM, st>>>(p, tg, td);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int n = (fin + H) * M * 3 * H;

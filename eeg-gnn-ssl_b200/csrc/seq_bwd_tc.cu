@@ -16,13 +16,15 @@
 // per step, pre-split / pre-tiled by pack_w_bwd_kernel, 3-slot ring).  Synchronisation is mbarrier-only
 // apart from two 128-thread named barriers around the diffT staging planes.
 // A slots are laid out [row group of 8][K group][8 rows x 16 B] (LBO = 128 B, SBO = 512 B).  Optional operand
-// image (daimg): warp 10 copies every finished A slot (hi and lo) to HBM with bulk stores into
-// DA[cta][t][hi|lo][row group][o/4 in r|u|c order][128 B] -- the B operand of the weight-gradient GEMM (dw_mm.cu).
+// image (daimg): warp 10 copies every finished A slot (hi and lo) to HBM with one tensor-map TMA store each into
+// the row-major image DA[cta*T + t][hi|lo][128 rows][192 columns r|u|c] -- the B operand of the weight-gradient
+// GEMM (dw_mm.cu).
 #include <cstring>
 
 #include "common.cuh"
 #include "dw.cuh"
 #include "tc_common.cuh"
+#include "tmap.cuh"
 
 namespace dcgru {
 using namespace tc;
@@ -126,7 +128,8 @@ __device__ __forceinline__ void prod_barrier() {             // the 8 producer w
 }
 // 32 lanes x 16 columns registers -> TMEM is not needed here; TMEM is only read (tmem_ld16)
 
-__global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcParams p) {
+__global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcParams p,
+                                                                   const __grid_constant__ CUtensorMap tm_d) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar_bfull[3], bar_afull[4], bar_cdone[4], bar_stored[4], bar_d1free, bar_d2free;
     __shared__ uint32_t tmem_slot;
@@ -220,24 +223,22 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
         __syncwarp();
     } else if (warp == 10) {
         // =================================== operand-image dump ==================================================
-        // lane = (hi|lo, row group): one 512-byte bulk store per finished A slot
-        if (dump) {
-            const int part = lane >> 4, rg = lane & 15;
-            const size_t rg_bytes = (size_t)(3 * BT_H / 4) * 128;           // 48 column quads
-            const size_t slab = 2 * 16 * rg_bytes;                          // one (cta, t)
-            uint8_t* gbase = p.daimg + (size_t)blockIdx.x * p.T * slab + ((size_t)part * 16 + rg) * rg_bytes;
-            const uint8_t* src0 = smem + BT_OFF_A + part * BT_A_BYTES + rg * (BT_RG_F4 * 16);
+        // one TMA tensor store per finished A slot part: box (4 o, 8 rows, 4 column quads, 16 row groups)
+        if (dump && lane == 0) {
+            tma_prefetch_desc(&tm_d);
             int q = 0, t = p.T - 1;
             for (unsigned g = 0; g < total_chunks; ++g) {
                 const int sa = g & 3;
                 // column quad of the chunk in [r | u | c] order: B1 = c, then u, then r
                 const int og0 = (q < 4) ? 32 + 4 * q : (q < 8 ? 16 + 4 * (q - 4) : 4 * (q - 8));
+                const int rg0 = (blockIdx.x * p.T + t) * 32;
                 mbar_wait(&bar_afull[sa], (g >> 2) & 1);
-                bulk_s2g(gbase + (size_t)t * slab + (size_t)og0 * 128, src0 + sa * BT_A_SLOT, BT_RG_F4 * 16);
+                const uint8_t* src = smem + BT_OFF_A + sa * BT_A_SLOT;
+                tma_store_4d(&tm_d, 0, 0, og0, rg0, src);
+                tma_store_4d(&tm_d, 0, 0, og0, rg0 + 16, src + BT_A_BYTES);
                 bulk_commit();
                 bulk_wait_read();
-                __syncwarp();
-                if (lane == 0) bt_arrive(&bar_stored[sa]);
+                bt_arrive(&bar_stored[sa]);
                 if (++q == BT_CHUNKS) { q = 0; --t; }
             }
             bulk_wait_all();
@@ -537,7 +538,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
 
 size_t seq_bwd_tc_wimg_bytes() { return (size_t)BT_CHUNKS * BT_B_SLOT; }
 size_t seq_bwd_tc_daimg_bytes(int B, int T) {
-    return (size_t)((B + BT_SB - 1) / BT_SB) * T * 2 * 16 * (3 * BT_H / 4) * 128;
+    return (size_t)((B + BT_SB - 1) / BT_SB) * T * 2 * 128 * 3 * BT_H * 4;
 }
 bool seq_bwd_tc_supported(int N, int H, int M, int smem_limit) {
     return H == BT_H && M == BT_M && N <= NP && BT_SMEM + 2304 <= smem_limit;
@@ -557,7 +558,17 @@ cudaError_t launch_seq_bwd_tc(int B, int T, int N, int fin, int act, const float
     p.daimg = reinterpret_cast<uint8_t*>(daimg);
     e = cudaFuncSetAttribute(seq_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM);
     if (e != cudaSuccess) return e;
-    seq_bwd_tc_kernel<<<(B + BT_SB - 1) / BT_SB, BT_THREADS, BT_SMEM, st>>>(p);
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof tm);
+    if (daimg) {
+        const unsigned long long rowb = 3 * BT_H * 4;
+        const unsigned long long dims[4] = {4, 8, 3 * BT_H / 4, (unsigned long long)((B + BT_SB - 1) / BT_SB) * T * 32};
+        const unsigned long long str[4] = {4, rowb, 16, 8 * rowb};
+        const unsigned box[4] = {4, 8, BT_KG, 16};
+        e = make_tmap_f32(&tm, daimg, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (e != cudaSuccess) return e;
+    }
+    seq_bwd_tc_kernel<<<(B + BT_SB - 1) / BT_SB, BT_THREADS, BT_SMEM, st>>>(p, tm);
     return cudaGetLastError();
 }
 
@@ -572,7 +583,9 @@ cudaError_t launch_dx_tc(int B, int T, int N, const float* P, const float* Wg, c
     p.mode = 1; p.B = B; p.T = T; p.N = N; p.P = P; p.wimg = wimg; p.dA = const_cast<float*>(dA); p.dx = dx;
     e = cudaFuncSetAttribute(seq_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM);
     if (e != cudaSuccess) return e;
-    seq_bwd_tc_kernel<<<(B + BT_SB - 1) / BT_SB, BT_THREADS, BT_SMEM, st>>>(p);
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof tm);
+    seq_bwd_tc_kernel<<<(B + BT_SB - 1) / BT_SB, BT_THREADS, BT_SMEM, st>>>(p, tm);
     return cudaGetLastError();
 }
 

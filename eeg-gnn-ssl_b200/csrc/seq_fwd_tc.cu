@@ -11,10 +11,11 @@
 // of 4 columns (20 broadcast float4 reads + 40 FMAs per column quad), splits them hi/lo and writes them
 // in kk = c*M + m order into a UMMA tile (2 stages) laid out [row group of 8][K group][8 rows x 16 B]
 // (canonical K-major no-swizzle: LBO = 128 B between K groups, SBO = 768 B between row groups).
-// Optional operand image (gsave): a dump warp copies every finished A stage (hi and lo) to HBM with bulk
-// stores, one 768-byte row-group slice per lane, into G[cta][t][hi|lo][row group][kg of the step][128 B].
-// In that layout an 8-row K block of the weight-gradient GEMM (dw_mm.cu) is one contiguous piece that is
-// already a valid MN-major UMMA operand, so dW needs no recomputation of the diffusion at all.
+// Optional operand image (gsave): a dump warp copies every finished A stage (hi and lo) to HBM with one
+// tensor-map TMA store each (a 4-D box that scatters the 16-byte words of the tile) into the row-major image
+// G[cta*T + t][hi|lo][128 rows][KKP floats]: the diffused operands [x | h | r*h] of every row in kk order.
+// The weight-gradient GEMM (dw_mm.cu) reads that image back with swizzling TMA loads as an MN-major UMMA
+// operand, so dW needs no recomputation of the diffusion at all.
 // B operand: the weights, pre-split and pre-tiled once per launch by pack_w_fwd_kernel, streamed chunk by
 // chunk from L2 with cp.async.bulk (TMA) into a 3-slot ring, each load issued one chunk ahead at the top
 // of the iteration so its latency hides behind two A-tile productions; mbarriers track "weights landed"
@@ -23,10 +24,12 @@
 // The epilogues read the accumulator with tcgen05.ld (thread = row) and fuse bias, sigmoid/tanh, r*h and
 // the GRU update.
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "dw.cuh"
 #include "tc_common.cuh"
+#include "tmap.cuh"
 
 namespace dcgru {
 using namespace tc;
@@ -133,7 +136,8 @@ __device__ __forceinline__ int ft_a_idx(int kg, int row) { return (row >> 3) * F
 
 // Warp-specialised: warps 0-7 build the A tiles and run the epilogues, warp 8 streams weights and x with TMA
 // and issues the MMAs; the only synchronisation inside a step is through mbarriers (no CTA-wide barrier).
-__global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcParams p) {
+__global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcParams p,
+                                                                   const __grid_constant__ CUtensorMap tm_g) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar_bfull[3], bar_xfull[FT_XRING], bar_afull[2], bar_done[2], bar_stored[2], bar_epi;
     __shared__ uint32_t tmem_slot;
@@ -263,24 +267,22 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
         __syncwarp();
     } else if (warp == 10) {
         // =================================== operand-image dump ==================================================
-        // lane = (hi|lo, row group): one 768-byte bulk store per finished A stage; the stage is released to the
-        // producers (bar_stored) once every lane's store has read its shared-memory source
-        if (dump) {
-            const int part = lane >> 4, rg = lane & 15;
-            const size_t kgt_bytes = (size_t)per_step * FT_KG * 128;       // one row group of a step
-            const size_t slab = 2 * 16 * kgt_bytes;                         // one (cta, t)
-            uint8_t* gdst = p.gsave + (size_t)blockIdx.x * p.T * slab + ((size_t)part * 16 + rg) * kgt_bytes;
-            const uint8_t* src0 = smem + FT_OFF_A + part * FT_A_BYTES + rg * (FT_RG_F4 * 16);
-            int q = 0;
+        // one TMA tensor store per finished A stage part: box (4 kk, 8 rows, 6 K groups, 16 row groups) = the
+        // stage part in shared-memory order, scattered into the row-major image.  The stage is released to the
+        // producers (bar_stored) once the stores have read their shared-memory source.
+        if (dump && lane == 0) {
+            tma_prefetch_desc(&tm_g);
+            int q = 0, rg0 = blockIdx.x * p.T * 32;                          // row-group coordinate of (cta, t = 0), hi part
             for (unsigned g = 0; g < total_chunks; ++g) {
                 const int sa = g & 1;
                 mbar_wait(&bar_afull[sa], (g >> 1) & 1);
-                bulk_s2g(gdst + (size_t)q * (FT_KG * 128), src0 + sa * FT_A_STAGE, FT_RG_F4 * 16);
+                const uint8_t* src = smem + FT_OFF_A + sa * FT_A_STAGE;
+                tma_store_4d(&tm_g, 0, 0, q * FT_KG, rg0, src);
+                tma_store_4d(&tm_g, 0, 0, q * FT_KG, rg0 + 16, src + FT_A_BYTES);
                 bulk_commit();
                 bulk_wait_read();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_stored[sa]);
-                if (++q == per_step) { q = 0; gdst += slab; }
+                mbar_arrive(&bar_stored[sa]);
+                if (++q == per_step) { q = 0; rg0 += 32; }
             }
             bulk_wait_all();
         }
@@ -501,8 +503,10 @@ size_t seq_fwd_tc_wimg_bytes(int fin) { return ft_wimg_bytes(fin); }
 // operand image geometry shared with dw_mm.cu: K groups per step, CTAs, bytes
 int seq_fwd_tc_kgt(int fin) { return (ft_nxc(fin) + 2 * (FT_H / FT_CC)) * FT_KG; }
 int seq_tc_nslab(int B, int T) { return ((B + FT_SB - 1) / FT_SB) * T; }
+// floats per image row: the kk of a step rounded up to whole 32-float groups (128-byte TMA rows)
+int seq_fwd_tc_kkp(int fin) { return (seq_fwd_tc_kgt(fin) * 4 + 31) / 32 * 32; }
 size_t seq_fwd_tc_gsave_bytes(int B, int T, int fin) {
-    return (size_t)seq_tc_nslab(B, T) * 2 * 16 * seq_fwd_tc_kgt(fin) * 128;
+    return (size_t)seq_tc_nslab(B, T) * 2 * 128 * seq_fwd_tc_kkp(fin) * 4;
 }
 bool seq_fwd_tc_supported(int N, int fin, int H, int M, int smem_limit) {
     return H == FT_H && M == FT_M && N <= NP && fin % 4 == 0 && FT_SMEM + 2304 <= smem_limit;
@@ -524,7 +528,18 @@ cudaError_t launch_seq_fwd_tc(int B, int T, int N, int fin, int act, const float
     p.dbgbuf = reinterpret_cast<long long*>(reinterpret_cast<uint8_t*>(wimg) + ((ft_wimg_bytes(fin) + 255) / 256) * 256);
     e = cudaFuncSetAttribute(seq_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM);
     if (e != cudaSuccess) return e;
-    seq_fwd_tc_kernel<<<(B + FT_SB - 1) / FT_SB, FT_THREADS, FT_SMEM, st>>>(p);
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof tm);
+    if (gsave) {
+        // 4-D view of the row-major image: (4 kk | row in group, stride = one row | K group, 16 B | row group)
+        const unsigned long long kkp = seq_fwd_tc_kkp(fin), rowb = kkp * 4;
+        const unsigned long long dims[4] = {4, 8, kkp / 4, (unsigned long long)seq_tc_nslab(B, T) * 32};
+        const unsigned long long str[4] = {4, rowb, 16, 8 * rowb};
+        const unsigned box[4] = {4, 8, FT_KG, 16};
+        e = make_tmap_f32(&tm, gsave, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (e != cudaSuccess) return e;
+    }
+    seq_fwd_tc_kernel<<<(B + FT_SB - 1) / FT_SB, FT_THREADS, FT_SMEM, st>>>(p, tm);
     return cudaGetLastError();
 }
 

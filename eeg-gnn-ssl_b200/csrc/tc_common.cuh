@@ -143,6 +143,30 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 // all committed groups are complete (the global writes are performed)
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 
+// ---- tensor-map TMA (cuTensorMapEncodeTiled descriptors passed as __grid_constant__ kernel parameters) --------
+// global (3-D box) -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+// shared -> global (4-D box), tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void tma_store_4d(const void* tmap, int c0, int c1, int c2, int c3, const void* smem_src) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];\n"
+                 ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(smem_src)) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(tmap) : "memory");
+}
+// MN-major fp32/tf32 operand: the only layout the tensor core accepts is "128-byte swizzle with 32-byte atoms"
+// (descriptor layout type 1; pinned with dcgru_tc_probe on a B200): element (mn, k) of a 128 x 8 tile lives at
+//   (mn/32)*LBO + (k/4)*SBO + (k%4)*128 + (((mn%32)/8) ^ (k%4))*32 + (mn%8)*4        [bytes]
+// i.e. row-major rows of 32 mn (128 B) whose four 32-byte chunks are XOR-ed with the row index -- exactly what a
+// TMA load with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B writes.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return make_smem_desc(saddr, lbo_bytes, sbo_bytes) | ((uint64_t)1 << 61);
+}
+
 // ---- 3xTF32 split ---------------------------------------------------------------------------------------
 // round-to-nearest on both parts keeps the representation error unbiased (a truncating split showed a
 // systematic ~3e-6 relative error at K=320 on hardware; with rounding it is random-walk ~1e-7)

@@ -76,6 +76,57 @@ __global__ void __launch_bounds__(NT, 1) tc_selftest_kernel(const float* A, cons
     if (warp == 0) tmem_dealloc<256>(taddr);
 }
 
+// Layout probe: ONE kind::tf32 MMA (128 x N x 8) over caller-provided raw shared-memory images of A and B with
+// caller-provided descriptor fields.  With one-hot / index-valued images the result shows which shared-memory
+// word the tensor core reads for a logical (row, k): that is how the MN-major operand layout of dw_mm.cu was
+// pinned down on hardware.
+__global__ void __launch_bounds__(128, 1) tc_probe_kernel(const float* Aimg, int a_bytes, const float* Bimg, int b_bytes,
+                                                          uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo,
+                                                          uint32_t idesc, uint32_t a_type, uint32_t b_type, float* D, int N) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float* sa = reinterpret_cast<float*>(smem_raw);
+    float* sb = reinterpret_cast<float*>(smem_raw + 16384);
+    for (int i = tid; i < a_bytes / 4; i += 128) sa[i] = Aimg[i];
+    for (int i = tid; i < b_bytes / 4; i += 128) sb[i] = Bimg[i];
+    if (warp == 0) tmem_alloc<256>(&tmem_slot);
+    if (tid == 0) { mbar_init(&mbar, 1); mbar_fence_init(); }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t taddr = tmem_slot;
+    if (tid == 0) {
+        const uint64_t da = make_smem_desc(smem_u32(sa), a_lbo, a_sbo) | ((uint64_t)a_type << 61);
+        const uint64_t db = make_smem_desc(smem_u32(sb), b_lbo, b_sbo) | ((uint64_t)b_type << 61);
+        umma_tf32(taddr, da, db, idesc, 0u);
+        umma_commit(&mbar);
+    }
+    mbar_wait(&mbar, 0);
+    tc_fence_after();
+    for (int cb = 0; cb < N; cb += 16) {
+        float v[16];
+        tmem_ld16(taddr + ((uint32_t)(32 * warp) << 16) + cb, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) D[(size_t)tid * N + cb + j] = v[j];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<256>(taddr);
+}
+
+cudaError_t launch_tc_probe(const float* Aimg, int a_bytes, const float* Bimg, int b_bytes, uint32_t a_lbo, uint32_t a_sbo,
+                            uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc, uint32_t a_type, uint32_t b_type, float* D, int N,
+                            cudaStream_t st) {
+    const int smem = 32768;
+    cudaError_t e = cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    tc_probe_kernel<<<1, 128, smem, st>>>(Aimg, a_bytes, Bimg, b_bytes, a_lbo, a_sbo, b_lbo, b_sbo, idesc, a_type, b_type, D, N);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_tc_selftest(const float* A, const float* B, float* C, int N, int K, cudaStream_t st) {
     int smem = 2 * (2 * 128 * ST_KC * 4 + 2 * N * ST_KC * 4);
     cudaError_t e = cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -64,6 +64,13 @@ int dcgru_timing_collect(char *buf, size_t cap);
  * C[128 x N] = A[128 x K] * B[N x K]^T in 3xTF32 (fp32-level accuracy); A, B, C device pointers,
  * row-major, K % 32 == 0, N in {64, 128, 192, 256}.                                              */
 int dcgru_tc_selftest(const float *A, const float *B, float *C, int32_t N, int32_t K, void *stream);
+/* Layout probe: one kind::tf32 MMA D[128 x N] = A[128 x 8] * B[N x 8]^T over raw shared-memory images of the
+ * operands (device pointers, copied verbatim into shared memory) with the given descriptor byte offsets,
+ * major-ness and layout type (descriptor bits 61-63: 0 none, 1 128B swizzle with 32B base, 2 128B, 4 64B, 6 32B).  tests/test_gpu_tc.py uses it to pin the operand layouts the kernels rely on.              */
+int dcgru_tc_probe(const float *a_img, int32_t a_bytes, const float *b_img, int32_t b_bytes,
+                   uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo,
+                   int32_t a_mn_major, int32_t b_mn_major, int32_t a_layout_type, int32_t b_layout_type,
+                   float *D, int32_t N, void *stream);
 
 /* ---- graph -> diffusion polynomials -------------------------------------------------------
  * Replaces the hop recurrence of DiffusionGraphConv.forward (model/cell.py:76-93): since
@@ -118,6 +125,8 @@ size_t dcgru_encoder_layer_bwd_workspace(const dcgru_cell_desc *d, int32_t batch
  * dA operand image, per-CTA partials of the weight-gradient GEMM} (0 = not used by this configuration). */
 int dcgru_debug_encoder_bwd_offsets(const dcgru_cell_desc *d, int32_t batch, int32_t seq_len,
                                     size_t *out3);
+/* clock64 stamps of the weight-gradient GEMM's loader / MMA-issuer threads (recorded when DCGRU_DBG & 8) */
+int dcgru_debug_dwmm_stamps(long long *out, int32_t n);
 
 /* Backward of the above (what autograd derives for the reference).
  * d_hseq:  (T,B,N*H) upstream gradient of h_seq (NULL = zeros)

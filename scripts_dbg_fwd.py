@@ -16,12 +16,12 @@ hseq = torch.empty(T, B, N * H, device=dev); ruc = torch.empty(T, B, N, 3 * H, d
 prm = ops._params([tuple(p.detach() for p in cell.flat_params())])
 for _ in range(2):
     _lib.check(L.dcgru_encoder_layer_fwd(C.byref(desc), B, T, ops._ptr(x), x.stride(0), x.stride(1), ops._ptr(h0), ops._ptr(P), prm,
-                                     ops._ptr(hseq), ops._ptr(ruc), ops._ptr(ws), nb, ops._stream()), "fwd")
+                                     ops._ptr(hseq), ops._ptr(ruc), None, 0, ops._ptr(ws), nb, ops._stream()), "fwd")
 torch.cuda.synchronize()
 wimg = 13 * 36864 + 8 * (24576 + 12288)
 off = (wimg + 255) // 256 * 256
 d = ws[off:off + 128 * 64].view(torch.int64).cpu().numpy().reshape(128, 8)
 t0 = d[0, 0]
 print("g  iss:start bfull afull issued | prod:start gotdone produced arrived   (cycles rel.)")
-for g in range(0, 64):
+for g in range(0, 96):
     print(g, *(int(v - t0) for v in d[g]))

@@ -73,11 +73,10 @@ def _run_layer(dev, B, T, fin, seed, use_gsave, want_dx=False):
                 dh0=dh0, dx=dx, gbytes=gbytes)
 
 
-def _unimage(buf, nslab, nq):
-    """[slab][hi|lo][16 row groups][nq quads][8 rows][4] bytes -> float64 (slab, 128 rows, nq*4)"""
-    t = buf.view(torch.float32).view(nslab, 2, 16, nq, 8, 4).double()
-    t = t[:, 0] + t[:, 1]
-    return t.permute(0, 1, 3, 2, 4).reshape(nslab, 128, nq * 4)
+def _unimage(buf, nslab, width, used):
+    """row-major image [slab][hi|lo][128 rows][width floats] (bytes) -> float64 hi + lo, first `used` columns"""
+    t = buf.view(torch.float32).view(nslab, 2, 128, width).double()
+    return (t[:, 0] + t[:, 1])[..., :used].contiguous()
 
 
 def _expected_g(r, B, T, fin):
@@ -114,7 +113,8 @@ def test_operand_images_and_gemm(dev, B, T, fin):
     nslab = ncta * T
     kgt = ((fin + 7) // 8 + 16) * 6
     # (1) G image
-    gimg = _unimage(r["gsave"], nslab, kgt)
+    kkp = (kgt * 4 + 31) // 32 * 32
+    gimg = _unimage(r["gsave"], nslab, kkp, kgt * 4)
     gexp = _expected_g(r, B, T, fin)
     eg = float((gimg - gexp).abs().max() / gexp.abs().max())
     print(f"G image vs torch: {eg:.2e}")
@@ -123,7 +123,7 @@ def test_operand_images_and_gemm(dev, B, T, fin):
     o_da, o_img, _ = r["off"]
     assert o_img > 0
     da = r["bws"][o_da: o_da + T * B * N * 3 * H * 4].view(torch.float32).view(T, B, N, 3 * H).double()
-    dimg = _unimage(r["bws"][o_img: o_img + nslab * 2 * 16 * 48 * 128], nslab, 48).view(ncta, T, 128, 3 * H)
+    dimg = _unimage(r["bws"][o_img: o_img + nslab * 2 * 128 * 3 * H * 4], nslab, 3 * H, 3 * H).view(ncta, T, 128, 3 * H)
     dexp = torch.zeros_like(dimg)
     for b in range(B):
         c, s = divmod(b, 6)

@@ -133,8 +133,10 @@ __global__ void __launch_bounds__(DWMM_THREADS, 1) dw_mm_kernel(const DwmmParams
                 tc_fence_after();
                 const uint32_t acc = since > 0 ? 1u : 0u;
                 const uint64_t so = (uint64_t)((st * DWMM_STAGE_BYTES) >> 4);
+                // narrow tiles first: the wide (long-running) MMAs are still queued while this thread waits for the
+                // next stage, so the tensor pipe does not drain between K blocks
 #pragma unroll
-                for (int j = 0; j < DWMM_MAXTILE; ++j)
+                for (int j = DWMM_MAXTILE - 1; j >= 0; --j)
                     if (j < ntile) {
                         umma_tf32(dcol[j], dal[j] + so, dbh[j] + so, idesc[j], acc);      // small terms first
                         umma_tf32(dcol[j], dah[j] + so, dbl[j] + so, idesc[j], 1u);
@@ -152,32 +154,36 @@ __global__ void __launch_bounds__(DWMM_THREADS, 1) dw_mm_kernel(const DwmmParams
         // TMEM lane = tile row, so thread = row; the partial is stored [column][row]: a warp access is one 128-byte line
         const int quad = warp & 3, half = (warp - 2) >> 2;
         const int row = 32 * quad + lane;
-        const int ncolh = S.ncoltot / 2;
+        const int csplit = ((S.ncoltot / 64 + 1) / 2) * 64;             // columns are handed out in blocks of 64
+        const int c_begin = half ? csplit : 0, c_end = half ? S.ncoltot : csplit;
         float* part = p.part + (size_t)blockIdx.x * 512 * 128 + row;
         for (int f = 0; f < nflush; ++f) {
             mbar_wait(&bar_accfull, f & 1);
             tc_fence_after();
-            for (int cb = half * ncolh; cb < (half + 1) * ncolh; cb += 16) {
-                float v[16], o[16];
+            for (int cb = c_begin; cb < c_end; cb += 64) {
+                float o[64];
                 float* q = part + (size_t)cb * 128;
-                if (f > 0) {                                          // all 16 loads in flight before the TMEM read returns
+                if (f > 0) {                                          // 64 loads in flight per thread: the partial comes back from HBM
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) o[j] = __ldcg(q + j * 128);
-                }
-                tmem_ld16(taddr + ((uint32_t)(32 * quad) << 16) + cb, v);
-                if (f > 0) {
+                    for (int j = 0; j < 64; ++j) o[j] = __ldcg(q + j * 128);
+                } else {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += o[j];
+                    for (int j = 0; j < 64; ++j) o[j] = 0.f;
                 }
 #pragma unroll
-                for (int j = 0; j < 16; ++j) __stcg(q + j * 128, v[j]);
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    float v[16];
+                    tmem_ld16(taddr + ((uint32_t)(32 * quad) << 16) + cb + 16 * c4, v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) __stcg(q + (16 * c4 + j) * 128, v[j] + o[16 * c4 + j]);
+                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_accempty);
         }
         if (nflush == 0)                                                // CTA without work: zero partial
-            for (int cb = half * ncolh; cb < (half + 1) * ncolh; ++cb) part[(size_t)cb * 128] = 0.f;
+            for (int cb = c_begin; cb < c_end; ++cb) part[(size_t)cb * 128] = 0.f;
     }
     tc_fence_before();
     __syncthreads();

@@ -15,7 +15,7 @@
 // Roles: warps 0-7 elementwise + A tiles + diffT, warp 8 MMA issue, warp 9 TMA weight loads (12 chunk blocks
 // per step, pre-split / pre-tiled by pack_w_bwd_kernel, 3-slot ring).  Synchronisation is mbarrier-only
 // apart from two 128-thread named barriers around the diffT staging planes.
-// A slots are laid out [row group of 8][K group][8 rows x 16 B] (LBO = 128 B, SBO = 512 B).  Optional operand
+// A slots are laid out [row group of 8][K-group pair][8 rows x 32 B] (K-major, 32-byte swizzle, SBO = 512 B).  Optional operand
 // image (daimg): warp 10 copies every finished A slot (hi and lo) to HBM with one tensor-map TMA store each into
 // the row-major image DA[cta*T + t][hi|lo][128 rows][192 columns r|u|c] -- the B operand of the weight-gradient
 // GEMM (dw_mm.cu).
@@ -46,7 +46,7 @@ constexpr int BT_OFF_A = 0;                                // 4 slots
 constexpr int BT_OFF_B = BT_OFF_A + 4 * BT_A_SLOT;         // 3 slots
 constexpr int BT_OFF_S = BT_OFF_B + 3 * BT_B_SLOT;         // 2 planes [128][36] (also the IO tiles 0)
 constexpr int BT_OFF_DH = BT_OFF_S + 2 * BT_ROWS * BT_PLD * 4;
-constexpr int BT_SMEM = BT_OFF_DH + BT_ROWS * BT_DLD * 4;
+constexpr int BT_SMEM = BT_OFF_DH + BT_ROWS * BT_DLD * 4 + 1024;   // + slack: the swizzled slots need an aligned base
 constexpr int BT_NPROD = 256;
 constexpr int BT_THREADS = 352;                            // + warp 10: operand-image dump
 constexpr int BT_RG_F4 = BT_KG * 8;                        // float4s per 8-row group of an A slot (512 B)
@@ -130,7 +130,8 @@ __device__ __forceinline__ void prod_barrier() {             // the 8 producer w
 
 __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcParams p,
                                                                    const __grid_constant__ CUtensorMap tm_d) {
-    extern __shared__ __align__(1024) uint8_t smem[];
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     __shared__ uint64_t bar_bfull[3], bar_afull[4], bar_cdone[4], bar_stored[4], bar_d1free, bar_d2free;
     __shared__ uint32_t tmem_slot;
     __shared__ uint64_t dA_desc[4][2][2];                    // [slot][k-step][hi, lo]
@@ -149,9 +150,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
         mbar_fence_init();
         for (int sl = 0; sl < 4; ++sl)
             for (int k = 0; k < 2; ++k) {
-                const uint32_t hi = smem_u32(smem + BT_OFF_A + sl * BT_A_SLOT) + 2 * k * 128;
-                dA_desc[sl][k][0] = make_smem_desc(hi, 128, BT_RG_F4 * 16);
-                dA_desc[sl][k][1] = make_smem_desc(hi + BT_A_BYTES, 128, BT_RG_F4 * 16);
+                const uint32_t hi = smem_u32(smem + BT_OFF_A + sl * BT_A_SLOT) + k * 256;
+                dA_desc[sl][k][0] = make_smem_desc_k32(hi, BT_RG_F4 * 16);
+                dA_desc[sl][k][1] = make_smem_desc_k32(hi + BT_A_BYTES, BT_RG_F4 * 16);
             }
         for (int sl = 0; sl < 3; ++sl)
             for (int k = 0; k < 2; ++k) {
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
         __syncwarp();
     } else if (warp == 10) {
         // =================================== operand-image dump ==================================================
-        // one TMA tensor store per finished A slot part: box (4 o, 8 rows, 4 column quads, 16 row groups)
+        // one TMA tensor store per finished A slot part: box (8 o, 8 rows, 2 column octets, 16 row groups)
         if (dump && lane == 0) {
             tma_prefetch_desc(&tm_d);
             int q = 0, t = p.T - 1;
@@ -234,8 +235,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
                 const int rg0 = (blockIdx.x * p.T + t) * 32;
                 mbar_wait(&bar_afull[sa], (g >> 2) & 1);
                 const uint8_t* src = smem + BT_OFF_A + sa * BT_A_SLOT;
-                tma_store_4d(&tm_d, 0, 0, og0, rg0, src);
-                tma_store_4d(&tm_d, 0, 0, og0, rg0 + 16, src + BT_A_BYTES);
+                tma_store_4d(&tm_d, 0, 0, og0 / 2, rg0, src);
+                tma_store_4d(&tm_d, 0, 0, og0 / 2, rg0 + 16, src + BT_A_BYTES);
                 bulk_commit();
                 bulk_wait_read();
                 bt_arrive(&bar_stored[sa]);
@@ -313,8 +314,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
                     float4 h, l;
                     split4(make_float4(v[16 * sub + 4 * kg], v[16 * sub + 4 * kg + 1], v[16 * sub + 4 * kg + 2],
                                        v[16 * sub + 4 * kg + 3]), h, l);
-                    a_hi[(row >> 3) * BT_RG_F4 + kg * 8 + (row & 7)] = h;
-                    a_lo[(row >> 3) * BT_RG_F4 + kg * 8 + (row & 7)] = l;
+                    a_hi[k32_idx<BT_KG / 2>(kg, row)] = h;
+                    a_lo[k32_idx<BT_KG / 2>(kg, row)] = l;
                 }
                 fence_async_smem();
             }
@@ -562,10 +563,10 @@ cudaError_t launch_seq_bwd_tc(int B, int T, int N, int fin, int act, const float
     memset(&tm, 0, sizeof tm);
     if (daimg) {
         const unsigned long long rowb = 3 * BT_H * 4;
-        const unsigned long long dims[4] = {4, 8, 3 * BT_H / 4, (unsigned long long)((B + BT_SB - 1) / BT_SB) * T * 32};
-        const unsigned long long str[4] = {4, rowb, 16, 8 * rowb};
-        const unsigned box[4] = {4, 8, BT_KG, 16};
-        e = make_tmap_f32(&tm, daimg, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+        const unsigned long long dims[4] = {8, 8, 3 * BT_H / 8, (unsigned long long)((B + BT_SB - 1) / BT_SB) * T * 32};
+        const unsigned long long str[4] = {4, rowb, 32, 8 * rowb};
+        const unsigned box[4] = {8, 8, BT_KG / 2, 16};
+        e = make_tmap_f32(&tm, daimg, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_32B);
         if (e != cudaSuccess) return e;
     }
     seq_bwd_tc_kernel<<<(B + BT_SB - 1) / BT_SB, BT_THREADS, BT_SMEM, st>>>(p, tm);

@@ -9,10 +9,10 @@
 // A operand: each thread owns one (sample, node) row and keeps that row of the diffusion polynomials P_m
 // in registers for the whole sequence; for every 8-column chunk of [x | h] it forms the M diffusion terms
 // of 4 columns (20 broadcast float4 reads + 40 FMAs per column quad), splits them hi/lo and writes them
-// in kk = c*M + m order into a UMMA tile (2 stages) laid out [row group of 8][K group][8 rows x 16 B]
-// (canonical K-major no-swizzle: LBO = 128 B between K groups, SBO = 768 B between row groups).
+// in kk = c*M + m order into a UMMA tile (2 stages) laid out [row group of 8][K-group pair][8 rows x 32 B]
+// (K-major, 32-byte swizzle: one MMA k-step = one 256-byte atom per row group, SBO = 768 B between row groups).
 // Optional operand image (gsave): a dump warp copies every finished A stage (hi and lo) to HBM with one
-// tensor-map TMA store each (a 4-D box that scatters the 16-byte words of the tile) into the row-major image
+// tensor-map TMA store each (a 4-D box that scatters the 32-byte row pieces of the tile) into the row-major image
 // G[cta*T + t][hi|lo][128 rows][KKP floats]: the diffused operands [x | h | r*h] of every row in kk order.
 // The weight-gradient GEMM (dw_mm.cu) reads that image back with swizzling TMA loads as an MN-major UMMA
 // operand, so dW needs no recomputation of the diffusion at all.
@@ -55,7 +55,7 @@ constexpr int FT_OFF_B = FT_OFF_A + 2 * FT_A_STAGE;        // 3 slots
 constexpr int FT_OFF_X = FT_OFF_B + 3 * FT_BX_BYTES;       // 3 slots
 constexpr int FT_XRING = 4;                                // x chunk ring slots (prefetch distance 2, race-free)
 constexpr int FT_OFF_ZH = FT_OFF_X + FT_XRING * FT_XSLOT;  // [128][64] hidden state (or r*h)
-constexpr int FT_SMEM = FT_OFF_ZH + FT_ROWS * FT_ZLD * 4;
+constexpr int FT_SMEM = FT_OFF_ZH + FT_ROWS * FT_ZLD * 4 + 1024;   // + slack: the swizzled tiles need an aligned base
 
 __host__ __device__ inline int ft_nxc(int fin) { return (fin + FT_CC - 1) / FT_CC; }
 __host__ __device__ inline size_t ft_wimg_bytes(int fin) {
@@ -132,13 +132,14 @@ __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.
 constexpr int FT_NPROD = 256;            // producer / epilogue threads (warps 0-7)
 constexpr int FT_THREADS = 352;          // + warp 8: MMA issue, warp 9: TMA weight loads, warp 10: operand-image dump
 constexpr int FT_RG_F4 = FT_KG * 8;      // float4s per 8-row group of an A tile (768 B)
-__device__ __forceinline__ int ft_a_idx(int kg, int row) { return (row >> 3) * FT_RG_F4 + kg * 8 + (row & 7); }
+__device__ __forceinline__ int ft_a_idx(int kg, int row) { return k32_idx<FT_KG / 2>(kg, row); }
 
 // Warp-specialised: warps 0-7 build the A tiles and run the epilogues, warp 8 streams weights and x with TMA
 // and issues the MMAs; the only synchronisation inside a step is through mbarriers (no CTA-wide barrier).
 __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcParams p,
                                                                    const __grid_constant__ CUtensorMap tm_g) {
-    extern __shared__ __align__(1024) uint8_t smem[];
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     __shared__ uint64_t bar_bfull[3], bar_xfull[FT_XRING], bar_afull[2], bar_done[2], bar_stored[2], bar_epi;
     __shared__ uint32_t tmem_slot;
     __shared__ __align__(16) float sbias[3 * FT_H];                      // bg (r | u) | bc
@@ -190,9 +191,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
         if (lane == 0) {
             for (int st = 0; st < 2; ++st)
                 for (int k = 0; k < 3; ++k) {
-                    const uint32_t hi = smem_u32(smem + FT_OFF_A + st * FT_A_STAGE) + 2 * k * 128;
-                    dA[st][k][0] = make_smem_desc(hi, 128, FT_RG_F4 * 16);
-                    dA[st][k][1] = make_smem_desc(hi + FT_A_BYTES, 128, FT_RG_F4 * 16);
+                    const uint32_t hi = smem_u32(smem + FT_OFF_A + st * FT_A_STAGE) + k * 256;
+                    dA[st][k][0] = make_smem_desc_k32(hi, FT_RG_F4 * 16);
+                    dA[st][k][1] = make_smem_desc_k32(hi + FT_A_BYTES, FT_RG_F4 * 16);
                 }
             for (int sl = 0; sl < 3; ++sl)
                 for (int kind = 0; kind < 3; ++kind) {
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
         __syncwarp();
     } else if (warp == 10) {
         // =================================== operand-image dump ==================================================
-        // one TMA tensor store per finished A stage part: box (4 kk, 8 rows, 6 K groups, 16 row groups) = the
+        // one TMA tensor store per finished A stage part: box (8 kk, 8 rows, 3 K-group pairs, 16 row groups) = the
         // stage part in shared-memory order, scattered into the row-major image.  The stage is released to the
         // producers (bar_stored) once the stores have read their shared-memory source.
         if (dump && lane == 0) {
@@ -277,8 +278,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
                 const int sa = g & 1;
                 mbar_wait(&bar_afull[sa], (g >> 1) & 1);
                 const uint8_t* src = smem + FT_OFF_A + sa * FT_A_STAGE;
-                tma_store_4d(&tm_g, 0, 0, q * FT_KG, rg0, src);
-                tma_store_4d(&tm_g, 0, 0, q * FT_KG, rg0 + 16, src + FT_A_BYTES);
+                tma_store_4d(&tm_g, 0, 0, q * (FT_KG / 2), rg0, src);
+                tma_store_4d(&tm_g, 0, 0, q * (FT_KG / 2), rg0 + 16, src + FT_A_BYTES);
                 bulk_commit();
                 bulk_wait_read();
                 mbar_arrive(&bar_stored[sa]);
@@ -363,10 +364,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
             float4 f2 = make_float4(a2[2], v0[3], a1[3], a2[3]);
             float4 h, l;
             const int kg0 = half * 3;
-            const int ai = ft_a_idx(kg0, row);
-            split4(f0, h, l); a_hi[ai] = h; a_lo[ai] = l;
-            split4(f1, h, l); a_hi[ai + 8] = h; a_lo[ai + 8] = l;
-            split4(f2, h, l); a_hi[ai + 16] = h; a_lo[ai + 16] = l;
+            const int ai0 = ft_a_idx(kg0, row), ai1 = ft_a_idx(kg0 + 1, row), ai2 = ft_a_idx(kg0 + 2, row);
+            split4(f0, h, l); a_hi[ai0] = h; a_lo[ai0] = l;
+            split4(f1, h, l); a_hi[ai1] = h; a_lo[ai1] = l;
+            split4(f2, h, l); a_hi[ai2] = h; a_lo[ai2] = l;
             if (rec) p.dbgbuf[g * 8 + 6] = clock64();
             fence_async_smem();
             __syncwarp();
@@ -531,12 +532,12 @@ cudaError_t launch_seq_fwd_tc(int B, int T, int N, int fin, int act, const float
     CUtensorMap tm;
     memset(&tm, 0, sizeof tm);
     if (gsave) {
-        // 4-D view of the row-major image: (4 kk | row in group, stride = one row | K group, 16 B | row group)
+        // 4-D view of the row-major image: (8 kk | row in group, stride = one row | K-group pair, 32 B | row group)
         const unsigned long long kkp = seq_fwd_tc_kkp(fin), rowb = kkp * 4;
-        const unsigned long long dims[4] = {4, 8, kkp / 4, (unsigned long long)seq_tc_nslab(B, T) * 32};
-        const unsigned long long str[4] = {4, rowb, 16, 8 * rowb};
-        const unsigned box[4] = {4, 8, FT_KG, 16};
-        e = make_tmap_f32(&tm, gsave, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+        const unsigned long long dims[4] = {8, 8, kkp / 8, (unsigned long long)seq_tc_nslab(B, T) * 32};
+        const unsigned long long str[4] = {4, rowb, 32, 8 * rowb};
+        const unsigned box[4] = {8, 8, FT_KG / 2, 16};
+        e = make_tmap_f32(&tm, gsave, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_32B);
         if (e != cudaSuccess) return e;
     }
     seq_fwd_tc_kernel<<<(B + FT_SB - 1) / FT_SB, FT_THREADS, FT_SMEM, st>>>(p, tm);

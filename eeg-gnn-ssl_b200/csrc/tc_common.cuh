@@ -158,6 +158,19 @@ __device__ __forceinline__ void tma_store_4d(const void* tmap, int c0, int c1, i
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(tmap) : "memory");
 }
+// K-major operand with the 32-byte swizzle (descriptor layout type 6): rows of 8 k (32 B), 8 rows = one 256-byte
+// atom, next 8 rows SBO further; the two 16-byte halves of a row are swapped in rows 4-7 of every atom (address
+// bit 4 ^= bit 7), which makes thread-per-row 16-byte stores conflict free and lets a TMA store with
+// CU_TENSOR_MAP_SWIZZLE_32B move whole 32-byte row pieces.  The tile base must be 256-byte aligned.
+__device__ __forceinline__ uint64_t make_smem_desc_k32(uint32_t saddr, uint32_t sbo_bytes) {
+    return make_smem_desc(saddr, 16, sbo_bytes) | ((uint64_t)6 << 61);
+}
+// float4 index of (row, K group kg) inside a tile of NKP K-group pairs laid out [row group][pair][8 rows][32 B]
+template <int NKP>
+__device__ __forceinline__ int k32_idx(int kg, int row) {
+    return (row >> 3) * (NKP * 16) + (kg >> 1) * 16 + (row & 7) * 2 + ((kg & 1) ^ ((row >> 2) & 1));
+}
+
 // MN-major fp32/tf32 operand: the only layout the tensor core accepts is "128-byte swizzle with 32-byte atoms"
 // (descriptor layout type 1; pinned with dcgru_tc_probe on a B200): element (mn, k) of a 128 x 8 tile lives at
 //   (mn/32)*LBO + (k/4)*SBO + (k%4)*128 + (((mn%32)/8) ^ (k%4))*32 + (mn%8)*4        [bytes]

@@ -24,15 +24,25 @@ def a_onehot_kmajor():
 # values must be exact in tf32 (10-bit mantissa): use word index for < 2048 words
 aidx = np.arange(2048, dtype=np.float32)
 print("== A MN-major, layout types")
-for (atype, albo, asbo) in [(1, 1024, 512), (1, 512, 1024), (1, 1024, 2048), (1, 2048, 512), (2, 1024, 512), (2, 1024, 1024), (4, 512, 512), (6, 256, 256)]:
+for (atype, albo, asbo) in [(1, 1024, 512)]:
     D = run(aimg=aidx, bimg=b_onehot_kmajor(), albo=albo, asbo=asbo, blbo=256, bsbo=128, amn=1, bmn=0, atype=atype)
     print(f"A probe: MN-major type={atype} lbo={albo} sbo={asbo}: word index read for (m, k=0..7):")
     for m in (0, 1, 2, 3, 4, 7, 8, 9, 15, 16, 24, 31, 32, 33, 63, 64, 96, 127):
         print(f"   m={m:3d}:", [int(D[m, k]) if np.isfinite(D[m, k]) else None for k in range(8)])
 print("== B MN-major, layout types")
 bidx = np.arange(2048, dtype=np.float32)
-for (btype, blbo, bsbo) in [(1, 1024, 512), (1, 512, 1024), (2, 1024, 512)]:
+for (btype, blbo, bsbo) in [(1, 1024, 512)]:
     D = run(aimg=a_onehot_kmajor(), bimg=bidx, albo=2048, asbo=128, blbo=blbo, bsbo=bsbo, amn=0, bmn=1, btype=btype, N=64)
     print(f"B probe: MN-major type={btype} lbo={blbo} sbo={bsbo}: word index read for (n, k=0..7):")
     for n in (0, 1, 2, 3, 4, 7, 8, 9, 15, 16, 24, 31, 32, 33, 63):
         print(f"   n={n:3d}:", [int(D[k, n]) if np.isfinite(D[k, n]) else None for k in range(8)])
+print("== A K-major, 32B swizzle (type 6): expect (m/8)*64 + (m%8)*8 + ((k/4)^((m%8)>>2))*4 + k%4")
+D = run(aimg=aidx, bimg=b_onehot_kmajor(), albo=16, asbo=256, blbo=256, bsbo=128, amn=0, bmn=0, atype=6)
+ok = True
+for m in range(128):
+    for k in range(8):
+        exp = (m // 8) * 64 + (m % 8) * 8 + ((k // 4) ^ ((m % 8) >> 2)) * 4 + k % 4
+        ok &= int(D[m, k]) == exp
+print("K-major SW32 layout as expected:", ok)
+for m in (0, 1, 3, 4, 5, 7, 8, 12):
+    print(f"   m={m:3d}:", [int(D[m, k]) for k in range(8)])

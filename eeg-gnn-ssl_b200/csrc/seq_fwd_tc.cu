@@ -130,6 +130,7 @@ __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 
 __device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
 constexpr int FT_NPROD = 256;            // producer / epilogue threads (warps 0-7)
+constexpr int FT_STASH = 192;            // TMEM columns 192..255: h_{t-1}, thread = row (the accumulator uses 0..191)
 constexpr int FT_THREADS = 352;          // + warp 8: MMA issue, warp 9: TMA weight loads, warp 10: operand-image dump
 constexpr int FT_RG_F4 = FT_KG * 8;      // float4s per 8-row group of an A tile (768 B)
 __device__ __forceinline__ int ft_a_idx(int kg, int row) { return k32_idx<FT_KG / 2>(kg, row); }
@@ -276,12 +277,16 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
             int q = 0, rg0 = blockIdx.x * p.T * 32;                          // row-group coordinate of (cta, t = 0), hi part
             for (unsigned g = 0; g < total_chunks; ++g) {
                 const int sa = g & 1;
+                const bool rec = (p.dbg & 4) && blockIdx.x == 0 && g < 128;
                 mbar_wait(&bar_afull[sa], (g >> 1) & 1);
+                if (rec) p.dbgbuf[1024 + g * 4 + 0] = clock64();
                 const uint8_t* src = smem + FT_OFF_A + sa * FT_A_STAGE;
                 tma_store_4d(&tm_g, 0, 0, q * (FT_KG / 2), rg0, src);
                 tma_store_4d(&tm_g, 0, 0, q * (FT_KG / 2), rg0 + 16, src + FT_A_BYTES);
                 bulk_commit();
+                if (rec) p.dbgbuf[1024 + g * 4 + 1] = clock64();
                 bulk_wait_read();
+                if (rec) p.dbgbuf[1024 + g * 4 + 2] = clock64();
                 mbar_arrive(&bar_stored[sa]);
                 if (++q == per_step) { q = 0; rg0 += 32; }
             }
@@ -428,8 +433,14 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
                 *reinterpret_cast<float4*>(stg + (rq + 4 * i) * 36 + 4 * f4) = q;
             }
         };
+        {   // TMEM stash <- h0: thread = (row, column half) keeps its 32 columns of h_{t-1} on chip for the GRU update
+            float hp[32];
+            global_to_stage(p.h0, FT_H, hf * 32);
+            stage_get(hp);
+            tmem_st32(taddr + lane_base + FT_STASH + hf * 32, hp);
+            producer_barrier();                       // the staging tiles alias the A stages the first chunk is built in
+        }
         for (int t = 0; t < p.T; ++t) {
-            const float* hprev = (t == 0) ? p.h0 : p.hseq + (size_t)(t - 1) * p.B * NH;
             float* hout = p.hseq + (size_t)t * p.B * NH;
             float* ruc = p.ruc + (size_t)t * p.B * NH * 3;
             // ---- X phase -------------------------------------------------------------------------------------
@@ -439,18 +450,24 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
             }
             // ---- gate: recurrent part ---------------------------------------------------------------------------
             for (int i = 0; i < nhc; ++i) produce(ZH, FT_ZLD, i * FT_CC, FT_CC, false);
+            const bool erec = (p.dbg & 4) && blockIdx.x == 0 && tid == 0 && t < 8;
+            long long* es = p.dbgbuf + 1536 + t * 16;
+            if (erec) es[0] = clock64();
             wait_all_mma();
-            // epilogue 1: warps 0-3 -> r (cols 0..63), warps 4-7 -> u (cols 64..127); thread = row.
+            if (erec) es[1] = clock64();
+            // epilogue 1: only the reset gate is on the critical path (the candidate needs r*h): thread = (row,
+            // column half) takes 32 columns of r.  The update gate's pre-activation stays in TMEM (columns 64..127
+            // are not touched by the candidate MMAs) and is turned into u by epilogue 2.
             // Global traffic goes through a warp-private staging tile so that every warp instruction moves
             // whole 128-byte lines (4 rows x 8 float4) instead of 32 scattered 16-byte pieces.
-            for (int cb = 0; cb < FT_H; cb += 32) {
+            {
                 float v[32];
-                tmem_ld32(taddr + lane_base + hf * FT_H + cb, v);
+                tmem_ld32(taddr + lane_base + hf * 32, v);
+                if (erec) es[2] = clock64();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fast_sigmoid(v[j] + sbias[hf * FT_H + cb + j]);
-                stage_put(v);
-                if (rvalid && hf == 0) {                                  // ZH <- r * h
-                    float4* z4 = reinterpret_cast<float4*>(ZH + row * FT_ZLD + cb);
+                for (int j = 0; j < 32; ++j) v[j] = fast_sigmoid(v[j] + sbias[hf * 32 + j]);
+                if (rvalid) {                                             // ZH <- r * h
+                    float4* z4 = reinterpret_cast<float4*>(ZH + row * FT_ZLD + hf * 32);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         float4 z = z4[j];
@@ -458,39 +475,53 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
                         z4[j] = z;
                     }
                 }
-                stage_to_global(ruc, 3 * FT_H, hf * FT_H + cb);
+                if (erec) es[3] = clock64();
+                stage_put(v);
+                stage_to_global(ruc, 3 * FT_H, hf * 32);
+                if (erec) es[4] = clock64();
             }
             tc_fence_before();
             producer_barrier();                                           // r*h of every row is visible
+            if (erec) es[5] = clock64();
             // ---- candidate: recurrent part ------------------------------------------------------------------------
             for (int i = 0; i < nhc; ++i) produce(ZH, FT_ZLD, i * FT_CC, FT_CC, false);
+            if (erec) es[6] = clock64();
             wait_all_mma();
-            {   // epilogue 2: 64 columns, each warp half takes 32 (same staged, line-sized global traffic)
+            if (erec) es[7] = clock64();
+            {   // epilogue 2: 64 columns, each warp half takes 32.  Everything it needs is on chip: the candidate
+                // and update-gate pre-activations in the accumulator, h_{t-1} in the TMEM stash (columns 192..255).
                 float v[32], u[32], hp[32];
-                global_to_stage(ruc, 3 * FT_H, FT_H + hf * 32);
-                stage_get(u);
-                global_to_stage(hprev, FT_H, hf * 32);
-                stage_get(hp);
                 tmem_ld32(taddr + lane_base + 128 + hf * 32, v);
+                tmem_ld32(taddr + lane_base + FT_H + hf * 32, u);
+                tmem_ld32(taddr + lane_base + FT_STASH + hf * 32, hp);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_epi);                     // TMEM is free for the next step's MMAs
+                if (lane == 0) mbar_arrive(&bar_epi);                     // the accumulator is free for the next step's MMAs
+                if (erec) es[8] = clock64();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float pre = v[j] + sbias[2 * FT_H + hf * 32 + j];
                     const float cv = (p.act == 0) ? fast_tanh(pre) : fmaxf(pre, 0.f);
+                    const float uv = fast_sigmoid(u[j] + sbias[FT_H + hf * 32 + j]);
                     v[j] = cv;
-                    u[j] = u[j] * hp[j] + (1.f - u[j]) * cv;               // h_new
+                    u[j] = uv;
+                    hp[j] = uv * hp[j] + (1.f - uv) * cv;                  // h_new
                 }
+                if (rvalid) {                                             // critical path first: the next step reads ZH
+                    float4* z4 = reinterpret_cast<float4*>(ZH + row * FT_ZLD + hf * 32);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) z4[j] = make_float4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3]);
+                }
+                if (erec) es[9] = clock64();
+                tmem_st32(taddr + lane_base + FT_STASH + hf * 32, hp);
+                if (erec) es[10] = clock64();
                 stage_put(v);
                 stage_to_global(ruc, 3 * FT_H, 2 * FT_H + hf * 32);
                 stage_put(u);
-                if (rvalid) {
-                    float4* z4 = reinterpret_cast<float4*>(ZH + row * FT_ZLD + hf * 32);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) z4[j] = make_float4(u[4 * j], u[4 * j + 1], u[4 * j + 2], u[4 * j + 3]);
-                }
+                stage_to_global(ruc, 3 * FT_H, FT_H + hf * 32);
+                stage_put(hp);
                 stage_to_global(hout, FT_H, hf * 32);
+                if (erec) es[11] = clock64();
             }
             producer_barrier();                                           // h_t of every row is visible
         }

@@ -1,8 +1,9 @@
 // Weight gradient as a pure TMA-fed tensor-core GEMM (tcgen05, 3xTF32) over the operand images that the
 // forward and backward sequence kernels leave in HBM:
 //     dW[kk][o] = sum over every (cta, t, row) of  G[row][kk] * dA[row][o]
-//   G  image (seq_fwd_tc.cu):  [slab = cta*T + t][hi|lo][128 rows][KKP floats]   (row-major, kk order of the step)
-//   dA image (seq_bwd_tc.cu):  [slab            ][hi|lo][128 rows][192 floats]   (row-major, columns r|u|c)
+//   G  image (seq_fwd_tc.cu):  [slab = cta*T + t][hi|lo][96 rows][KKP floats]   (row-major, kk order of the step)
+//   dA image (seq_bwd_tc.cu):  [slab            ][hi|lo][96 rows][192 floats]   (row-major, columns r|u|c)
+//   (96 rows = 4 samples x the 24 rows that can be non-zero: 12 K blocks of 8 rows per slab)
 // Both operands of this GEMM are "MN-major" (the GEMM's K index is the image row, the contiguous index is kk / o).
 // For fp32/tf32 the tensor core reads MN-major operands in exactly one layout -- 128-byte rows of 32 values whose
 // 32-byte chunks are XOR-swizzled with the row index (tc_common.cuh) -- and that is what a TMA load with
@@ -31,6 +32,7 @@ namespace dcgru {
 using namespace tc;
 
 constexpr int DWMM_NSTAGE = 4;
+constexpr int DWMM_KB_PER_SLAB = TC_IMG_ROWS / 8;   // K blocks (8 image rows) per (cta, t)
 constexpr int DWMM_FLUSH = 80;                       // K blocks between flushes (640 rows)
 constexpr int DWMM_THREADS = 320;                    // warp 0: loader, warp 1: MMA issuer, warps 2-9: flush
 constexpr int DWMM_TILE_BYTES = 4 * 1024;            // one of hi / lo of a 128-kk tile: 4 groups x (8 rows x 128 B)
@@ -87,19 +89,20 @@ __global__ void __launch_bounds__(DWMM_THREADS, 1) dw_mm_kernel(const DwmmParams
                 if (i >= DWMM_NSTAGE) mbar_wait(&bar_empty[st], ((i / DWMM_NSTAGE) - 1) & 1);
                 if (rec) dwmm_dbg[i * 8 + 1] = clock64();
                 const long kb = kb0 + i;
-                // image row of the K block: slab = kb / 16, row group = kb % 16; the lo part is 128 rows further
-                const int row_hi = (int)((kb >> 4) * 256 + (kb & 15) * 8);
+                // image row of the K block: slab = kb / 12, row group = kb % 12; the lo part is 96 rows further
+                const long slab = kb / DWMM_KB_PER_SLAB;
+                const int row_hi = (int)(slab * 2 * TC_IMG_ROWS + (kb - slab * DWMM_KB_PER_SLAB) * 8);
                 uint8_t* sbase = smem + st * DWMM_STAGE_BYTES;
                 mbar_expect_tx(&bar_full[st], tx);
 #pragma unroll
                 for (int j = 0; j < DWMM_MAXTILE; ++j)
                     if (j < ntile) {
                         tma_load_3d(sbase + (2 * j) * DWMM_TILE_BYTES, &tm_g, 0, row_hi, grp[j], &bar_full[st]);
-                        tma_load_3d(sbase + (2 * j + 1) * DWMM_TILE_BYTES, &tm_g, 0, row_hi + 128, grp[j], &bar_full[st]);
+                        tma_load_3d(sbase + (2 * j + 1) * DWMM_TILE_BYTES, &tm_g, 0, row_hi + TC_IMG_ROWS, grp[j], &bar_full[st]);
                     }
                 uint8_t* sb = sbase + DWMM_MAXTILE * 2 * DWMM_TILE_BYTES;
                 tma_load_3d(sb, &tm_d, 0, row_hi, 0, &bar_full[st]);
-                tma_load_3d(sb + DWMM_B_BYTES, &tm_d, 0, row_hi + 128, 0, &bar_full[st]);
+                tma_load_3d(sb + DWMM_B_BYTES, &tm_d, 0, row_hi + TC_IMG_ROWS, 0, &bar_full[st]);
                 if (rec) dwmm_dbg[i * 8 + 2] = clock64();
             }
         }
@@ -249,7 +252,7 @@ bool dwmm_plan(int fin, int H, int M, long nslab, int nsms, DwmmParams* out) {
     const int kgx = nxc * 6, kgt = kgx + 96;                            // x | gate h | candidate h
     DwmmParams& p = *out;
     p.KGT = kgt;
-    p.nkb = nslab * 16;
+    p.nkb = nslab * DWMM_KB_PER_SLAB;
     p.nset = 0;
     const int ntile = (kgt + 31) / 32;
     DwmmTile tiles[16];
@@ -312,7 +315,7 @@ cudaError_t launch_dw_mm(const DwmmParams& p_, int fin, int H, int M, float* dWg
     { const char* e = getenv("DCGRU_DBG"); p.dbg = e ? (atoi(e) & 8) : 0; }
     // swizzling 3-D views of the row-major images: (32 floats = one 128-byte row piece | image row | 32-float group)
     CUtensorMap tg, td;
-    const unsigned long long rows = (unsigned long long)(p.nkb / 16) * 256;
+    const unsigned long long rows = (unsigned long long)(p.nkb / DWMM_KB_PER_SLAB) * 2 * TC_IMG_ROWS;
     {
         const unsigned long long kkp = seq_fwd_tc_kkp(fin);
         const unsigned long long dims[3] = {32, rows, kkp / 32};

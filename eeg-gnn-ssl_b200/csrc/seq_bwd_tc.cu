@@ -1,6 +1,6 @@
 // Persistent encoder-layer backward (BPTT) on the tensor cores (tcgen05, 3xTF32) -- SURVEY A.4.
 //
-// One CTA = 6 samples (M = 128 rows = 6 x 20 padded nodes) for all T steps, time running backwards.
+// One CTA = 4 samples (M = 128 rows = 4 x 32, one warp per sample: see tc_common.cuh) for all T steps, time running backwards.
 // Per step two UMMA GEMMs whose A operand is the elementwise gate gradient (no diffusion on the input
 // side) and whose 192 output columns are the M = 3 diffusion terms of the 64 hidden columns; the
 // transposed diffusion sum_m P_m^T is applied on the output side by the producer warps:
@@ -17,7 +17,7 @@
 // apart from two 128-thread named barriers around the diffT staging planes.
 // A slots are laid out [row group of 8][K-group pair][8 rows x 32 B] (K-major, 32-byte swizzle, SBO = 512 B).  Optional operand
 // image (daimg): warp 10 copies every finished A slot (hi and lo) to HBM with one tensor-map TMA store each into
-// the row-major image DA[cta*T + t][hi|lo][128 rows][192 columns r|u|c] -- the B operand of the weight-gradient
+// the row-major image DA[cta*T + t][hi|lo][96 rows = sample*24 + node][192 columns r|u|c] -- the B operand of the weight-gradient
 // GEMM (dw_mm.cu).
 #include <cstring>
 
@@ -29,7 +29,8 @@
 namespace dcgru {
 using namespace tc;
 
-constexpr int BT_SB = 6;
+constexpr int BT_SB = TC_SB;
+constexpr int BT_RP = TC_RP;
 constexpr int BT_ROWS = 128;
 constexpr int BT_H = 64;
 constexpr int BT_M = 3;
@@ -180,8 +181,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
             int q = 0, step = 0, sb = 0, kb = 0;
             for (unsigned g = 0; g < total_chunks; ++g) {
                 const int sa = g & 3;
-                mbar_wait(&bar_bfull[sb], kb);
-                mbar_wait(&bar_afull[sa], (g >> 2) & 1);
+                // one combined poll (weights landed, A slot built): see seq_fwd_tc.cu
+                mbar_wait2(&bar_bfull[sb], kb, &bar_afull[sa], (g >> 2) & 1);
                 if (step > 0) {                                           // the previous step's reads of D are done
                     if (q == 0) mbar_wait(&bar_d1free, (step - 1) & 1);
                     if (q == 4 && p.mode == 0) mbar_wait(&bar_d2free, (step - 1) & 1);
@@ -224,22 +225,26 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
         __syncwarp();
     } else if (warp == 10) {
         // =================================== operand-image dump ==================================================
-        // one TMA tensor store per finished A slot part: box (8 o, 8 rows, 2 column octets, 16 row groups)
-        if (dump && lane == 0) {
-            tma_prefetch_desc(&tm_d);
+        // lane = (hi|lo, sample): one TMA tensor store per finished A slot part and sample: box (8 o, 8 rows, 2 column
+        // octets, 3 row groups) = the 24 rows of the sample that can be non-zero
+        if (dump) {
+            const int part = lane >> 2, s = lane & 3;
+            if (lane == 0) tma_prefetch_desc(&tm_d);
             int q = 0, t = p.T - 1;
             for (unsigned g = 0; g < total_chunks; ++g) {
                 const int sa = g & 3;
                 // column quad of the chunk in [r | u | c] order: B1 = c, then u, then r
                 const int og0 = (q < 4) ? 32 + 4 * q : (q < 8 ? 16 + 4 * (q - 4) : 4 * (q - 8));
-                const int rg0 = (blockIdx.x * p.T + t) * 32;
+                const int rg0 = (((blockIdx.x * p.T + t) * 2 + part) * BT_SB + s) * TC_RG;
                 mbar_wait(&bar_afull[sa], (g >> 2) & 1);
-                const uint8_t* src = smem + BT_OFF_A + sa * BT_A_SLOT;
-                tma_store_4d(&tm_d, 0, 0, og0 / 2, rg0, src);
-                tma_store_4d(&tm_d, 0, 0, og0 / 2, rg0 + 16, src + BT_A_BYTES);
-                bulk_commit();
+                if (lane < 2 * BT_SB) {
+                    const uint8_t* src = smem + BT_OFF_A + sa * BT_A_SLOT + part * BT_A_BYTES + s * (4 * BT_RG_F4 * 16);
+                    tma_store_4d(&tm_d, 0, 0, og0 / 2, rg0, src);
+                    bulk_commit();
+                }
                 bulk_wait_read();
-                bt_arrive(&bar_stored[sa]);
+                __syncwarp();
+                if (lane == 0) bt_arrive(&bar_stored[sa]);
                 if (++q == BT_CHUNKS) { q = 0; --t; }
             }
             bulk_wait_all();
@@ -248,9 +253,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
     } else {
         // =================================== producers ===========================================================
         const int row = tid & 127, hf = tid >> 7;
-        const int s_ = row / NP, n_ = row - s_ * NP;
+        const int s_ = row / BT_RP, n_ = row - s_ * BT_RP;
         const int b_ = b0 + s_;
-        const bool rvalid = (s_ < BT_SB) && (n_ < N) && (b_ < p.B);
+        const bool rvalid = (n_ < N) && (b_ < p.B);
         // column j = n_ of the polynomials (= row n_ of P^T), kept in registers for the whole sequence
         float PT1[NP], PT2[NP];
 #pragma unroll
@@ -269,8 +274,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int r = 32 * (warp & 3) + rq + 4 * i;
-            const int s = r / NP, n = r - s * NP, b = b0 + s;
-            grow[i] = (s < BT_SB && n < N && b < p.B) ? ((size_t)b * N + n) : ~(size_t)0;
+            const int s = r / BT_RP, n = r - s * BT_RP, b = b0 + s;
+            grow[i] = (n < N && b < p.B) ? ((size_t)b * N + n) : ~(size_t)0;
         }
         auto tile_load = [&](float* tile, const float* base, int ld, int col0) {          // async: cp.async
 #pragma unroll
@@ -302,10 +307,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
         unsigned g = 0;
         auto put_chunk = [&](const float (&v)[32], int owner_hf, int sub) {
             const int sa = g & 3;
-            if (g >= 4) {
-                mbar_wait(&bar_cdone[sa], ((g >> 2) - 1) & 1);            // the MMAs that read this slot are done
-                if (dump) mbar_wait(&bar_stored[sa], ((g >> 2) - 1) & 1); // ... and so is its copy to the operand image
-            }
+            if (g >= 4)                                                   // the MMAs that read this slot are done, and so is its
+                mbar_wait2(&bar_cdone[sa], ((g >> 2) - 1) & 1,            // copy to the operand image (one combined poll)
+                           dump ? &bar_stored[sa] : &bar_cdone[sa], ((g >> 2) - 1) & 1);
             if (hf == owner_hf) {
                 float4* a_hi = reinterpret_cast<float4*>(smem + BT_OFF_A + sa * BT_A_SLOT);
                 float4* a_lo = reinterpret_cast<float4*>(smem + BT_OFF_A + sa * BT_A_SLOT + BT_A_BYTES);
@@ -348,12 +352,12 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
                     }
                 }
                 prod_barrier();                                            // planes written by every row
-                if (row < BT_SB * NP) {
+                if (n_ < NP) {                                            // (all lanes of a warp read the same plane rows: broadcast)
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) {
                         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                        const float* z1 = S1 + (s_ * NP) * BT_PLD + 16 * hf + 4 * q4;
-                        const float* z2 = S2 + (s_ * NP) * BT_PLD + 16 * hf + 4 * q4;
+                        const float* z1 = S1 + (s_ * BT_RP) * BT_PLD + 16 * hf + 4 * q4;
+                        const float* z2 = S2 + (s_ * BT_RP) * BT_PLD + 16 * hf + 4 * q4;
 #pragma unroll
                         for (int nb = 0; nb < NP; nb += 5) {
                             float4 u1[5], u2[5];
@@ -539,7 +543,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
 
 size_t seq_bwd_tc_wimg_bytes() { return (size_t)BT_CHUNKS * BT_B_SLOT; }
 size_t seq_bwd_tc_daimg_bytes(int B, int T) {
-    return (size_t)((B + BT_SB - 1) / BT_SB) * T * 2 * 128 * 3 * BT_H * 4;
+    return (size_t)((B + BT_SB - 1) / BT_SB) * T * 2 * TC_IMG_ROWS * 3 * BT_H * 4;
 }
 bool seq_bwd_tc_supported(int N, int H, int M, int smem_limit) {
     return H == BT_H && M == BT_M && N <= NP && BT_SMEM + 2304 <= smem_limit;
@@ -563,9 +567,10 @@ cudaError_t launch_seq_bwd_tc(int B, int T, int N, int fin, int act, const float
     memset(&tm, 0, sizeof tm);
     if (daimg) {
         const unsigned long long rowb = 3 * BT_H * 4;
-        const unsigned long long dims[4] = {8, 8, 3 * BT_H / 8, (unsigned long long)((B + BT_SB - 1) / BT_SB) * T * 32};
+        const unsigned long long dims[4] = {8, 8, 3 * BT_H / 8,
+                                            (unsigned long long)((B + BT_SB - 1) / BT_SB) * T * 2 * BT_SB * TC_RG};
         const unsigned long long str[4] = {4, rowb, 32, 8 * rowb};
-        const unsigned box[4] = {8, 8, BT_KG / 2, 16};
+        const unsigned box[4] = {8, 8, BT_KG / 2, TC_RG};
         e = make_tmap_f32(&tm, daimg, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_32B);
         if (e != cudaSuccess) return e;
     }

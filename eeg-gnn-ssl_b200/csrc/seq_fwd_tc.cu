@@ -1,8 +1,8 @@
 // Persistent encoder-layer forward on the tensor cores (tcgen05, 3xTF32): all T steps of one layer for a
-// group of 6 samples per CTA, no relaunch (model/model.py:93-96 x model/cell.py:182-210).
+// group of 4 samples per CTA, no relaunch (model/model.py:93-96 x model/cell.py:182-210).
 //
-// Per step the three projections of the cell run as UMMA GEMMs with M = 128 rows (6 samples x 20 padded
-// nodes), accumulating in one 128 x 192 fp32 TMEM tile:
+// Per step the three projections of the cell run as UMMA GEMMs with M = 128 rows (4 samples x 32 rows, one
+// warp per sample: see tc_common.cuh), accumulating in one 128 x 192 fp32 TMEM tile:
 //     X : D[:, 0:192] (=)  diffuse(x_t)      @ [Wg_x | Wc_x]     (K = Fin*M)
 //     Hg: D[:, 0:128] (+)= diffuse(h_{t-1})  @  Wg_h             (K = H*M)      -> r, u = sigmoid(. + bg)
 //     Hc: D[:,128:192](+)= diffuse(r*h_{t-1})@  Wc_h             (K = H*M)      -> c = act(. + bc), GRU update
@@ -13,7 +13,7 @@
 // (K-major, 32-byte swizzle: one MMA k-step = one 256-byte atom per row group, SBO = 768 B between row groups).
 // Optional operand image (gsave): a dump warp copies every finished A stage (hi and lo) to HBM with one
 // tensor-map TMA store each (a 4-D box that scatters the 32-byte row pieces of the tile) into the row-major image
-// G[cta*T + t][hi|lo][128 rows][KKP floats]: the diffused operands [x | h | r*h] of every row in kk order.
+// G[cta*T + t][hi|lo][96 rows = sample*24 + node][KKP floats]: the diffused operands [x | h | r*h] in kk order.
 // The weight-gradient GEMM (dw_mm.cu) reads that image back with swizzling TMA loads as an MN-major UMMA
 // operand, so dW needs no recomputation of the diffusion at all.
 // B operand: the weights, pre-split and pre-tiled once per launch by pack_w_fwd_kernel, streamed chunk by
@@ -34,7 +34,8 @@
 namespace dcgru {
 using namespace tc;
 
-constexpr int FT_SB = 6;                 // samples per CTA
+constexpr int FT_SB = TC_SB;             // samples per CTA
+constexpr int FT_RP = TC_RP;             // rows per sample
 constexpr int FT_ROWS = 128;
 constexpr int FT_CC = 8;                 // source columns per chunk
 constexpr int FT_H = 64;
@@ -161,9 +162,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
     // hidden state <- h0, x ring <- 0 (rows of pad nodes / missing samples stay zero for ever)
     for (int idx = tid; idx < FT_ROWS * (FT_H / 4); idx += FT_THREADS) {
         const int r = idx / (FT_H / 4), c4 = (idx - r * (FT_H / 4)) * 4;
-        const int s = r / NP, n = r - s * NP, b = b0 + s;
+        const int s = r / FT_RP, n = r - s * FT_RP, b = b0 + s;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (s < FT_SB && n < N && b < p.B) v = *reinterpret_cast<const float4*>(p.h0 + ((size_t)b * N + n) * FT_H + c4);
+        if (n < N && b < p.B) v = *reinterpret_cast<const float4*>(p.h0 + ((size_t)b * N + n) * FT_H + c4);
         *reinterpret_cast<float4*>(ZH + r * FT_ZLD + c4) = v;
     }
     for (int idx = tid; idx < FT_XRING * FT_XSLOT / 16; idx += FT_THREADS)
@@ -215,9 +216,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
                 const int sa = g & 1;
                 const bool rec = (p.dbg & 4) && blockIdx.x == 0 && g < 128;
                 if (rec) p.dbgbuf[g * 8 + 0] = clock64();
-                mbar_wait(&bar_bfull[sb], kb);
                 if (rec) p.dbgbuf[g * 8 + 1] = clock64();
-                mbar_wait(&bar_afull[sa], (g >> 1) & 1);
+                // one combined poll (weights landed, A tile built): this thread issues MMAs almost synchronously (the
+                // tensor core queues only ~2 of them), so every cycle it spends elsewhere is a cycle the pipe drains
+                mbar_wait2(&bar_bfull[sb], kb, &bar_afull[sa], (g >> 1) & 1);
                 if (rec) p.dbgbuf[g * 8 + 2] = clock64();
                 if (q == 0 && t > 0) mbar_wait(&bar_epi, (t - 1) & 1);   // the previous step's TMEM reads are done
                 tc_fence_after();
@@ -269,26 +271,31 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
         __syncwarp();
     } else if (warp == 10) {
         // =================================== operand-image dump ==================================================
-        // one TMA tensor store per finished A stage part: box (8 kk, 8 rows, 3 K-group pairs, 16 row groups) = the
-        // stage part in shared-memory order, scattered into the row-major image.  The stage is released to the
-        // producers (bar_stored) once the stores have read their shared-memory source.
-        if (dump && lane == 0) {
-            tma_prefetch_desc(&tm_g);
-            int q = 0, rg0 = blockIdx.x * p.T * 32;                          // row-group coordinate of (cta, t = 0), hi part
+        // lane = (hi|lo, sample): one TMA tensor store per finished A stage part and sample: box (8 kk, 8 rows,
+        // 3 K-group pairs, 3 row groups) = the 24 rows of the sample that can be non-zero, in shared-memory order,
+        // scattered into the row-major image.  The stage is released to the producers (bar_stored) once the
+        // stores have read their shared-memory source.
+        if (dump) {
+            const int part = lane >> 2, s = lane & 3;
+            if (lane == 0) tma_prefetch_desc(&tm_g);
+            int q = 0;
+            int rg0 = ((blockIdx.x * p.T * 2 + part) * FT_SB + s) * TC_RG;  // image row group of (cta, t = 0, part, sample)
             for (unsigned g = 0; g < total_chunks; ++g) {
                 const int sa = g & 1;
-                const bool rec = (p.dbg & 4) && blockIdx.x == 0 && g < 128;
+                const bool rec = (p.dbg & 4) && blockIdx.x == 0 && lane == 0 && g < 128;
                 mbar_wait(&bar_afull[sa], (g >> 1) & 1);
                 if (rec) p.dbgbuf[1024 + g * 4 + 0] = clock64();
-                const uint8_t* src = smem + FT_OFF_A + sa * FT_A_STAGE;
-                tma_store_4d(&tm_g, 0, 0, q * (FT_KG / 2), rg0, src);
-                tma_store_4d(&tm_g, 0, 0, q * (FT_KG / 2), rg0 + 16, src + FT_A_BYTES);
-                bulk_commit();
+                if (lane < 2 * FT_SB) {
+                    const uint8_t* src = smem + FT_OFF_A + sa * FT_A_STAGE + part * FT_A_BYTES + s * (4 * FT_RG_F4 * 16);
+                    tma_store_4d(&tm_g, 0, 0, q * (FT_KG / 2), rg0, src);
+                    bulk_commit();
+                }
                 if (rec) p.dbgbuf[1024 + g * 4 + 1] = clock64();
                 bulk_wait_read();
+                __syncwarp();
                 if (rec) p.dbgbuf[1024 + g * 4 + 2] = clock64();
-                mbar_arrive(&bar_stored[sa]);
-                if (++q == per_step) { q = 0; rg0 += 32; }
+                if (lane == 0) mbar_arrive(&bar_stored[sa]);
+                if (++q == per_step) { q = 0; rg0 += 2 * FT_SB * TC_RG; }
             }
             bulk_wait_all();
         }
@@ -296,9 +303,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
     } else {
         // =================================== producers / epilogue ================================================
         const int row = tid & 127, half = tid >> 7;
-        const int s_ = row / NP, n_ = row - s_ * NP;
+        const int s_ = row / FT_RP, n_ = row - s_ * FT_RP;
         const int b_ = b0 + s_;
-        const bool rvalid = (s_ < FT_SB) && (n_ < N) && (b_ < p.B);
+        const bool rvalid = (n_ < N) && (b_ < p.B);
         // this row of the diffusion polynomials, kept in registers for the whole sequence
         float P1[NP], P2[NP];
 #pragma unroll
@@ -316,9 +323,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
             if (q_ >= total_x) return;
             const int t = q_ / nxc, i = q_ - t * nxc;
             const int r = tid >> 1, q4 = (tid & 1) * 4;
-            const int s = r / NP, n = r - s * NP, b = b0 + s;
+            const int s = r / FT_RP, n = r - s * FT_RP, b = b0 + s;
             const int c = i * FT_CC + q4;
-            if (s < FT_SB && n < N && b < p.B && c < fin) {
+            if (n < N && b < p.B && c < fin) {
                 float* dst = reinterpret_cast<float*>(smem + FT_OFF_X + (q_ % FT_XRING) * FT_XSLOT) + r * FT_XLD + q4;
                 cp_async16(dst, p.x + (size_t)t * p.xs_t + (size_t)b * p.xs_b + n * fin + c);
             }
@@ -331,24 +338,27 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
             const int sa = g & 1;
             const bool rec = (p.dbg & 4) && blockIdx.x == 0 && tid == 0 && g < 128;
             if (rec) p.dbgbuf[g * 8 + 4] = clock64();
-            if (g >= 2) {
-                mbar_wait(&bar_done[sa], ((g >> 1) - 1) & 1);            // the MMAs that read this stage are done
-                if (dump) mbar_wait(&bar_stored[sa], ((g >> 1) - 1) & 1); // ... and so is its copy to the operand image
-            }
-            if (rec) p.dbgbuf[g * 8 + 5] = clock64();
+            // stage free = the MMAs that read it are done and so is its copy to the operand image; for an x chunk
+            // also wait for the streamed columns (requested two chunks ago).  One combined poll: see mbar_wait2.
+            const uint32_t fpar = ((g >> 1) - 1) & 1;
+            uint64_t* bst = dump ? &bar_stored[sa] : &bar_done[sa];
             if (is_x) {
+                if (g >= 2) mbar_wait3(&bar_done[sa], fpar, bst, fpar, &bar_xfull[xq % FT_XRING], (xq / FT_XRING) & 1);
+                else mbar_wait(&bar_xfull[xq % FT_XRING], (xq / FT_XRING) & 1);
                 // every producer is past chunk g-2, so the slot x chunk xq-2 lived in can be refilled
                 issue_x(xq + 2);
-                mbar_wait(&bar_xfull[xq % FT_XRING], (xq / FT_XRING) & 1);
+            } else if (g >= 2) {
+                mbar_wait2(&bar_done[sa], fpar, bst, fpar);
             }
+            if (rec) p.dbgbuf[g * 8 + 5] = clock64();
             float4* a_hi = reinterpret_cast<float4*>(smem + FT_OFF_A + sa * FT_A_STAGE);
             float4* a_lo = reinterpret_cast<float4*>(smem + FT_OFF_A + sa * FT_A_STAGE + FT_A_BYTES);
             const int c = c0 + 4 * half;
             float v0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
-            if (4 * half < cvalid && row < FT_SB * NP) {
+            if (4 * half < cvalid && n_ < NP) {                           // (all lanes of a warp read the same z rows: broadcast)
                 const float4 own = *reinterpret_cast<const float4*>(zsrc + row * zld + c);
                 v0[0] = own.x; v0[1] = own.y; v0[2] = own.z; v0[3] = own.w;
-                const float* zq = zsrc + (s_ * NP) * zld + c;
+                const float* zq = zsrc + (s_ * FT_RP) * zld + c;
 #pragma unroll
                 for (int jb = 0; jb < NP; jb += 10) {                     // rows j >= N are zero, so are P1/P2 there
                     float4 z[10];
@@ -400,8 +410,8 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int r = 32 * (warp & 3) + rq + 4 * i;
-            const int s = r / NP, n = r - s * NP, b = b0 + s;
-            grow[i] = (s < FT_SB && n < N && b < p.B) ? ((size_t)b * N + n) : ~(size_t)0;
+            const int s = r / FT_RP, n = r - s * FT_RP, b = b0 + s;
+            grow[i] = (n < N && b < p.B) ? ((size_t)b * N + n) : ~(size_t)0;
         }
         auto stage_put = [&](const float (&v)[32]) {
             __syncwarp();
@@ -538,7 +548,7 @@ int seq_tc_nslab(int B, int T) { return ((B + FT_SB - 1) / FT_SB) * T; }
 // floats per image row: the kk of a step rounded up to whole 32-float groups (128-byte TMA rows)
 int seq_fwd_tc_kkp(int fin) { return (seq_fwd_tc_kgt(fin) * 4 + 31) / 32 * 32; }
 size_t seq_fwd_tc_gsave_bytes(int B, int T, int fin) {
-    return (size_t)seq_tc_nslab(B, T) * 2 * 128 * seq_fwd_tc_kkp(fin) * 4;
+    return (size_t)seq_tc_nslab(B, T) * 2 * TC_IMG_ROWS * seq_fwd_tc_kkp(fin) * 4;
 }
 bool seq_fwd_tc_supported(int N, int fin, int H, int M, int smem_limit) {
     return H == FT_H && M == FT_M && N <= NP && fin % 4 == 0 && FT_SMEM + 2304 <= smem_limit;
@@ -565,9 +575,9 @@ cudaError_t launch_seq_fwd_tc(int B, int T, int N, int fin, int act, const float
     if (gsave) {
         // 4-D view of the row-major image: (8 kk | row in group, stride = one row | K-group pair, 32 B | row group)
         const unsigned long long kkp = seq_fwd_tc_kkp(fin), rowb = kkp * 4;
-        const unsigned long long dims[4] = {8, 8, kkp / 8, (unsigned long long)seq_tc_nslab(B, T) * 32};
+        const unsigned long long dims[4] = {8, 8, kkp / 8, (unsigned long long)seq_tc_nslab(B, T) * 2 * FT_SB * TC_RG};
         const unsigned long long str[4] = {4, rowb, 32, 8 * rowb};
-        const unsigned box[4] = {8, 8, FT_KG / 2, 16};
+        const unsigned box[4] = {8, 8, FT_KG / 2, TC_RG};
         e = make_tmap_f32(&tm, gsave, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_32B);
         if (e != cudaSuccess) return e;
     }

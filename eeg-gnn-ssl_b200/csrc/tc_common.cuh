@@ -18,6 +18,17 @@
 namespace dcgru {
 namespace tc {
 
+// Row layout of the tensor-core sequence kernels: a CTA owns TC_SB = 4 samples, sample s sits in rows
+// [32 s, 32 s + 32) of the 128-row UMMA tile (nodes 0..N-1, the rest zero).  One warp = one sample, so every
+// shared-memory read of the diffusion (all lanes read the same node row of the same sample) is a single
+// broadcast wavefront -- with the denser 20-row packing (6 samples) a warp straddled samples and each such
+// read cost 4 wavefronts, which made the kernels shared-memory bound.  B = 512 needs 128 CTAs: still one wave.
+// Only the first TC_RG = 3 row groups (24 rows) of a sample are ever non-zero; the operand images keep just those.
+constexpr int TC_SB = 4;
+constexpr int TC_RP = 32;
+constexpr int TC_RG = 3;
+constexpr int TC_IMG_ROWS = TC_SB * TC_RG * 8;      // 96 image rows per (cta, t, hi|lo)
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
@@ -197,6 +208,41 @@ __device__ __forceinline__ int k32_idx(int kg, int row) {
 // TMA load with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B writes.
 __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return make_smem_desc(saddr, lbo_bytes, sbo_bytes) | ((uint64_t)1 << 61);
+}
+
+// wait for two (three) barriers at once: the polls are issued back to back so their latencies (~200 cycles each,
+// even when the phase completed long ago) overlap instead of adding up on the waiting thread's critical path
+__device__ __forceinline__ void mbar_wait2(uint64_t* b0, uint32_t p0, uint64_t* b1, uint32_t p1) {
+    const uint32_t a0 = smem_u32(b0), a1 = smem_u32(b1);
+    uint32_t d0 = 0, d1 = 0;
+    for (uint32_t it = 0; it < (1u << 26); ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%2], %3;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 q, [%4], %5;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "selp.u32 %1, 1, 0, q;\n\t}\n"
+            : "=r"(d0), "=r"(d1) : "r"(a0), "r"(p0), "r"(a1), "r"(p1) : "memory");
+        if (d0 & d1) return;
+    }
+    asm volatile("trap;\n");
+}
+__device__ __forceinline__ void mbar_wait3(uint64_t* b0, uint32_t p0, uint64_t* b1, uint32_t p1, uint64_t* b2, uint32_t p2) {
+    const uint32_t a0 = smem_u32(b0), a1 = smem_u32(b1), a2 = smem_u32(b2);
+    uint32_t d0 = 0, d1 = 0, d2 = 0;
+    for (uint32_t it = 0; it < (1u << 26); ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p, q, r;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%3], %4;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 q, [%5], %6;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 r, [%7], %8;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "selp.u32 %1, 1, 0, q;\n\t"
+            "selp.u32 %2, 1, 0, r;\n\t}\n"
+            : "=r"(d0), "=r"(d1), "=r"(d2) : "r"(a0), "r"(p0), "r"(a1), "r"(p1), "r"(a2), "r"(p2) : "memory");
+        if (d0 & d1 & d2) return;
+    }
+    asm volatile("trap;\n");
 }
 
 // ---- 3xTF32 split ---------------------------------------------------------------------------------------

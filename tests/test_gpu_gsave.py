@@ -12,6 +12,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 N, H, K = 19, 64, 2
+SB, IMG_ROWS = 4, 96            # samples per CTA; image rows per (cta, t, hi|lo) = 4 samples x 24 rows (tc_common.cuh)
 
 
 @pytest.fixture(scope="module")
@@ -74,15 +75,15 @@ def _run_layer(dev, B, T, fin, seed, use_gsave, want_dx=False):
 
 
 def _unimage(buf, nslab, width, used):
-    """row-major image [slab][hi|lo][128 rows][width floats] (bytes) -> float64 hi + lo, first `used` columns"""
-    t = buf.view(torch.float32).view(nslab, 2, 128, width).double()
+    """row-major image [slab][hi|lo][96 rows][width floats] (bytes) -> float64 hi + lo, first `used` columns"""
+    t = buf.view(torch.float32).view(nslab, 2, IMG_ROWS, width).double()
     return (t[:, 0] + t[:, 1])[..., :used].contiguous()
 
 
 def _expected_g(r, B, T, fin):
-    """diffused operands [x | h_prev | r*h_prev] in kk = c*3 + m order, rows = sample*20 + node, per (cta, t)"""
+    """diffused operands [x | h_prev | r*h_prev] in kk = c*3 + m order, rows = sample*24 + node, per (cta, t)"""
     nxc = (fin + 7) // 8
-    ncta = (B + 5) // 6
+    ncta = (B + SB - 1) // SB
     P = r["P"].double()                                                   # (B, 2, N, N)
     x = r["x"].double().view(T, B, N, fin)
     hs = torch.cat([r["h0"].double().view(1, B, N, H), r["h_seq"].double().view(T, B, N, H)[:-1]], 0)
@@ -98,18 +99,18 @@ def _expected_g(r, B, T, fin):
 
     full = torch.cat([terms(x, nxc * 8), terms(hs, H), terms(rg * hs, H)], -1)      # (T,B,N,KK)
     kk = full.shape[-1]
-    img = torch.zeros(ncta, T, 128, kk, dtype=torch.float64, device=full.device)
+    img = torch.zeros(ncta, T, IMG_ROWS, kk, dtype=torch.float64, device=full.device)
     for b in range(B):
-        c, s = divmod(b, 6)
-        img[c, :, s * 20: s * 20 + N] = full[:, b]
-    return img.reshape(ncta * T, 128, kk)
+        c, s = divmod(b, SB)
+        img[c, :, s * 24: s * 24 + N] = full[:, b]
+    return img.reshape(ncta * T, IMG_ROWS, kk)
 
 
 @pytest.mark.parametrize("B,T,fin", [(7, 3, 100), (13, 2, 64), (6, 1, 100)])
 def test_operand_images_and_gemm(dev, B, T, fin):
     r = _run_layer(dev, B, T, fin, seed=B + fin, use_gsave=True)
     assert r["gbytes"] > 0, "operand-image path not selected on this device"
-    ncta = (B + 5) // 6
+    ncta = (B + SB - 1) // SB
     nslab = ncta * T
     kgt = ((fin + 7) // 8 + 16) * 6
     # (1) G image
@@ -123,16 +124,16 @@ def test_operand_images_and_gemm(dev, B, T, fin):
     o_da, o_img, _ = r["off"]
     assert o_img > 0
     da = r["bws"][o_da: o_da + T * B * N * 3 * H * 4].view(torch.float32).view(T, B, N, 3 * H).double()
-    dimg = _unimage(r["bws"][o_img: o_img + nslab * 2 * 128 * 3 * H * 4], nslab, 3 * H, 3 * H).view(ncta, T, 128, 3 * H)
+    dimg = _unimage(r["bws"][o_img: o_img + nslab * 2 * IMG_ROWS * 3 * H * 4], nslab, 3 * H, 3 * H).view(ncta, T, IMG_ROWS, 3 * H)
     dexp = torch.zeros_like(dimg)
     for b in range(B):
-        c, s = divmod(b, 6)
-        dexp[c, :, s * 20: s * 20 + N] = da[:, b]
+        c, s = divmod(b, SB)
+        dexp[c, :, s * 24: s * 24 + N] = da[:, b]
     ed = float((dimg - dexp).abs().max() / dexp.abs().max())
     print(f"dA image vs row-major dA: {ed:.2e}")
     assert ed < 1e-6, ed
     # (3) GEMM over the images
-    full = torch.einsum("srk,sro->ko", gimg, dimg.view(nslab, 128, 3 * H))           # (KK, 192)
+    full = torch.einsum("srk,sro->ko", gimg, dimg.view(nslab, IMG_ROWS, 3 * H))      # (KK, 192)
     nx = ((fin + 7) // 8) * 8 * 3
     ref_g = torch.cat([full[: fin * 3, : 2 * H], full[nx: nx + 3 * H, : 2 * H]], 0)
     ref_c = torch.cat([full[: fin * 3, 2 * H:], full[nx + 3 * H: nx + 6 * H, 2 * H:]], 0)

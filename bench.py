@@ -327,25 +327,81 @@ def main():
         else:
             resident_step()
 
-    def e2e_fast():
-        if graph is None:
-            return e2e_step()
-        d_x.copy_(host["x"], non_blocking=True)
-        d_y.copy_(host["y"], non_blocking=True)
-        d_sl.copy_(host["sl"], non_blocking=True)
-        if not corr:
-            d_sup[0].copy_(host["sup"], non_blocking=True)
-        graph.replay()
-        return static_loss.item()
+    # ---- e2e: double-buffered input pipeline ------------------------------------------------------------------
+    # Every step's batch is copied from pinned host memory (K copies for K steps, all inside the timed region) and
+    # every step's loss is read back; the copy of batch k+1 runs on a copy stream while step k computes, which is
+    # what a training loop with a prefetching loader does (the reference's DataLoader + .to(device), train.py:246).
+    e2e_note = "serial copy then step"
+    bufs, graphs2, losses2 = None, None, None
+    if graph is not None:
+        try:
+            copy_stream = torch.cuda.Stream()
+            bufs = [dict(x=d_x, y=d_y, sl=d_sl, sup=d_sup),
+                    dict(x=torch.empty_like(d_x), y=torch.empty_like(d_y), sl=torch.empty_like(d_sl),
+                         sup=[torch.empty_like(d_sup[0])] if not corr else None)]
+            bufs[1]["x"].copy_(d_x); bufs[1]["y"].copy_(d_y); bufs[1]["sl"].copy_(d_sl)
+            if not corr:
+                bufs[1]["sup"][0].copy_(d_sup[0])
+            torch.cuda.synchronize()
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                l1 = step(bufs[1]["x"], bufs[1]["y"], bufs[1]["sl"],
+                          bufs[1]["sup"] if not corr else supports_for(bufs[1]["x"]))
+            graphs2, losses2 = [graph, g1], [static_loss, l1]
+            copied = [torch.cuda.Event(), torch.cuda.Event()]
+            consumed = [torch.cuda.Event(), torch.cuda.Event()]
+            e2e_note = "double-buffered: H2D copy of batch k+1 on a copy stream overlaps step k"
+        except Exception as exc:
+            bufs = None
+            e2e_note = f"serial copy then step (double buffering failed: {type(exc).__name__})"
+            torch.cuda.synchronize()
+
+    def enqueue_copy(i):
+        b = bufs[i]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i])           # the step that last read this buffer has finished
+            b["x"].copy_(host["x"], non_blocking=True)
+            b["y"].copy_(host["y"], non_blocking=True)
+            b["sl"].copy_(host["sl"], non_blocking=True)
+            if not corr:
+                b["sup"][0].copy_(host["sup"], non_blocking=True)
+            copied[i].record(copy_stream)
+
+    def e2e_run(steps):
+        """K steps: returns nothing; every step = (its own H2D copy) + graph + loss.item()"""
+        if bufs is None:
+            for _ in range(steps):
+                if graph is None:
+                    e2e_step()
+                else:
+                    d_x.copy_(host["x"], non_blocking=True)
+                    d_y.copy_(host["y"], non_blocking=True)
+                    d_sl.copy_(host["sl"], non_blocking=True)
+                    if not corr:
+                        d_sup[0].copy_(host["sup"], non_blocking=True)
+                    graph.replay()
+                    static_loss.item()
+            return
+        main = torch.cuda.current_stream()
+        for i in range(2):
+            consumed[i].record(main)
+        enqueue_copy(0)
+        for k in range(steps):
+            i = k & 1
+            main.wait_event(copied[i])
+            graphs2[i].replay()
+            consumed[i].record(main)
+            if k + 1 < steps:
+                enqueue_copy(i ^ 1)
+            losses2[i].item()                           # D2H read of this step's loss, as train.py:269 does every step
 
     L = _lib.lib()
     with ClockSampler(local) as clk:
         for _ in range(2):
             resident_fast()
         total_ms = timed(resident_fast, args.steps)
-        for _ in range(2):
-            e2e_fast()
-        e2e_ms = timed(e2e_fast, args.steps)
+        e2e_run(2)
+        e2e_ms = timed(lambda: e2e_run(args.steps), 1)
         # per-kernel device times: a few eager steps with the library's event hooks on (same kernels as the graph)
         L.dcgru_timing_enable(1)
         ksteps = min(args.steps, 3)
@@ -419,7 +475,7 @@ def main():
                        "parallelism": f"dp{world}", "l2": "inputs larger than L2 (x = 233 MB/rank, saved "
                        "activations ~1.2 GB/rank are rewritten every step)",
                        "step": "zero_grad+fwd+loss+bwd+allreduce+clip+adam", "grad_allreduce_bytes": sync.nbytes,
-                       "launch": graph_note},
+                       "launch": graph_note, "e2e_pipeline": e2e_note},
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches, "roofline": roofline, "clocks": clk.summary()}

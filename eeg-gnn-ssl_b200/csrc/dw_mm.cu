@@ -223,19 +223,39 @@ __global__ void dwmm_reduce_kernel(const DwmmParams p, int fin, int H, int M, fl
 
 // ---- db: column sums of the row-major dA (rows x 3H), two fixed-order stages ------------------------------------
 constexpr int CS_CTAS = 592;
-__global__ void colsum_kernel(const float* dA, long rows, int H3, float* partial) {
-    const int c = threadIdx.x;
+// thread = (column quad, row slot): float4 loads, 4 rows in flight per thread, 4 row slots per CTA; fixed summation order
+__global__ void __launch_bounds__(192) colsum_kernel(const float* dA, long rows, int H3, float* partial) {
+    __shared__ float4 red[4][48];
+    const int nq = H3 / 4;                                             // 48 column quads (H = 64)
+    const int cq = threadIdx.x % nq, slot = threadIdx.x / nq;
     const long r0 = rows * blockIdx.x / gridDim.x, r1 = rows * (blockIdx.x + 1) / gridDim.x;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    long r = r0;
-    for (; r + 3 < r1; r += 4) {
-        a0 += dA[(size_t)r * H3 + c];
-        a1 += dA[(size_t)(r + 1) * H3 + c];
-        a2 += dA[(size_t)(r + 2) * H3 + c];
-        a3 += dA[(size_t)(r + 3) * H3 + c];
+    const float4* src = reinterpret_cast<const float4*>(dA) + cq;
+    float4 a[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    long r = r0 + slot;
+    for (; r + 12 < r1; r += 16) {
+        float4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = __ldcs(src + (size_t)(r + 4 * i) * nq);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { a[i].x += v[i].x; a[i].y += v[i].y; a[i].z += v[i].z; a[i].w += v[i].w; }
     }
-    for (; r < r1; ++r) a0 += dA[(size_t)r * H3 + c];
-    partial[(size_t)blockIdx.x * H3 + c] = (a0 + a1) + (a2 + a3);
+    for (; r < r1; r += 4) {
+        const float4 v = __ldcs(src + (size_t)r * nq);
+        a[0].x += v.x; a[0].y += v.y; a[0].z += v.z; a[0].w += v.w;
+    }
+    float4 s;
+    s.x = (a[0].x + a[1].x) + (a[2].x + a[3].x); s.y = (a[0].y + a[1].y) + (a[2].y + a[3].y);
+    s.z = (a[0].z + a[1].z) + (a[2].z + a[3].z); s.w = (a[0].w + a[1].w) + (a[2].w + a[3].w);
+    red[slot][cq] = s;
+    __syncthreads();
+    if (slot == 0) {
+        const float4 b = red[1][cq], c = red[2][cq], d = red[3][cq];
+        s.x = (s.x + b.x) + (c.x + d.x); s.y = (s.y + b.y) + (c.y + d.y);
+        s.z = (s.z + b.z) + (c.z + d.z); s.w = (s.w + b.w) + (c.w + d.w);
+        reinterpret_cast<float4*>(partial + (size_t)blockIdx.x * H3)[cq] = s;
+    }
 }
 __global__ void colsum_final_kernel(const float* partial, int n, int H, float* dbg, float* dbc) {
     const int c = threadIdx.x;
@@ -342,7 +362,8 @@ cudaError_t launch_dw_mm(const DwmmParams& p_, int fin, int H, int M, float* dWg
 }
 
 cudaError_t launch_colsum(const float* dA, long rows, int H, float* partial, float* dbg, float* dbc, cudaStream_t st) {
-    colsum_kernel<<<CS_CTAS, 3 * H, 0, st>>>(dA, rows, 3 * H, partial);
+    if (H != 64) return cudaErrorInvalidValue;                         // 48 column quads x 4 row slots = 192 threads
+    colsum_kernel<<<CS_CTAS, 192, 0, st>>>(dA, rows, 3 * H, partial);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     colsum_final_kernel<<<1, 3 * H, 0, st>>>(partial, CS_CTAS, H, dbg, dbc);

@@ -1,6 +1,6 @@
 """Timeline of dw_mm_kernel's loader / MMA-issuer threads (CTA 0) at BASELINE config 2 size: DCGRU_DBG=8."""
 import ctypes as C, os, sys, numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ["DCGRU_DBG"] = "8"
 from eeg_gnn_ssl_b200 import _lib
 from eeg_gnn_ssl_b200.model.model import DCRNNEncoder

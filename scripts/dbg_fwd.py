@@ -1,7 +1,7 @@
 """Timeline of seq_fwd_tc_kernel (CTA 0): clock64 stamps of the MMA issuer, a producer thread and the dump warp (DCGRU_DBG=4).
 usage: python scripts_dbg_fwd.py [gsave: 0|1]"""
 import ctypes as C, os, sys, numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ["DCGRU_DBG"] = "4"
 from eeg_gnn_ssl_b200 import _lib, ops
 from eeg_gnn_ssl_b200.model.cell import DCGRUCell

@@ -1,6 +1,6 @@
 """Reverse-engineer UMMA operand addressing: which smem word is read for logical (row, k)?"""
 import ctypes as C, os, sys, numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from eeg_gnn_ssl_b200 import _lib
 L = _lib.lib(); dev = torch.device("cuda:0")
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)

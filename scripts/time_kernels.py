@@ -2,7 +2,7 @@
 nvidia-smi sampling): prints per-kernel ms from the library's event hooks."""
 import ctypes, sys, os, time
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from eeg_gnn_ssl_b200 import _lib
 from eeg_gnn_ssl_b200.model.model import DCRNNEncoder
 from oracle.graph_oracle import scaled_laplacian

@@ -307,9 +307,10 @@ def main():
         resident_step()
     # ---- whole training step captured in a CUDA graph (removes ~200 launch gaps per step; same work) ----------
     graph, static_loss, graph_note = None, None, "eager"
-    if world == 1 and os.environ.get("DCGRU_BENCH_GRAPH", "1") == "1":
+    # (N > 1: the flat-gradient NCCL all-reduce is captured inside the graph too; DCGRU_BENCH_GRAPH=0 -> eager)
+    if os.environ.get("DCGRU_BENCH_GRAPH", "1") == "1":
         try:
-            torch.cuda.synchronize()
+            barrier()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 static_loss = step(d_x, d_y, d_sl, supports_for(d_x))
@@ -488,7 +489,13 @@ def main():
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # CUDA graphs that captured NCCL work have to die before the communicator does, and tearing either down can
+        # block; the numbers are out, so leave without running destructors (every rank, after a last rendezvous)
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

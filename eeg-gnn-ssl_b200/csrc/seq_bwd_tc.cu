@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
                                                                    const __grid_constant__ CUtensorMap tm_d) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    __shared__ uint64_t bar_bfull[3], bar_afull[4], bar_cdone[4], bar_stored[4], bar_d1free, bar_d2free;
+    __shared__ uint64_t bar_bfull[3], bar_afull[4], bar_cdone[4], bar_stored[4], bar_d1free, bar_d2free, bar_b1done;
     __shared__ uint32_t tmem_slot;
     __shared__ uint64_t dA_desc[4][2][2];                    // [slot][k-step][hi, lo]
     __shared__ uint64_t dB_desc[3][2][2];
@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
         for (int i = 0; i < 4; ++i) { mbar_init(&bar_afull[i], BT_NPROD / 32); mbar_init(&bar_cdone[i], 1); mbar_init(&bar_stored[i], 1); }
         mbar_init(&bar_d1free, BT_NPROD / 32);
         mbar_init(&bar_d2free, BT_NPROD / 32);
+        mbar_init(&bar_b1done, 1);
         mbar_fence_init();
         for (int sl = 0; sl < 4; ++sl)
             for (int k = 0; k < 2; ++k) {
@@ -200,6 +201,10 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
                     acc = 1u;
                 }
                 umma_commit(&bar_cdone[sa]);
+                // B1 complete: its own barrier, one phase per step.  (bar_cdone of B1's last slot cannot be used for
+                // this: the producers refill that slot with a B2 chunk before they wait, and if that chunk's MMAs also
+                // finish before a late warp polls, the slot barrier has advanced two phases and the poll never succeeds.)
+                if (q == 3 && p.mode == 0) umma_commit(&bar_b1done);
                 if (++q == BT_CHUNKS) { q = 0; ++step; }
                 if (++sb == 3) { sb = 0; kb ^= 1; }
             }
@@ -479,7 +484,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1) seq_bwd_tc_kernel(const BwdTcPa
             // ---- B2, u half: reuses the A slots of B1 as soon as B1's MMAs have consumed them -----------------------
             put_chunk(dAu, 0, 0); put_chunk(dAu, 0, 1); put_chunk(dAu, 1, 0); put_chunk(dAu, 1, 1);
             // ---- d(rH) = diffT(D1) -----------------------------------------------------------------------------------
-            wait_chunk(g0 + 3);
+            mbar_wait(&bar_b1done, (p.T - 1 - t) & 1);                  // all B1 MMAs of this step are complete
+            tc_fence_after();
 #pragma unroll
             for (int j = 0; j < 32; ++j) w0[j] = 0.f;
             diff_t(BT_D1, w0);                                            // w0 = d(rH), own 32 columns

@@ -197,7 +197,7 @@ def run_reference_arm(args, cfg, rank):
     sample_b = min(cfg["B"], 64)
     steps, warm = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
     cps, sec = cpu_reference_leg(cfg, sample_b, steps, warm)
-    line = {"impl": "reference", "metric": "EEG clips/sec (fwd+bwd)", "value": cps, "unit": "clips/s",
+    line = {"impl": "reference", "metric": "EEG clips/sec (fwd+bwd, T=60, N=19)", "value": cps, "unit": "clips/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": {"workload": cfg["name"], "sample_batch": sample_b},

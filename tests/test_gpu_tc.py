@@ -150,3 +150,40 @@ def test_tc_path_full_size_accuracy(dev, monkeypatch):
         e = float((a_ - b_).abs().max() / b_.abs().max())
         print(f"{n}: {e:.2e}")
         assert e < 1e-4, (n, e)
+
+
+def _probe(dev, a_img, b_img, a_off, b_off, a_mn, b_mn, a_type, b_type, n):
+    from eeg_gnn_ssl_b200 import _lib
+    L = _lib.lib()
+    a = torch.tensor(a_img, dtype=torch.float32, device=dev)
+    b = torch.tensor(b_img, dtype=torch.float32, device=dev)
+    d = torch.full((128, n), float("nan"), device=dev)
+    _lib.check(L.dcgru_tc_probe(C.c_void_p(a.data_ptr()), a.numel() * 4, C.c_void_p(b.data_ptr()), b.numel() * 4,
+                                a_off[0], a_off[1], b_off[0], b_off[1], a_mn, b_mn, a_type, b_type,
+                                C.c_void_p(d.data_ptr()), n, C.c_void_p(torch.cuda.current_stream().cuda_stream)), "probe")
+    torch.cuda.synchronize()
+    return d.cpu().numpy()
+
+
+def test_umma_operand_layouts_pinned_on_hardware(dev):
+    """The shared-memory layouts the kernels rely on, read back from the tensor core itself: one MMA with an
+    index-valued A image and a one-hot B shows which word the hardware reads for a logical (row, k)."""
+    idx = np.arange(2048, dtype=np.float32)                  # exact in tf32
+    onehot_b = np.zeros(16 * 8, dtype=np.float32)            # K-major no-swizzle B, N = 16: [k/4][n][4], one-hot n == k
+    for n in range(8):
+        onehot_b[(n // 4) * 64 + n * 4 + n % 4] = 1.0
+    m = np.arange(128)[:, None]
+    k = np.arange(8)[None, :]
+    # (1) K-major, no swizzle (weights): [k/4][row][4], LBO = 2048, SBO = 128
+    d = _probe(dev, idx, onehot_b, (2048, 128), (256, 128), 0, 0, 0, 0, 16)
+    assert (d[:, :8] == (k // 4) * 512 + m * 4 + k % 4).all()
+    # (2) K-major, 32-byte swizzle (activation tiles of the sequence kernels): rows of 8 k, halves swapped in rows 4-7
+    d = _probe(dev, idx, onehot_b, (16, 256), (256, 128), 0, 0, 6, 0, 16)
+    assert (d[:, :8] == (m // 8) * 64 + (m % 8) * 8 + ((k // 4) ^ ((m % 8) >> 2)) * 4 + k % 4).all()
+    # (3) MN-major fp32 in the no-swizzle layout is NOT read by the tensor core (exact zeros) ...
+    d = _probe(dev, idx, onehot_b, (128, 128), (256, 128), 1, 0, 0, 0, 16)
+    assert (d[:, :8] == 0).all()
+    # (4) ... MN-major needs layout type 1: 128-byte rows of 32 mn, 32-byte chunks XOR-ed with the row (dw_mm.cu)
+    d = _probe(dev, idx, onehot_b, (1024, 512), (256, 128), 1, 0, 1, 0, 16)
+    exp = (m // 32) * 256 + (k // 4) * 128 + (k % 4) * 32 + ((((m % 32) // 8) ^ (k % 4)) * 8) + m % 8
+    assert (d[:, :8] == exp).all()

@@ -4,8 +4,8 @@
 // Per step the three projections of the cell run as UMMA GEMMs with M = 128 rows (4 samples x 32 rows, one
 // warp per sample: see tc_common.cuh), accumulating in one 128 x 192 fp32 TMEM tile:
 //     X : D[:, 0:192] (=)  diffuse(x_t)      @ [Wg_x | Wc_x]     (K = Fin*M)
-//     Hg: D[:, 0:128] (+)= diffuse(h_{t-1})  @  Wg_h             (K = H*M)      -> r, u = sigmoid(. + bg)
-//     Hc: D[:,128:192](+)= diffuse(r*h_{t-1})@  Wc_h             (K = H*M)      -> c = act(. + bc), GRU update
+//     Hg: D[:, 0:128] (+)= diffuse(h_{t-1})  @  Wg_h             (K = H*M)      -> r = sigmoid(D[:,0:64] + bg)  (u: later)
+//     Hc: D[:,128:192](+)= diffuse(r*h_{t-1})@  Wc_h             (K = H*M)      -> c = act(. + bc), u = sigmoid(D[:,64:128] + bg), GRU update
 // A operand: each thread owns one (sample, node) row and keeps that row of the diffusion polynomials P_m
 // in registers for the whole sequence; for every 8-column chunk of [x | h] it forms the M diffusion terms
 // of 4 columns (20 broadcast float4 reads + 40 FMAs per column quad), splits them hi/lo and writes them
@@ -19,8 +19,8 @@
 // B operand: the weights, pre-split and pre-tiled once per launch by pack_w_fwd_kernel, streamed chunk by
 // chunk from L2 with cp.async.bulk (TMA) into a 3-slot ring, each load issued one chunk ahead at the top
 // of the iteration so its latency hides behind two A-tile productions; mbarriers track "weights landed"
-// and "MMAs done".  x_t is streamed the same way, 8 columns at a time, with cp.async into a 3-slot ring
-// (two chunks ahead); only the hidden state stays resident in shared memory.
+// and "MMAs done".  x_t is streamed 8 columns at a time with cp.async into a 4-slot ring (two chunks ahead);
+// the hidden state stays resident in shared memory (r*h overwrites it for the candidate) and in a TMEM stash.
 // The epilogues read the accumulator with tcgen05.ld (thread = row) and fuse bias, sigmoid/tanh, r*h and
 // the GRU update.
 #include <cstdlib>
@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
                 if (rec) p.dbgbuf[g * 8 + 1] = clock64();
                 // one combined poll (weights landed, A tile built): this thread issues MMAs almost synchronously (the
                 // tensor core queues only ~2 of them), so every cycle it spends elsewhere is a cycle the pipe drains
+                // (a non-blocking look-ahead at the next chunk's barriers from inside the issue loop was tried: slower)
                 mbar_wait2(&bar_bfull[sb], kb, &bar_afull[sa], (g >> 1) & 1);
                 if (rec) p.dbgbuf[g * 8 + 2] = clock64();
                 if (q == 0 && t > 0) mbar_wait(&bar_epi, (t - 1) & 1);   // the previous step's TMEM reads are done

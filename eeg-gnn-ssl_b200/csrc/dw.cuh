@@ -38,12 +38,14 @@ struct DwParams {
 constexpr int DWMM_MAXTILE = 4;
 constexpr int DWMM_MAXSET = 4;
 struct DwmmTile {
-    int kg0, nkg;      // K groups (4 kk each) of the G image this 128-row tile covers / loads
+    int kg0, nkg;      // K groups (4 kk each) of the G image this 128-row tile covers
     int og0, ncol;     // first column quad of the dA image and number of columns (64, 128 or 192)
     int tcol;          // TMEM column base inside the set
+    int soff;          // byte offset of the tile's hi part inside a pipeline stage (lo part: + 8 KB)
 };
 struct DwmmSet {
     int ntile, ncoltot, cta0, ncta, ogmin, ogcnt;
+    int nbox, boxgrp[2];   // TMA boxes of the G image per K block: a pair of adjacent tiles, hi and lo, in one load
     DwmmTile tile[DWMM_MAXTILE];
 };
 struct DwmmParams {

@@ -10,6 +10,10 @@
 // CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B produces from a row-major image.  So this kernel has no producer threads:
 // one thread issues tensor-map TMA loads into a 4-stage ring (one K block = 8 image rows), one thread issues the
 // MMAs, eight warps only wake up to flush the TMEM accumulators into the CTA's split-K partial.
+// A K block is fetched with at most three TMA instructions: one 4-D box (32 floats x 8 rows x 8 groups x hi|lo =
+// 16 KB) per PAIR of adjacent tiles and one (12 KB) for the dA rows.  (With one box per tile and part -- ten
+// instructions of ~70 issue cycles each plus a ~300-cycle barrier poll -- the single loader thread was as slow as the
+// MMA issuer and the ring kept running dry: 3.8 TB/s with DRAM only 49 % busy.)
 //
 // Work split: the M dimension (kk) is cut into 128-row tiles; a tile that straddles the x / gate-h / candidate-h
 // parts of the image simply takes the union of the dA columns those parts need (rows x columns that mean nothing
@@ -36,8 +40,10 @@ constexpr int DWMM_KB_PER_SLAB = TC_IMG_ROWS / 8;   // K blocks (8 image rows) p
 constexpr int DWMM_FLUSH = 80;                       // K blocks between flushes (640 rows)
 constexpr int DWMM_THREADS = 320;                    // warp 0: loader, warp 1: MMA issuer, warps 2-9: flush
 constexpr int DWMM_TILE_BYTES = 4 * 1024;            // one of hi / lo of a 128-kk tile: 4 groups x (8 rows x 128 B)
+constexpr int DWMM_BOX_BYTES = 4 * DWMM_TILE_BYTES;  // one G box: [hi | lo][2 tiles]
 constexpr int DWMM_B_BYTES = 6 * 1024;               // one of hi / lo of the dA block: 6 groups of 32 columns
-constexpr int DWMM_STAGE_BYTES = DWMM_MAXTILE * 2 * DWMM_TILE_BYTES + 2 * DWMM_B_BYTES;   // 44 KB
+constexpr int DWMM_B_OFF = 2 * DWMM_BOX_BYTES;       // stage = [box 0][box 1][dA hi | lo]
+constexpr int DWMM_STAGE_BYTES = DWMM_B_OFF + 2 * DWMM_B_BYTES;   // 44 KB
 constexpr int DWMM_SMEM = DWMM_NSTAGE * DWMM_STAGE_BYTES + 1024;                            // + alignment slack
 
 // timing experiment (DCGRU_DBG & 8): clock64 stamps of CTA 0, [K block][loader: top, waited, issued | issuer: top, full, accfree, issued]
@@ -78,10 +84,8 @@ __global__ void __launch_bounds__(DWMM_THREADS, 1) dw_mm_kernel(const DwmmParams
         if (lane == 0) {
             tma_prefetch_desc(&tm_g);
             tma_prefetch_desc(&tm_d);
-            const uint32_t tx = ntile * 2 * DWMM_TILE_BYTES + 2 * DWMM_B_BYTES;     // out-of-bounds groups are zero-filled and counted
-            int grp[DWMM_MAXTILE];
-#pragma unroll
-            for (int j = 0; j < DWMM_MAXTILE; ++j) grp[j] = (j < ntile) ? S.tile[j].kg0 / 8 : 0;
+            const int nbox = S.nbox, grp0 = S.boxgrp[0], grp1 = S.boxgrp[1];
+            const uint32_t tx = nbox * DWMM_BOX_BYTES + 2 * DWMM_B_BYTES;             // out-of-bounds groups are zero-filled and counted
             for (int i = 0; i < nkb; ++i) {
                 const int st = i % DWMM_NSTAGE;
                 const bool rec = p.dbg && blockIdx.x == 0 && i < 256;
@@ -94,15 +98,9 @@ __global__ void __launch_bounds__(DWMM_THREADS, 1) dw_mm_kernel(const DwmmParams
                 const int row_hi = (int)(slab * 2 * TC_IMG_ROWS + (kb - slab * DWMM_KB_PER_SLAB) * 8);
                 uint8_t* sbase = smem + st * DWMM_STAGE_BYTES;
                 mbar_expect_tx(&bar_full[st], tx);
-#pragma unroll
-                for (int j = 0; j < DWMM_MAXTILE; ++j)
-                    if (j < ntile) {
-                        tma_load_3d(sbase + (2 * j) * DWMM_TILE_BYTES, &tm_g, 0, row_hi, grp[j], &bar_full[st]);
-                        tma_load_3d(sbase + (2 * j + 1) * DWMM_TILE_BYTES, &tm_g, 0, row_hi + TC_IMG_ROWS, grp[j], &bar_full[st]);
-                    }
-                uint8_t* sb = sbase + DWMM_MAXTILE * 2 * DWMM_TILE_BYTES;
-                tma_load_3d(sb, &tm_d, 0, row_hi, 0, &bar_full[st]);
-                tma_load_3d(sb + DWMM_B_BYTES, &tm_d, 0, row_hi + TC_IMG_ROWS, 0, &bar_full[st]);
+                tma_load_4d(sbase, &tm_g, 0, row_hi, grp0, 0, &bar_full[st]);
+                if (nbox > 1) tma_load_4d(sbase + DWMM_BOX_BYTES, &tm_g, 0, row_hi, grp1, 0, &bar_full[st]);
+                tma_load_4d(sbase + DWMM_B_OFF, &tm_d, 0, row_hi, 0, 0, &bar_full[st]);
                 if (rec) dwmm_dbg[i * 8 + 2] = clock64();
             }
         }
@@ -114,12 +112,13 @@ __global__ void __launch_bounds__(DWMM_THREADS, 1) dw_mm_kernel(const DwmmParams
         if (lane == 0) {
             uint64_t dah[DWMM_MAXTILE], dal[DWMM_MAXTILE], dbh[DWMM_MAXTILE], dbl[DWMM_MAXTILE];
             uint32_t idesc[DWMM_MAXTILE], dcol[DWMM_MAXTILE];
-            const uint32_t base = smem_u32(smem), bbase = base + DWMM_MAXTILE * 2 * DWMM_TILE_BYTES;
+            const uint32_t base = smem_u32(smem), bbase = base + DWMM_B_OFF;
 #pragma unroll
             for (int j = 0; j < DWMM_MAXTILE; ++j) {
                 const int og0 = (j < ntile) ? S.tile[j].og0 : 0;
-                dah[j] = make_smem_desc_mn(base + (2 * j) * DWMM_TILE_BYTES, 1024, 512);
-                dal[j] = make_smem_desc_mn(base + (2 * j + 1) * DWMM_TILE_BYTES, 1024, 512);
+                const uint32_t soff = (j < ntile) ? S.tile[j].soff : 0;
+                dah[j] = make_smem_desc_mn(base + soff, 1024, 512);
+                dal[j] = make_smem_desc_mn(base + soff + 2 * DWMM_TILE_BYTES, 1024, 512);
                 dbh[j] = make_smem_desc_mn(bbase + (og0 / 8) * 1024, 1024, 512);
                 dbl[j] = make_smem_desc_mn(bbase + DWMM_B_BYTES + (og0 / 8) * 1024, 1024, 512);
                 idesc[j] = make_idesc_tf32_mn(128, j < ntile ? S.tile[j].ncol : 64);
@@ -289,20 +288,27 @@ bool dwmm_plan(int fin, int H, int M, long nslab, int nsms, DwmmParams* out) {
         if (oc) { if (lo > 32) lo = 32; hi = 48; }
         t.og0 = lo; t.ncol = 4 * (hi - lo); t.tcol = 0;
     }
-    // first-fit decreasing into sets of <= 512 TMEM columns and <= DWMM_MAXTILE tiles
-    bool used[16] = {false};
-    for (int placed = 0; placed < ntile;) {
+    // pairs of adjacent tiles (one TMA box each), first-fit decreasing into sets of <= 512 TMEM columns and <= 2 pairs
+    const int npair = (ntile + 1) / 2;
+    int pcols[8];
+    for (int k = 0; k < npair; ++k) pcols[k] = tiles[2 * k].ncol + (2 * k + 1 < ntile ? tiles[2 * k + 1].ncol : 0);
+    bool used[8] = {false};
+    for (int placed = 0; placed < npair;) {
         if (p.nset == DWMM_MAXSET) return false;
         DwmmSet& S = p.set[p.nset++];
-        S.ntile = 0; S.ncoltot = 0;
-        for (int want = 192; want >= 64; want -= 64)
-            for (int j = 0; j < ntile; ++j)
-                if (!used[j] && tiles[j].ncol == want && S.ncoltot + want <= 512 && S.ntile < DWMM_MAXTILE) {
-                    used[j] = true; ++placed;
-                    DwmmTile t = tiles[j];
-                    t.tcol = S.ncoltot;
-                    S.ncoltot += want;
-                    S.tile[S.ntile++] = t;
+        S.ntile = 0; S.ncoltot = 0; S.nbox = 0; S.boxgrp[0] = S.boxgrp[1] = 0;
+        for (int want = 384; want >= 64; want -= 64)
+            for (int k = 0; k < npair; ++k)
+                if (!used[k] && pcols[k] == want && S.ncoltot + want <= 512 && S.nbox < 2) {
+                    used[k] = true; ++placed;
+                    for (int j = 2 * k; j < 2 * k + 2 && j < ntile; ++j) {
+                        DwmmTile t = tiles[j];
+                        t.tcol = S.ncoltot;
+                        t.soff = S.nbox * (4 * 4096) + (j - 2 * k) * 4096;      // [box][hi|lo][tile of the pair][4 KB]
+                        S.ncoltot += t.ncol;
+                        S.tile[S.ntile++] = t;
+                    }
+                    S.boxgrp[S.nbox++] = 8 * k;
                 }
         int lo = 48, hi = 0;
         for (int j = 0; j < S.ntile; ++j) {
@@ -333,22 +339,23 @@ size_t colsum_part_floats(int H) { return (size_t)CS_CTAS * 3 * H; }
 cudaError_t launch_dw_mm(const DwmmParams& p_, int fin, int H, int M, float* dWg, float* dWc, cudaStream_t st) {
     DwmmParams p = p_;
     { const char* e = getenv("DCGRU_DBG"); p.dbg = e ? (atoi(e) & 8) : 0; }
-    // swizzling 3-D views of the row-major images: (32 floats = one 128-byte row piece | image row | 32-float group)
+    // swizzling 4-D views of the row-major images: (32 floats = one 128-byte row piece | image row | 32-float group |
+    // hi / lo part, 96 rows further); the row coordinate always addresses the hi part
     CUtensorMap tg, td;
     const unsigned long long rows = (unsigned long long)(p.nkb / DWMM_KB_PER_SLAB) * 2 * TC_IMG_ROWS;
     {
         const unsigned long long kkp = seq_fwd_tc_kkp(fin);
-        const unsigned long long dims[3] = {32, rows, kkp / 32};
-        const unsigned long long str[3] = {4, kkp * 4, 128};
-        const unsigned box[3] = {32, 8, 4};
-        cudaError_t e = make_tmap_f32(&tg, p.G, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        const unsigned long long dims[4] = {32, rows, kkp / 32, 2};
+        const unsigned long long str[4] = {4, kkp * 4, 128, TC_IMG_ROWS * kkp * 4};
+        const unsigned box[4] = {32, 8, 8, 2};
+        cudaError_t e = make_tmap_f32(&tg, p.G, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (e != cudaSuccess) return e;
     }
     {
-        const unsigned long long dims[3] = {32, rows, (unsigned long long)(3 * H / 32)};
-        const unsigned long long str[3] = {4, (unsigned long long)3 * H * 4, 128};
-        const unsigned box[3] = {32, 8, 6};
-        cudaError_t e = make_tmap_f32(&td, p.DA, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+        const unsigned long long dims[4] = {32, rows, (unsigned long long)(3 * H / 32), 2};
+        const unsigned long long str[4] = {4, (unsigned long long)3 * H * 4, 128, (unsigned long long)TC_IMG_ROWS * 3 * H * 4};
+        const unsigned box[4] = {32, 8, 6, 2};
+        cudaError_t e = make_tmap_f32(&td, p.DA, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
         if (e != cudaSuccess) return e;
     }
     cudaError_t e = cudaFuncSetAttribute(dw_mm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DWMM_SMEM);

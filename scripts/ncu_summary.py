@@ -1,7 +1,7 @@
 """Turn `ncu --set full` reports (gpurun_out/full_<kernel>.ncu-rep) into the text summaries committed under profiles/
-and the per-launch DRAM traffic table bench.py reports as roofline.traffic.   usage: python scripts/ncu_summary.py r01b"""
+and the per-launch DRAM traffic table bench.py reports as roofline.traffic.   usage: python scripts/ncu_summary.py r01c"""
 import csv, json, subprocess, sys
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01b"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01c"
 KERNELS = {"seq_fwd_tc": "seq_fwd_tc_kernel", "seq_bwd_tc": "seq_bwd_tc_kernel", "dw_mm": "dw_mm_kernel"}
 WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "launch__shared_mem_per_block_dynamic", "dram__bytes_read.sum", "dram__bytes_write.sum",

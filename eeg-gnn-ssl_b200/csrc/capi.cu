@@ -438,6 +438,28 @@ int dcgru_debug_dwmm_stamps(long long* out, int32_t n) {
     return 0;
 }
 
+// plan of the weight-gradient GEMM as plain integers (host logic only: testable without a device):
+// out[0] = number of sets, out[1] = K blocks, then per set 4 + 6*ntile ints:
+//   ntile, TMEM columns, CTAs, TMA boxes, and per tile kg0, nkg, og0, ncol, tcol, soff
+int dcgru_debug_dwmm_plan(int32_t input_dim, int32_t batch, int32_t seq_len, int32_t num_sms, int32_t* out, int32_t cap) {
+    if (!out || cap < 2) return fail("bad arguments");
+    DwmmParams q;
+    if (!dwmm_plan(input_dim, 64, 3, seq_tc_nslab(batch, seq_len), num_sms, &q)) return fail("no plan for this shape");
+    int n = 0;
+    auto put = [&](long v) { if (n < cap) out[n] = (int32_t)v; ++n; };
+    put(q.nset); put(q.nkb);
+    for (int s = 0; s < q.nset; ++s) {
+        const DwmmSet& S = q.set[s];
+        put(S.ntile); put(S.ncoltot); put(S.ncta); put(S.nbox);
+        for (int j = 0; j < S.ntile; ++j) {
+            const DwmmTile& t = S.tile[j];
+            put(t.kg0); put(t.nkg); put(t.og0); put(t.ncol); put(t.tcol); put(t.soff);
+        }
+    }
+    if (n > cap) return fail("output buffer too small (%d > %d)", n, cap);
+    return 0;
+}
+
 int dcgru_debug_encoder_bwd_offsets(const dcgru_cell_desc* d, int32_t batch, int32_t seq_len, size_t* out3) {
     if (check_desc(d) || batch < 1 || seq_len < 1 || !out3) return fail("bad arguments");
     float *WgT, *WcT, *dA, *part, *partb, *ptbuf, *daimg, *mmpart, *cspart;

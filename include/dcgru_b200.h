@@ -125,6 +125,9 @@ size_t dcgru_encoder_layer_bwd_workspace(const dcgru_cell_desc *d, int32_t batch
  * dA operand image, per-CTA partials of the weight-gradient GEMM} (0 = not used by this configuration). */
 int dcgru_debug_encoder_bwd_offsets(const dcgru_cell_desc *d, int32_t batch, int32_t seq_len,
                                     size_t *out3);
+/* the tile / set / CTA plan of the weight-gradient GEMM as integers (pure host logic; see capi.cu for the layout) */
+int dcgru_debug_dwmm_plan(int32_t input_dim, int32_t batch, int32_t seq_len, int32_t num_sms,
+                          int32_t *out, int32_t cap);
 /* clock64 stamps of the weight-gradient GEMM's loader / MMA-issuer threads (recorded when DCGRU_DBG & 8) */
 int dcgru_debug_dwmm_stamps(long long *out, int32_t n);
 

@@ -121,3 +121,48 @@ def test_hyphenated_directory_works_as_drop_in_root():
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
     assert out.returncode == 0, out.stderr
     assert out.stdout.strip() == "model.cell"
+
+
+@pytest.mark.parametrize("fin,batch,seq,sms", [(100, 512, 60, 148), (64, 512, 60, 148), (100, 7, 3, 148), (64, 1, 1, 132),
+                                               (100, 4096, 12, 148)])
+def test_weight_gradient_gemm_plan_invariants(fin, batch, seq, sms):
+    """dw_mm.cu's host-side planner: every K group of the operand image is covered by exactly one tile, every set
+    fits TMEM (512 columns) and two TMA boxes, the CTAs of all sets fill the device in one wave."""
+    _ensure_built()
+    from eeg_gnn_ssl_b200 import _lib
+    L = _lib.lib()
+    buf = (C.c_int32 * 256)()
+    assert L.dcgru_debug_dwmm_plan(fin, batch, seq, sms, buf, 256) == 0, L.dcgru_last_error()
+    v = list(buf)
+    nset, nkb = v[0], v[1]
+    nslab = (batch + 3) // 4 * seq
+    assert nkb == nslab * 12                                 # 96 image rows per slab = 12 K blocks of 8 rows
+    kgt = ((fin + 7) // 8 + 16) * 6                          # K groups per step: x chunks + 8 gate + 8 candidate chunks
+    kgx = (fin + 7) // 8 * 6
+    pos, covered, ctas = 2, [], 0
+    for _ in range(nset):
+        ntile, ncol, ncta, nbox = v[pos:pos + 4]
+        pos += 4
+        assert 1 <= ntile <= 4 and ncol <= 512 and 1 <= nbox <= 2 and ncta >= 1
+        tcols = 0
+        for j in range(ntile):
+            kg0, nkg, og0, nc, tcol, soff = v[pos:pos + 6]
+            pos += 6
+            assert kg0 % 32 == 0 and 1 <= nkg <= 32 and nc in (64, 128, 192) and tcol == tcols
+            assert soff % 4096 == 0 and soff // 16384 < nbox and (soff // 4096) % 4 in (0, 1)
+            # the dA columns of the tile cover what the parts it overlaps need: x -> r|u|c, gate h -> r|u, candidate h -> c
+            lo, hi = og0, og0 + nc // 4
+            if kg0 < kgx:
+                assert (lo, hi) == (0, 48)
+            if kg0 < kgx + 48 and kg0 + nkg > kgx:
+                assert lo == 0 and hi >= 32
+            if kg0 + nkg > kgx + 48:
+                assert lo <= 32 and hi == 48
+            tcols += nc
+            covered += list(range(kg0, kg0 + nkg))
+        assert tcols == ncol
+        ctas += ncta
+    assert sorted(covered) == list(range(kgt))
+    assert ctas == min(sms, max(nset, ctas)) and ctas <= sms
+    if nkb >= sms:
+        assert ctas == sms                                    # one full wave

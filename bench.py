@@ -244,8 +244,15 @@ def main():
     model = DCRNNModel_classification(model_args(cfg), cfg["classes"]).to(dev)
     broadcast_parameters(model)
     model.train()
-    sync = FlatGradSync(model.parameters(), world_size=world)
-    opt = torch.optim.Adam(model.parameters(), lr=3e-4, weight_decay=5e-4, capturable=True)
+    # optimiser tail of the step (train.py:273-275): fused clip + Adam over the flat buffers (optim.cu; parity with
+    # torch in tests/test_gpu_optim.py), or torch's own clip_grad_norm_ + Adam with DCGRU_FUSED_OPT=0
+    fused_opt = os.environ.get("DCGRU_FUSED_OPT", "1") == "1"
+    sync = FlatGradSync(model.parameters(), world_size=world, align=4 if fused_opt else 1)
+    if fused_opt:
+        from eeg_gnn_ssl_b200.optim import FusedClipAdam
+        opt = FusedClipAdam(model.parameters(), lr=3e-4, weight_decay=5e-4, max_grad_norm=5.0, grad_sync=sync)
+    else:
+        opt = torch.optim.Adam(model.parameters(), lr=3e-4, weight_decay=5e-4, capturable=True)
 
     x, y, sl, sup = make_batch(cfg, 123 + rank)
     corr = sup is None
@@ -268,7 +275,8 @@ def main():
         loss = loss_of(cfg, logits, yd)
         loss.backward()
         sync.sync()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)
+        if not fused_opt:
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 5.0)
         opt.step()
         return loss
 
@@ -476,7 +484,8 @@ def main():
                        "parallelism": f"dp{world}", "l2": "inputs larger than L2 (x = 233 MB/rank, saved "
                        "activations ~1.2 GB/rank are rewritten every step)",
                        "step": "zero_grad+fwd+loss+bwd+allreduce+clip+adam", "grad_allreduce_bytes": sync.nbytes,
-                       "launch": graph_note, "e2e_pipeline": e2e_note},
+                       "launch": graph_note, "e2e_pipeline": e2e_note,
+                       "optimizer": "fused clip+Adam (optim.cu)" if fused_opt else "torch clip_grad_norm_ + Adam"},
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": launches, "roofline": roofline, "clocks": clk.summary()}

@@ -557,6 +557,22 @@ int dcgru_encoder_layer_bwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
     return 0;
 }
 
+// ---- fused optimiser step -------------------------------------------------------------------------------
+size_t dcgru_clip_adam_workspace(size_t n) { return align_up((size_t)clip_adam_npart(n) * 4); }
+
+int dcgru_clip_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, size_t n, const float* lr,
+                         int32_t* step, float beta1, float beta2, float eps, float weight_decay, float max_grad_norm,
+                         float* total_norm, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!params || !grads || !exp_avg || !exp_avg_sq || !lr || !step || !workspace) return fail("null pointer");
+    if (n == 0) return fail("empty parameter buffer");
+    if (workspace_bytes < dcgru_clip_adam_workspace(n)) return fail("workspace too small");
+    if (!(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f) || !(eps > 0.f)) return fail("bad Adam hyper-parameters");
+    cudaStream_t st = (cudaStream_t)stream;
+    LAUNCH("clip_adam", launch_clip_adam(params, grads, exp_avg, exp_avg_sq, n, lr, step, beta1, beta2, eps, weight_decay,
+                                         max_grad_norm, (float*)workspace, total_norm, st));
+    return 0;
+}
+
 // ---- decoder ------------------------------------------------------------------------------------------
 static int check_dec(const dcgru_cell_desc* d, int L, int B, int T) {
     if (check_desc(d)) return 1;

@@ -12,19 +12,23 @@ import torch.distributed as dist
 
 
 class FlatGradSync:
-    def __init__(self, params, world_size=None, process_group=None):
+    def __init__(self, params, world_size=None, process_group=None, align=1):
+        """``align``: every parameter's slice starts at a multiple of ``align`` elements (4 = 16 bytes: what
+        ``optim.FusedClipAdam`` needs to lay the parameters out the same way; the gaps stay zero)."""
         self.params = [p for p in params if p.requires_grad]
         # tied parameters appear once in .parameters(); keep it that way
         self.group = process_group
         self.world = world_size if world_size is not None else (
             dist.get_world_size(process_group) if dist.is_initialized() else 1)
-        n = sum(p.numel() for p in self.params)
+        self.offsets, n = [], 0
+        for p in self.params:
+            n = (n + align - 1) // align * align
+            self.offsets.append(n)
+            n += p.numel()
         dev = self.params[0].device
         self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
-        off = 0
-        for p in self.params:
+        for p, off in zip(self.params, self.offsets):
             p.grad = self.flat[off: off + p.numel()].view_as(p)
-            off += p.numel()
 
     @property
     def nbytes(self):

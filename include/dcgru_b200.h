@@ -146,6 +146,20 @@ int dcgru_encoder_layer_bwd(const dcgru_cell_desc *d, int32_t batch, int32_t seq
                             const void *gsave, size_t gsave_bytes,
                             void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- fused optimiser step ---------------------------------------------------
+ * The tail of the reference's training step on flat fp32 buffers of n elements (train.py:273-275):
+ * torch.nn.utils.clip_grad_norm_(max_grad_norm) followed by torch.optim.Adam(lr, betas, eps,
+ * weight_decay).step() (L2 form: grad += weight_decay * param), in two launches.
+ * lr and step are DEVICE scalars: step is incremented by the call (bias correction uses the new value),
+ * lr may be changed by a scheduler between calls even when the call sits inside a CUDA graph.
+ * grads is overwritten with the clipped gradient, total_norm (device, may be NULL) receives the
+ * pre-clip global norm (the return value of clip_grad_norm_).  max_grad_norm <= 0 disables clipping. */
+size_t dcgru_clip_adam_workspace(size_t n);
+int dcgru_clip_adam_step(float *params, float *grads, float *exp_avg, float *exp_avg_sq, size_t n,
+                         const float *lr, int32_t *step, float beta1, float beta2, float eps,
+                         float weight_decay, float max_grad_norm, float *total_norm,
+                         void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- decoder -------------------------------------------------------------------------------
  * One launch = DCGRUDecoder.forward (model/model.py:149-204): To autoregressive steps x L
  * cells + Linear(H->Fo) per node.  d describes cell 0 (input_dim = Fo); cells >= 1 have

@@ -23,7 +23,8 @@ def _worker(rank, world, port, q):
     torch.manual_seed(100 + rank)                       # different init per rank on purpose
     model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 1))
     broadcast_parameters(model)
-    sync = FlatGradSync(model.parameters(), world_size=world)
+    sync = FlatGradSync(model.parameters(), world_size=world, align=4)     # padded slices, as FusedClipAdam lays them out
+    assert all(o % 4 == 0 for o in sync.offsets) and sync.flat.numel() >= sum(p.numel() for p in model.parameters())
     g = torch.Generator().manual_seed(0)
     x, y = torch.randn(8, 6, generator=g), torch.randn(8, 1, generator=g)
     sync.zero()

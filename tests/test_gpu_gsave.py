@@ -177,7 +177,7 @@ def _module_grads(dev, B, T, L, seed):
     return [top.detach().cpu().double(), h0.grad.cpu().double()] + [p.grad.cpu().double() for p in enc.parameters()]
 
 
-@pytest.mark.parametrize("B,T,L", [(13, 5, 2), (150, 3, 2), (512, 7, 2)])
+@pytest.mark.parametrize("B,T,L", [(13, 5, 2), (150, 3, 2), (512, 7, 2), (700, 2, 2)])   # 700 clips = 175 CTAs: more than one wave
 def test_gsave_module_parity(dev, monkeypatch, B, T, L):
     """DCRNNEncoder through the drop-in modules: operand-image path (default) vs recompute path vs fp32 FMA path"""
     monkeypatch.setenv("DCGRU_DISABLE_TC", "1")

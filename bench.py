@@ -282,7 +282,12 @@ class Workload:
         # optimiser tail of the step (train.py:273-275): fused clip + Adam over the flat buffers (optim.cu; parity
         # with torch in tests/test_gpu_optim.py), or torch's own clip_grad_norm_ + Adam with DCGRU_FUSED_OPT=0
         self.fused_opt = os.environ.get("DCGRU_FUSED_OPT", "1") == "1"
-        self.sync = FlatGradSync(self.model.parameters(), world_size=world, align=4 if self.fused_opt else 1)
+        # data-parallel exchange: bucketed all-reduce on a side stream as backward produces the gradients; the 1/world
+        # scale is folded into the fused optimiser pass (DCGRU_DP_OVERLAP=0: one collective after backward)
+        self.sync = FlatGradSync(self.model.parameters(), world_size=world, align=4 if self.fused_opt else 1,
+                                 overlap=os.environ.get("DCGRU_DP_OVERLAP", "1") == "1",
+                                 scale_in_optimizer=self.fused_opt,
+                                 bucket_counts=[4] * (cfg["L"] * (2 if cfg["task"] == "ssl" else 1)))
         if self.fused_opt:
             self.opt = FusedClipAdam(self.model.parameters(), lr=3e-4, weight_decay=5e-4, max_grad_norm=5.0,
                                      grad_sync=self.sync)

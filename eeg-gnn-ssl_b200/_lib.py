@@ -72,7 +72,7 @@ def lib():
     L.dcgru_debug_dwmm_stamps.argtypes = [C.POINTER(C.c_longlong), i32]
     L.dcgru_clip_adam_workspace.argtypes = [sz]
     L.dcgru_clip_adam_workspace.restype = sz
-    L.dcgru_clip_adam_step.argtypes = [vp, vp, vp, vp, sz, vp, vp, f32, f32, f32, f32, f32, vp, vp, sz, vp]
+    L.dcgru_clip_adam_step.argtypes = [vp, vp, vp, vp, sz, vp, vp, f32, f32, f32, f32, f32, f32, vp, vp, sz, vp]
     L.dcgru_debug_dwmm_plan.argtypes = [i32, i32, i32, i32, C.POINTER(i32), i32]
     L.dcgru_timing_enable.argtypes = [C.c_int]
     L.dcgru_timing_collect.argtypes = [C.c_char_p, sz]

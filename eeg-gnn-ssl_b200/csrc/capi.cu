@@ -60,18 +60,21 @@ struct Timed {
         CUDA_TRY(expr);             \
     } while (0)
 
-struct DevInfo { int sms = 0; int smem = 0; bool ok = false; };
-DevInfo& devinfo() {
+struct DevInfo { int sms = 0; int smem = 0; };
+DevInfo query_dev(int dev) {
+    DevInfo r;
+    cudaDeviceGetAttribute(&r.sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&r.smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    return r;
+}
+// per-device attributes, filled once per device under std::call_once (callers: training thread + autograd thread)
+const DevInfo& devinfo() {
     static DevInfo d[64];
+    static std::once_flag once[64];
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
-    DevInfo& r = d[dev];
-    if (!r.ok) {
-        cudaDeviceGetAttribute(&r.sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaDeviceGetAttribute(&r.smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        r.ok = r.sms > 0;
-    }
-    return r;
+    std::call_once(once[dev], [dev] { d[dev] = query_dev(dev); });
+    return d[dev];
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -372,7 +375,7 @@ int dcgru_encoder_layer_fwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
         return fail("x/h0/h_seq/weights must be 16-byte aligned with strides multiple of 4 floats");
     cudaStream_t st = (cudaStream_t)stream;
     // tensor-core path (tcgen05, 3xTF32): K=2 / one support / 64 units -- the reference's default cell
-    if (tc_enabled() && ruc && workspace && aligned16(workspace) &&
+    if (tc_enabled() && workspace && aligned16(workspace) &&
         workspace_bytes >= align_up(seq_fwd_tc_wimg_bytes(d->input_dim)) + 16384 &&
         seq_fwd_tc_supported(d->num_nodes, d->input_dim, d->hid_dim, M, devinfo().smem)) {
         if (gsave) {
@@ -558,18 +561,20 @@ int dcgru_encoder_layer_bwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
 }
 
 // ---- fused optimiser step -------------------------------------------------------------------------------
-size_t dcgru_clip_adam_workspace(size_t n) { return align_up((size_t)clip_adam_npart(n) * 4); }
+size_t dcgru_clip_adam_workspace(size_t n) { return align_up((size_t)clip_adam_npart(n) * 8); }
 
 int dcgru_clip_adam_step(float* params, float* grads, float* exp_avg, float* exp_avg_sq, size_t n, const float* lr,
                          int32_t* step, float beta1, float beta2, float eps, float weight_decay, float max_grad_norm,
-                         float* total_norm, void* workspace, size_t workspace_bytes, void* stream) {
+                         float grad_scale, float* total_norm, void* workspace, size_t workspace_bytes, void* stream) {
     if (!params || !grads || !exp_avg || !exp_avg_sq || !lr || !step || !workspace) return fail("null pointer");
     if (n == 0) return fail("empty parameter buffer");
     if (workspace_bytes < dcgru_clip_adam_workspace(n)) return fail("workspace too small");
     if (!(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f) || !(eps > 0.f)) return fail("bad Adam hyper-parameters");
+    if (!(grad_scale > 0.f)) return fail("grad_scale must be positive (1 = none, 1/world = data-parallel average)");
+    if (reinterpret_cast<uintptr_t>(workspace) & 7) return fail("workspace must be 8-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     LAUNCH("clip_adam", launch_clip_adam(params, grads, exp_avg, exp_avg_sq, n, lr, step, beta1, beta2, eps, weight_decay,
-                                         max_grad_norm, (float*)workspace, total_norm, st));
+                                         max_grad_norm, grad_scale, (double*)workspace, total_norm, st));
     return 0;
 }
 

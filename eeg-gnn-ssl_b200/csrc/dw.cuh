@@ -102,8 +102,8 @@ cudaError_t launch_dx_tc(int B, int T, int N, const float* P, const float* Wg, c
                          float* wimg, float* dx, cudaStream_t st);
 int clip_adam_npart(size_t n);
 cudaError_t launch_clip_adam(float* p, float* g, float* m, float* v, size_t n, const float* lr_dev, int* step,
-                             float beta1, float beta2, float eps, float wd, float max_norm, float* partial,
-                             float* norm_out, cudaStream_t st);
+                             float beta1, float beta2, float eps, float wd, float max_norm, float gscale,
+                             double* partial, float* norm_out, cudaStream_t st);
 cudaError_t launch_tc_selftest(const float* A, const float* B, float* C, int N, int K, cudaStream_t st);
 cudaError_t launch_tc_probe(const float* Aimg, int a_bytes, const float* Bimg, int b_bytes, uint32_t a_lbo, uint32_t a_sbo,
                             uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc, uint32_t a_type, uint32_t b_type, float* D, int N,

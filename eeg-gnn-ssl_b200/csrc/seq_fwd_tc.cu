@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
                 }
                 if (erec) es[3] = clock64();
                 stage_put(v);
-                stage_to_global(ruc, 3 * FT_H, hf * 32);
+                if (p.ruc) stage_to_global(ruc, 3 * FT_H, hf * 32);     // ruc = NULL: inference, nothing saved for BPTT
                 if (erec) es[4] = clock64();
             }
             tc_fence_before();
@@ -526,10 +526,12 @@ __global__ void __launch_bounds__(FT_THREADS, 1) seq_fwd_tc_kernel(const FwdTcPa
                 if (erec) es[9] = clock64();
                 tmem_st32(taddr + lane_base + FT_STASH + hf * 32, hp);
                 if (erec) es[10] = clock64();
-                stage_put(v);
-                stage_to_global(ruc, 3 * FT_H, 2 * FT_H + hf * 32);
-                stage_put(u);
-                stage_to_global(ruc, 3 * FT_H, FT_H + hf * 32);
+                if (p.ruc) {
+                    stage_put(v);
+                    stage_to_global(ruc, 3 * FT_H, 2 * FT_H + hf * 32);
+                    stage_put(u);
+                    stage_to_global(ruc, 3 * FT_H, FT_H + hf * 32);
+                }
                 stage_put(hp);
                 stage_to_global(hout, FT_H, hf * 32);
                 if (erec) es[11] = clock64();

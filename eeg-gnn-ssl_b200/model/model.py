@@ -4,8 +4,9 @@
 Encoder: one persistent CUDA kernel per layer over all T steps (model/model.py:90-99).
 Decoder: one persistent CUDA kernel for all To steps x L cells + projection (model/model.py:182-202).
 """
-import math
 import random
+
+import numpy as np
 
 import torch
 import torch.nn as nn
@@ -165,6 +166,8 @@ class DCRNNModel_nextTimePred(nn.Module):
         ratio = None
         if self.training and self.use_curriculum_learning and batches_seen is not None:
             # inverse-sigmoid scheduled sampling (utils.py:385-390)
-            ratio = self.cl_decay_steps / (self.cl_decay_steps + math.exp(batches_seen / self.cl_decay_steps))
+            # np.exp like the reference: saturates to inf (ratio 0) instead of raising OverflowError in long runs
+            with np.errstate(over="ignore"):
+                ratio = float(self.cl_decay_steps / (self.cl_decay_steps + np.exp(batches_seen / self.cl_decay_steps)))
         out = self.decoder(decoder_inputs.transpose(0, 1), context, supports, teacher_forcing_ratio=ratio)
         return out.reshape(to_len, b, n, -1).transpose(0, 1)

@@ -153,11 +153,13 @@ int dcgru_encoder_layer_bwd(const dcgru_cell_desc *d, int32_t batch, int32_t seq
  * lr and step are DEVICE scalars: step is incremented by the call (bias correction uses the new value),
  * lr may be changed by a scheduler between calls even when the call sits inside a CUDA graph.
  * grads is overwritten with the clipped gradient, total_norm (device, may be NULL) receives the
- * pre-clip global norm (the return value of clip_grad_norm_).  max_grad_norm <= 0 disables clipping. */
+ * pre-clip global norm (the return value of clip_grad_norm_).  max_grad_norm <= 0 disables clipping.
+ * grad_scale multiplies the gradient first (1 = none; 1/world_size turns the all-reduced SUM into the
+ * data-parallel average without a separate pass); the norm and the clip are those of the scaled gradient. */
 size_t dcgru_clip_adam_workspace(size_t n);
 int dcgru_clip_adam_step(float *params, float *grads, float *exp_avg, float *exp_avg_sq, size_t n,
                          const float *lr, int32_t *step, float beta1, float beta2, float eps,
-                         float weight_decay, float max_grad_norm, float *total_norm,
+                         float weight_decay, float max_grad_norm, float grad_scale, float *total_norm,
                          void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- decoder -------------------------------------------------------------------------------

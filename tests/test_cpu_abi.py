@@ -172,14 +172,14 @@ def test_fused_optimizer_entry_point_validates_arguments():
     _ensure_built()
     from eeg_gnn_ssl_b200 import _lib
     L = _lib.lib()
-    assert L.dcgru_clip_adam_workspace(168641) >= 4 * 42          # one partial per 4096 elements
-    assert L.dcgru_clip_adam_workspace(10 ** 9) <= 4096            # capped at 512 partials
-    rc = L.dcgru_clip_adam_step(None, None, None, None, 16, None, None, 0.9, 0.999, 1e-8, 0.0, 5.0, None, None, 0, None)
+    assert L.dcgru_clip_adam_workspace(168641) >= 8 * 42          # one partial per 4096 elements
+    assert L.dcgru_clip_adam_workspace(10 ** 9) <= 8192            # capped at 512 partials
+    rc = L.dcgru_clip_adam_step(None, None, None, None, 16, None, None, 0.9, 0.999, 1e-8, 0.0, 5.0, 1.0, None, None, 0, None)
     assert rc != 0 and b"null" in L.dcgru_last_error()
     buf = (C.c_float * 16)()
     step = (C.c_int32 * 1)()
     p = C.cast(buf, C.c_void_p)
-    rc = L.dcgru_clip_adam_step(p, p, p, p, 16, p, C.cast(step, C.c_void_p), 1.5, 0.999, 1e-8, 0.0, 5.0, None, p, 4096, None)
+    rc = L.dcgru_clip_adam_step(p, p, p, p, 16, p, C.cast(step, C.c_void_p), 1.5, 0.999, 1e-8, 0.0, 5.0, 1.0, None, p, 4096, None)
     assert rc != 0 and b"hyper" in L.dcgru_last_error()             # rejected before any launch
 
 

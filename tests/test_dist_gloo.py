@@ -23,7 +23,10 @@ def _worker(rank, world, port, q):
     torch.manual_seed(100 + rank)                       # different init per rank on purpose
     model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 1))
     broadcast_parameters(model)
-    sync = FlatGradSync(model.parameters(), world_size=world, align=4)     # padded slices, as FusedClipAdam lays them out
+    # padded slices, as FusedClipAdam lays them out; one bucket per Linear: each bucket's all-reduce is issued from the
+    # gradient hook of its last parameter while backward is still running (the last layer's bucket goes first)
+    sync = FlatGradSync(model.parameters(), world_size=world, align=4, bucket_counts=[2, 2])
+    assert sync.overlap and [b[:2] for b in sync._buckets] == [[0, sync.offsets[2]], [sync.offsets[2], sync.flat.numel()]]
     assert all(o % 4 == 0 for o in sync.offsets) and sync.flat.numel() >= sum(p.numel() for p in model.parameters())
     g = torch.Generator().manual_seed(0)
     x, y = torch.randn(8, 6, generator=g), torch.randn(8, 1, generator=g)
@@ -31,8 +34,17 @@ def _worker(rank, world, port, q):
     xs, ys = shard_batch(x, rank, world), shard_batch(y, rank, world)
     torch.nn.functional.mse_loss(model(xs), ys).backward()
     assert all(p.grad.data_ptr() >= sync.flat.data_ptr() for p in model.parameters())   # still views
+    assert sync._launched == 2                           # both buckets were issued during backward
     sync.sync()
     flat_dp = sync.flat.clone()
+    # the same through the single-collective path
+    sync1 = FlatGradSync(model.parameters(), world_size=world, align=4, overlap=False)
+    torch.nn.functional.mse_loss(model(xs), ys).backward()
+    sync1.sync()
+    assert torch.equal(sync1.flat, flat_dp)
+    for h in sync._hooks:
+        h.remove()
+    sync = sync1
     # single-process reference on the full batch with rank 0's weights
     sync.zero()                                          # (zero_grad() would drop the views)
     torch.nn.functional.mse_loss(model(x), y).backward()

@@ -13,6 +13,7 @@ SYMBOLS = [
     "dcgru_timing_enable", "dcgru_timing_collect", "dcgru_tc_selftest", "dcgru_debug_encoder_bwd_offsets",
     "dcgru_debug_dwmm_stamps", "dcgru_debug_dwmm_plan", "dcgru_tc_probe",
     "dcgru_clip_adam_workspace", "dcgru_clip_adam_step",
+    "dcgru_debug_bulk_dp_workspace", "dcgru_debug_bulk_dp",
 ]
 
 MAX_LAYERS = 4
@@ -74,12 +75,16 @@ def lib():
     L.dcgru_clip_adam_workspace.restype = sz
     L.dcgru_clip_adam_step.argtypes = [vp, vp, vp, vp, sz, vp, vp, f32, f32, f32, f32, f32, f32, vp, vp, sz, vp]
     L.dcgru_debug_dwmm_plan.argtypes = [i32, i32, i32, i32, C.POINTER(i32), i32]
+    L.dcgru_debug_bulk_dp_workspace.argtypes = [i32, i32, i32, i32]
+    L.dcgru_debug_bulk_dp_workspace.restype = sz
+    L.dcgru_debug_bulk_dp.argtypes = [i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, sz, vp]
     L.dcgru_timing_enable.argtypes = [C.c_int]
     L.dcgru_timing_collect.argtypes = [C.c_char_p, sz]
     for name in SYMBOLS:
         if name not in ("dcgru_last_error", "dcgru_encoder_layer_bwd_workspace", "dcgru_encoder_layer_fwd_workspace",
                         "dcgru_encoder_layer_gsave_bytes", "dcgru_clip_adam_workspace",
-                        "dcgru_decoder_fwd_workspace", "dcgru_decoder_bwd_workspace"):
+                        "dcgru_decoder_fwd_workspace", "dcgru_decoder_bwd_workspace",
+                        "dcgru_debug_bulk_dp_workspace"):
             getattr(L, name).restype = C.c_int
     _lib = L
     return L

@@ -1,0 +1,381 @@
+// Bulk "diffuse, then project" on the tensor cores (tcgen05, 2xFP16) for every (tile, step) of a layer at once:
+//     out[t][b][n][:] = ( sum_m  (P_m z_t)[n][:] @ W_m ) * scale + bias          z_t = src[t][b] (N x Cin, fp32)
+// The two non-recurrent contractions of a DCGRU layer are instances of it:
+//   * x-part pre-projection (model/cell.py:73-116 restricted to the input columns, legal for the whole
+//     sequence because a layer's input exists up front, model/model.py:98):  z = x_t, W = [Wg_x | Wc_x] (N = 3H),
+//     + biases.  The recurrent kernel (rnn_fwd.cu) starts every step from this pre-activation.  The diffused operand
+//     tiles are also dumped to the operand image (columns [0, KXP)) for the weight-gradient GEMM.
+//   * input gradient dX (BPTT of the same columns):  z = [dA_r | dA_u | dA_c]_t, P_m -> P_m^T, W = W_x^T (N = Fin).
+// Work item = (tile of 4 samples, t); a persistent CTA owns a contiguous range of items (so the tile's polynomials
+// are reloaded only when the tile changes).  Per item the K dimension is cut into chunks of 64 (f16_common.cuh); the
+// K order is term-major, kk = m * Cin + c, so a chunk is a column range of at most two terms.
+//   warps 0-7  workers: one warp per (sample, chunk) task -- fp32 diffusion, hi/lo split, write the A chunk
+//                       (3-slot ring); afterwards the epilogue of the PREVIOUS item (TMEM -> bias/scale -> global),
+//                       so the MMAs of an item have a whole item's worth of diffusion time to finish
+//   warp 8     MMA issuer (one thread): per chunk 3 x 4 kind::f16 MMAs into one of two TMEM accumulators
+//   warp 9     loader (one thread): source tile (one bulk copy per sample) and the weight pieces (hi / lo plane of
+//                       a chunk, pre-swizzled by pack_w16_kernel) from L2 into a ring, cp.async.bulk + mbarrier
+//   warp 10    operand-image dump: one 2-D tensor-map TMA store per (plane, sample) and chunk
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "dw.cuh"
+#include "f16_common.cuh"
+#include "tmap.cuh"
+
+namespace dcgru {
+using namespace f16;
+
+constexpr int BK_NS = 3;                  // A chunk slots
+constexpr int BK_MAXQ = 16;               // chunks per item (M * Cin <= 1024)
+constexpr int BK_THREADS = 352;
+constexpr int BK_NWORK = 256;
+
+struct BulkParams {
+    int B, T, N, Cin, M, Nout, transposeP;
+    int ntile, item0_stride;              // items = ntile * T, split evenly over the grid
+    int NQ, NW, piece_bytes;
+    const float* src; long long ss_t, ss_b;
+    const float* P;
+    const uint8_t* wimg;
+    const float* bias;
+    float* out; long long os_t, os_b; int out_ld;
+    float out_scale;
+    const float* scale_ptr;               // optional device scalar: out *= 1 / *scale_ptr (gradient scaling, rnn_bwd.cu)
+    int dump, img_col0;
+    int off_w, off_x, off_pt, off_id;     // shared-memory offsets
+};
+
+__device__ __forceinline__ void named_bar_workers() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+
+__global__ void __launch_bounds__(BK_THREADS, 1) bulk_dp_kernel(const BulkParams p, const __grid_constant__ CUtensorMap tm_img) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ uint64_t bar_afull[BK_MAXQ], bar_aempty[BK_NS], bar_stored[BK_NS], bar_wfull[8], bar_wempty[8];
+    __shared__ uint64_t bar_xfull, bar_xfree, bar_accfull[2], bar_accfree[2];
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = p.N, Cin = p.Cin, M = p.M, NQ = p.NQ, NW = p.NW;
+    const long nitems = (long)p.ntile * p.T;
+    const long it0 = nitems * blockIdx.x / gridDim.x, it1 = nitems * (blockIdx.x + 1) / gridDim.x;
+    const int nloc = (int)(it1 - it0);
+    uint8_t* Aslots = smem;
+    uint8_t* Wring = smem + p.off_w;
+    float* XT = reinterpret_cast<float*>(smem + p.off_x);
+    float* PTs = reinterpret_cast<float*>(smem + p.off_pt);
+    float* PTid = reinterpret_cast<float*>(smem + p.off_id);
+    const int srow = N * Cin;                                   // floats per sample of the source tile
+
+    if (warp == 0) tmem_alloc<512>(&tmem_slot);
+    if (tid == 0) {
+        for (int i = 0; i < BK_MAXQ; ++i) mbar_init(&bar_afull[i], SB);
+        for (int i = 0; i < BK_NS; ++i) { mbar_init(&bar_aempty[i], 1); mbar_init(&bar_stored[i], 1); }
+        for (int i = 0; i < 8; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], 1); }
+        mbar_init(&bar_xfull, 1);
+        mbar_init(&bar_xfree, BK_NWORK / 32);
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_accfull[i], 1); mbar_init(&bar_accfree[i], BK_NWORK / 32); }
+        mbar_fence_init();
+    }
+    // chunk slots, source tile and polynomial blocks start as zeros: pad rows / pad nodes are never written again
+    for (int i = tid; i < BK_NS * SLOT / 16; i += BK_THREADS) reinterpret_cast<uint4*>(Aslots)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < SB * srow; i += BK_THREADS) XT[i] = 0.f;
+    for (int i = tid; i < SB * (M - 1) * PT_STRIDE; i += BK_THREADS) PTs[i] = 0.f;
+    for (int i = tid; i < PT_STRIDE; i += BK_THREADS) PTid[i] = (i / NPAD == i % NPAD) ? 1.f : 0.f;
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t taddr = tmem_slot;
+
+    if (warp == 8) {
+        // =================================== MMA issuer =================================================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_f16(128, p.Nout);
+            const uint32_t a_base = smem_u32(Aslots), w_base = smem_u32(Wring);
+            unsigned pc = 0;                                    // weight piece counter (2 per chunk)
+            for (int k = 0; k < nloc; ++k) {
+                const int acc_i = k & 1;
+                if (k >= 2) mbar_wait(&bar_accfree[acc_i], ((k >> 1) - 1) & 1);
+                const uint32_t d = taddr + acc_i * 256;
+                for (int q = 0; q < NQ; ++q) {
+                    const unsigned g = (unsigned)k * NQ + q;
+                    const int slot = g % BK_NS;
+                    const uint32_t ah = a_base + slot * SLOT, al = ah + PLANE;
+                    const int ws0 = pc % NW, ws1 = (pc + 1) % NW;
+                    mbar_wait2(&bar_afull[q], k & 1, &bar_wfull[ws0], (pc / NW) & 1);
+                    tc_fence_after();
+                    const uint32_t bh = w_base + ws0 * p.piece_bytes;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        umma_f16(d, make_desc_k128(al + 32 * ks), make_desc_k128(bh + 32 * ks), idesc, (q | ks) ? 1u : 0u);
+                        umma_f16(d, make_desc_k128(ah + 32 * ks), make_desc_k128(bh + 32 * ks), idesc, 1u);
+                    }
+                    umma_commit(&bar_wempty[ws0]);
+                    mbar_wait(&bar_wfull[ws1], ((pc + 1) / NW) & 1);
+                    tc_fence_after();
+                    const uint32_t bl = w_base + ws1 * p.piece_bytes;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_f16(d, make_desc_k128(ah + 32 * ks), make_desc_k128(bl + 32 * ks), idesc, 1u);
+                    umma_commit(&bar_wempty[ws1]);
+                    umma_commit(&bar_aempty[slot]);
+                    pc += 2;
+                }
+                umma_commit(&bar_accfull[acc_i]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 9) {
+        // =================================== loader ======================================================================
+        if (lane == 0) {
+            unsigned pc = 0;
+            for (int k = 0; k < nloc; ++k) {
+                const long it = it0 + k;
+                const int tile = (int)(it / p.T), t = (int)(it - (long)tile * p.T);
+                if (k >= 1) mbar_wait(&bar_xfree, (k - 1) & 1);
+                int nvalid = p.B - tile * SB; if (nvalid > SB) nvalid = SB;
+                mbar_expect_tx(&bar_xfull, (uint32_t)(nvalid * srow * 4));
+                for (int s = 0; s < nvalid; ++s)
+                    bulk_g2s(XT + s * srow, p.src + (size_t)t * p.ss_t + (size_t)(tile * SB + s) * p.ss_b, (uint32_t)(srow * 4), &bar_xfull);
+                for (int q = 0; q < 2 * NQ; ++q, ++pc) {
+                    const int ws = pc % NW;
+                    if (pc >= (unsigned)NW) mbar_wait(&bar_wempty[ws], ((pc / NW) - 1) & 1);
+                    mbar_expect_tx(&bar_wfull[ws], (uint32_t)p.piece_bytes);
+                    bulk_g2s(Wring + ws * p.piece_bytes, p.wimg + (size_t)q * p.piece_bytes, (uint32_t)p.piece_bytes, &bar_wfull[ws]);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 10) {
+        // =================================== operand-image dump ==========================================================
+        if (p.dump) {
+            const int plane = lane >> 2, s = lane & 3;
+            if (lane == 0) tma_prefetch_desc(&tm_img);
+            for (int k = 0; k < nloc; ++k) {
+                const long it = it0 + k;
+                for (int q = 0; q < NQ; ++q) {
+                    const unsigned g = (unsigned)k * NQ + q;
+                    const int slot = g % BK_NS;
+                    mbar_wait(&bar_afull[q], k & 1);
+                    if (lane < 2 * SB) {
+                        tma_store_2d(&tm_img, p.img_col0 + 64 * q, (int)((it * 2 + plane) * IMG_ROWS + s * (RG * 8)),
+                                     Aslots + slot * SLOT + plane * PLANE + s * (RP * 128));
+                        bulk_commit();
+                    }
+                    bulk_wait_read();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_stored[slot]);
+                }
+            }
+            bulk_wait_all();
+        }
+        __syncwarp();
+    } else {
+        // =================================== workers =====================================================================
+        const int row = 32 * (warp & 3) + lane, half = warp >> 2;
+        const int es = row >> 5, en = row & 31;                 // epilogue: sample / node of this thread's row
+        const int ncol = p.Nout / 2;                            // columns per thread in the epilogue
+        float oscale = p.out_scale;
+        if (p.scale_ptr) oscale *= 1.f / __ldg(p.scale_ptr);
+        auto epilogue = [&](int k) {
+            const long it = it0 + k;
+            const int tile = (int)(it / p.T), t = (int)(it - (long)tile * p.T);
+            const int acc_i = k & 1;
+            mbar_wait(&bar_accfull[acc_i], (k >> 1) & 1);
+            tc_fence_after();
+            const int b = tile * SB + es;
+            const bool valid = en < N && b < p.B;
+            float* orow = p.out + (size_t)t * p.os_t + (size_t)(valid ? b : 0) * p.os_b + (size_t)(valid ? en : 0) * p.out_ld + half * ncol;
+            const uint32_t tb = taddr + ((uint32_t)(32 * (warp & 3)) << 16) + acc_i * 256 + half * ncol;
+            for (int cb = 0; cb < ncol; cb += 32) {
+                float v[32];
+                tmem_ld32(tb + cb, v);
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o;
+                        const int c = half * ncol + cb + j;
+                        o.x = v[j] * oscale; o.y = v[j + 1] * oscale; o.z = v[j + 2] * oscale; o.w = v[j + 3] * oscale;
+                        if (p.bias) { o.x += __ldg(p.bias + c); o.y += __ldg(p.bias + c + 1); o.z += __ldg(p.bias + c + 2); o.w += __ldg(p.bias + c + 3); }
+                        *reinterpret_cast<float4*>(orow + cb + j) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_accfree[acc_i]);
+        };
+        int cur_tile = -1;
+        const int kkmax = M * Cin;
+        for (int k = 0; k < nloc; ++k) {
+            const long it = it0 + k;
+            const int tile = (int)(it / p.T);
+            if (tile != cur_tile) {                             // (every worker is past the tasks of the previous item)
+                named_bar_workers();
+                load_pt(PTs, p.P, tile * SB, p.B, N, M - 1, p.transposeP, tid, BK_NWORK);
+                named_bar_workers();
+                cur_tile = tile;
+            }
+            mbar_wait(&bar_xfull, k & 1);
+            // fewer chunks than slots: nothing else keeps this item's tasks from completing a chunk barrier a second
+            // time before the issuer has seen the first completion -> wait for the previous item's MMAs here
+            if (NQ < BK_NS && k >= 1) mbar_wait(&bar_accfull[(k - 1) & 1], ((k - 1) >> 1) & 1);
+            for (int tt = warp; tt < SB * NQ; tt += BK_NWORK / 32) {
+                const int q = tt / SB, s = tt - q * SB;
+                const unsigned g = (unsigned)k * NQ + q;
+                const int slot = g % BK_NS;
+                const unsigned use = g / BK_NS;
+                if (use >= 1) {
+                    if (p.dump) mbar_wait2(&bar_aempty[slot], (use - 1) & 1, &bar_stored[slot], (use - 1) & 1);
+                    else mbar_wait(&bar_aempty[slot], (use - 1) & 1);
+                }
+                uint8_t* sl = Aslots + slot * SLOT;
+                const int kk = 64 * q + 2 * lane;
+                const bool kvalid = kk < kkmax && (tile * SB + s) < p.B;
+                int m = 0, c = 0;
+                if (kvalid) { m = kk / Cin; c = kk - m * Cin; }
+                const float* z = XT + s * srow + c;
+                float acc[NPAD][2];
+                if (__all_sync(0xffffffffu, m == 0)) {          // identity term (or padding): plain copy
+#pragma unroll
+                    for (int n = 0; n < NPAD; ++n) {
+                        float2 zz = make_float2(0.f, 0.f);
+                        if (kvalid && n < N) zz = *reinterpret_cast<const float2*>(z + n * Cin);
+                        acc[n][0] = zz.x; acc[n][1] = zz.y;
+                    }
+                } else {
+                    const float* pt = (m == 0) ? PTid : PTs + (s * (M - 1) + (m - 1)) * PT_STRIDE;
+                    diffuse2(z, Cin, N, pt, acc);
+                    if (!kvalid) {
+#pragma unroll
+                        for (int n = 0; n < NPAD; ++n) { acc[n][0] = 0.f; acc[n][1] = 0.f; }
+                    }
+                }
+                store_cols2(sl, s * RP, lane, N, acc, 1.f);
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_afull[q]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_xfree);
+            if (k >= 1) epilogue(k - 1);
+        }
+        if (nloc > 0) epilogue(nloc - 1);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(taddr);
+}
+
+// ---- weight images ----------------------------------------------------------------------------------------------------
+// piece (chunk q, plane) = [nrows][64 k] fp16 in the K-major SWIZZLE_128B byte order, so a plain bulk copy drops it into
+// shared memory ready for the tensor core.  The value of (output row n, kk = 64 q + k) depends on the GEMM:
+//   mode 0  x pre-projection   kk = m*fin + c;  n < 2H: Wg[(c*M+m)][n], else Wc[(c*M+m)][n-2H]                 nrows = 3H
+//   mode 1  dX                 kk = m*3H + o;   n = input column c:  o < 2H ? Wg[(n*M+m)][o] : Wc[(n*M+m)][o-2H]   nrows = fin
+//   mode 2  gate, h part       kk = m*H + c;    Wg[((fin+c)*M+m)][n]                                            nrows = 2H
+//   mode 3  candidate, h part  kk = m*H + c;    Wc[((fin+c)*M+m)][n]                                            nrows = H
+//   mode 4  BPTT B1 (d(rh))    kk = m*H + o;    n = hidden column c:  Wc[((fin+n)*M+m)][o]                      nrows = H
+//   mode 5  BPTT B2 (dh)       kk = (2m+g)*H + o (g = 0: r, 1: u);  Wg[((fin+n)*M+m)][g*H + o]                  nrows = H
+__global__ void pack_w16_kernel(const float* Wg, const float* Wc, int fin, int H, int M, int mode, int nrows, int nq, uint8_t* img) {
+    const int q = blockIdx.x;
+    const size_t piece = (size_t)nrows * 128;
+    uint8_t* hi = img + (size_t)(2 * q) * piece;
+    uint8_t* lo = hi + piece;
+    const int H2 = 2 * H, H3 = 3 * H;
+    for (int idx = threadIdx.x; idx < nrows * 64; idx += blockDim.x) {
+        const int n = idx >> 6, k = idx & 63, kk = 64 * q + k;
+        float w = 0.f;
+        if (mode == 0) {
+            if (kk < M * fin) { const int m = kk / fin, c = kk - m * fin; const size_t r = (size_t)c * M + m;
+                                w = n < H2 ? Wg[r * H2 + n] : Wc[r * H + (n - H2)]; }
+        } else if (mode == 1) {
+            if (kk < M * H3) { const int m = kk / H3, o = kk - m * H3; const size_t r = (size_t)n * M + m;
+                               w = o < H2 ? Wg[r * H2 + o] : Wc[r * H + (o - H2)]; }
+        } else if (mode == 2 || mode == 3) {
+            if (kk < M * H) { const int m = kk / H, c = kk - m * H; const size_t r = (size_t)(fin + c) * M + m;
+                              w = mode == 2 ? Wg[r * H2 + n] : Wc[r * H + n]; }
+        } else if (mode == 4) {
+            if (kk < M * H) { const int m = kk / H, o = kk - m * H; w = Wc[((size_t)(fin + n) * M + m) * H + o]; }
+        } else {
+            if (kk < 2 * M * H) { const int mg = kk / H, o = kk - mg * H, m = mg >> 1, g = mg & 1;
+                                  w = Wg[((size_t)(fin + n) * M + m) * H2 + g * H + o]; }
+        }
+        __half h, l;
+        split1(w, h, l);
+        const uint32_t off = k128_off(n, k);
+        *reinterpret_cast<__half*>(hi + off) = h;
+        *reinterpret_cast<__half*>(lo + off) = l;
+    }
+}
+
+cudaError_t launch_pack_w16(const float* Wg, const float* Wc, int fin, int H, int M, int mode, int nrows, int nq,
+                            void* img, cudaStream_t st) {
+    pack_w16_kernel<<<nq, 256, 0, st>>>(Wg, Wc, fin, H, M, mode, nrows, nq, reinterpret_cast<uint8_t*>(img));
+    return cudaGetLastError();
+}
+
+// ---- geometry shared with rnn_fwd.cu / rnn_bwd.cu / dw_mm16.cu ----------------------------------------------------------
+int g16_nq(int cin, int M) { return (M * cin + 63) / 64; }
+int g16_kxp(int fin, int M) { return g16_nq(fin, M) * 64; }
+int g16_kkp(int fin, int H, int M) { return g16_kxp(fin, M) + 2 * M * H; }
+int g16_ntile(int B) { return (B + SB - 1) / SB; }
+size_t g16_image_bytes(int B, int T, int cols) { return (size_t)g16_ntile(B) * T * 2 * IMG_ROWS * cols * 2; }
+size_t bulk_wimg_bytes(int cin, int M, int nout) { return (size_t)g16_nq(cin, M) * 2 * nout * 128; }
+
+static bool bulk_layout(int N, int Cin, int M, int Nout, int smem_limit, BulkParams* p) {
+    p->piece_bytes = Nout * 128;
+    const int xbytes = ((SB * N * Cin * 4 + 1023) / 1024) * 1024;
+    const int ptbytes = ((SB * (M - 1) * PT_STRIDE * 4 + 15) / 16) * 16;
+    for (int nw = 8; nw >= 2; --nw) {
+        int off = BK_NS * SLOT;
+        p->off_w = off; off += ((nw * p->piece_bytes + 1023) / 1024) * 1024;
+        p->off_x = off; off += xbytes;
+        p->off_pt = off; off += ptbytes;
+        p->off_id = off; off += PT_STRIDE * 4;
+        if (off + 1024 + 1024 <= smem_limit) { p->NW = nw; return true; }      // + alignment slack + static shared memory
+    }
+    return false;
+}
+static int bulk_smem(const BulkParams& p) { return p.off_id + PT_STRIDE * 4 + 1024; }
+
+bool bulk_dp_supported(int N, int Cin, int M, int Nout, int smem_limit) {
+    BulkParams p;
+    if (N > NPAD || Cin % 4 || (N * Cin) % 4 || M < 1 || g16_nq(Cin, M) > BK_MAXQ) return false;
+    if (Nout != 64 && Nout != 192) return false;
+    return bulk_layout(N, Cin, M, Nout, smem_limit, &p);
+}
+
+// out (+)= ... see the header comment.  img: operand image base or nullptr; img_cols: floats.. fp16 values per image row
+cudaError_t launch_bulk_dp(int B, int T, int N, int Cin, int M, int Nout, int transposeP, const float* src, long long ss_t,
+                           long long ss_b, const float* P, const void* wimg, const float* bias, float* out, long long os_t,
+                           long long os_b, int out_ld, float out_scale, const float* scale_ptr, void* img, int img_cols,
+                           int img_col0, int nsms, int smem_limit, cudaStream_t st) {
+    BulkParams p;
+    memset(&p, 0, sizeof p);
+    if (!bulk_layout(N, Cin, M, Nout, smem_limit, &p)) return cudaErrorInvalidConfiguration;
+    p.B = B; p.T = T; p.N = N; p.Cin = Cin; p.M = M; p.Nout = Nout; p.transposeP = transposeP;
+    p.ntile = g16_ntile(B); p.NQ = g16_nq(Cin, M);
+    p.src = src; p.ss_t = ss_t; p.ss_b = ss_b; p.P = P; p.wimg = reinterpret_cast<const uint8_t*>(wimg); p.bias = bias;
+    p.out = out; p.os_t = os_t; p.os_b = os_b; p.out_ld = out_ld; p.out_scale = out_scale; p.scale_ptr = scale_ptr;
+    p.dump = img != nullptr; p.img_col0 = img_col0;
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof tm);
+    if (img) {
+        // 2-D view of the fp16 image [rows][img_cols]; box = 64 columns (128 bytes) x the 24 rows of one sample
+        const unsigned long long dims[2] = {(unsigned long long)img_cols, (unsigned long long)p.ntile * T * 2 * IMG_ROWS};
+        const unsigned long long str[2] = {2, (unsigned long long)img_cols * 2};
+        const unsigned box[2] = {64, RG * 8};
+        cudaError_t e = make_tmap(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, img, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (e != cudaSuccess) return e;
+    }
+    const int smem = bulk_smem(p);
+    cudaError_t e = cudaFuncSetAttribute(bulk_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    long nitems = (long)p.ntile * T;
+    int grid = nsms < nitems ? nsms : (int)nitems;
+    bulk_dp_kernel<<<grid, BK_THREADS, smem, st>>>(p, tm);
+    return cudaGetLastError();
+}
+
+}  // namespace dcgru

@@ -560,6 +560,30 @@ int dcgru_encoder_layer_bwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
     return 0;
 }
 
+// ---- second-generation kernels: stage-level debug entry points (tests/test_gpu_g2.py) ---------------------------------
+size_t dcgru_debug_bulk_dp_workspace(int32_t mode, int32_t fin, int32_t H, int32_t M) {
+    return align_up(mode == 0 ? bulk_wimg_bytes(fin, M, 3 * H) : bulk_wimg_bytes(3 * H, M, fin));
+}
+
+int dcgru_debug_bulk_dp(int32_t mode, int32_t B, int32_t T, int32_t N, int32_t fin, int32_t H, int32_t M, const float* src,
+                        const float* P, const float* Wg, const float* Wc, const float* bias, float* out, void* img,
+                        int32_t img_cols, int32_t img_col0, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!src || !Wg || !Wc || !out || !workspace) return fail("null pointer");
+    if (M > 1 && !P) return fail("null P");
+    if (H != 64) return fail("hid_dim=%d unsupported by the 2xFP16 kernels", H);
+    const int Cin = mode == 0 ? fin : 3 * H, Nout = mode == 0 ? 3 * H : fin;
+    const DevInfo& di = devinfo();
+    if (!bulk_dp_supported(N, Cin, M, Nout, di.smem)) return fail("bulk_dp: unsupported shape (N=%d Cin=%d M=%d Nout=%d)", N, Cin, M, Nout);
+    if (workspace_bytes < dcgru_debug_bulk_dp_workspace(mode, fin, H, M)) return fail("workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    LAUNCH("pack_w16", launch_pack_w16(Wg, Wc, fin, H, M, mode == 0 ? 0 : 1, Nout, g16_nq(Cin, M), workspace, st));
+    LAUNCH(mode == 0 ? "xproj" : "dx16",
+           launch_bulk_dp(B, T, N, Cin, M, Nout, mode == 0 ? 0 : 1, src, (long long)B * N * Cin, (long long)N * Cin, P, workspace,
+                          bias, out, (long long)B * N * Nout, (long long)N * Nout, Nout, 1.f, nullptr, img, img_cols, img_col0,
+                          di.sms, di.smem, st));
+    return 0;
+}
+
 // ---- fused optimiser step -------------------------------------------------------------------------------
 size_t dcgru_clip_adam_workspace(size_t n) { return align_up((size_t)clip_adam_npart(n) * 8); }
 

@@ -108,4 +108,19 @@ cudaError_t launch_tc_selftest(const float* A, const float* B, float* C, int N, 
 cudaError_t launch_tc_probe(const float* Aimg, int a_bytes, const float* Bimg, int b_bytes, uint32_t a_lbo, uint32_t a_sbo,
                             uint32_t b_lbo, uint32_t b_sbo, uint32_t idesc, uint32_t a_type, uint32_t b_type, float* D, int N,
                             cudaStream_t st);
+// ---- second-generation tensor-core kernels (2xFP16, f16_common.cuh) ----------------------------------------------------
+int g16_nq(int cin, int M);
+int g16_kxp(int fin, int M);
+int g16_kkp(int fin, int H, int M);
+int g16_ntile(int B);
+size_t g16_image_bytes(int B, int T, int cols);
+size_t bulk_wimg_bytes(int cin, int M, int nout);
+bool bulk_dp_supported(int N, int Cin, int M, int Nout, int smem_limit);
+cudaError_t launch_pack_w16(const float* Wg, const float* Wc, int fin, int H, int M, int mode, int nrows, int nq,
+                            void* img, cudaStream_t st);
+cudaError_t launch_bulk_dp(int B, int T, int N, int Cin, int M, int Nout, int transposeP, const float* src, long long ss_t,
+                           long long ss_b, const float* P, const void* wimg, const float* bias, float* out, long long os_t,
+                           long long os_b, int out_ld, float out_scale, const float* scale_ptr, void* img, int img_cols,
+                           int img_col0, int nsms, int smem_limit, cudaStream_t st);
+
 }  // namespace dcgru

@@ -1,0 +1,158 @@
+// Building blocks of the second-generation tensor-core kernels (bulk_dp.cu, rnn_fwd.cu, rnn_bwd.cu, dw_mm16.cu).
+//
+// Arithmetic: "2xFP16" -- every fp32 operand x is split into hi = fp16(x) (round to nearest) and lo = fp16(x - hi);
+// hi + lo carries 22 significand bits (fp16 has 11), and a product a*b is issued as three kind::f16 MMAs
+//     a_lo*b_hi + a_hi*b_lo + a_hi*b_hi
+// whose fp16 x fp16 products are exact in the fp32 accumulator (TMEM).  The dropped a_lo*b_lo term is 2^-22 relative:
+// the same accuracy class as the 3xTF32 scheme of the first-generation kernels (tc_common.cuh), at twice the tensor
+// rate (kind::f16 has K = 16 per instruction, kind::tf32 K = 8) and half the operand bytes in shared memory and HBM.
+// Range: fp16 holds |x| < 65504 and resolves down to 6e-8.  Forward operands (standardised inputs, gates in (0,1),
+// tanh states, Xavier weights, diffusion polynomials) sit far inside; the backward kernels multiply the gradient
+// by a power of two chosen from the upstream gradient's magnitude before the split and undo it after the
+// accumulator is read (exact), see rnn_bwd.cu.
+//
+// Operand tiles ("chunks"): 64 K-values (128 bytes) per row, canonical K-major SWIZZLE_128B layout
+//     byte(row r, k) = (r / 8) * 1024 + (r % 8) * 128 + (((k / 8) ^ (r % 8)) * 16) + (k % 8) * 2
+// i.e. exactly what a TMA box with a 128-byte inner extent and CU_TENSOR_MAP_SWIZZLE_128B reads / writes, so the
+// same bytes serve as UMMA operand and as source of the operand-image dumps.  One MMA k-step (16 values) is a
+// 32-byte advance of the descriptor's start address.  A chunk slot = hi plane (16 KB for 128 rows) + lo plane.
+//
+// Diffusion: P_m (19 x 19 per sample) is applied by the worker warps with fp32 FMAs, one warp per (sample, chunk):
+// lane = two adjacent source columns, registers = the 19 (padded 20) output rows; the rows of P^T are broadcast
+// reads from shared memory.  Every lane is busy whatever the node count (the first generation mapped lane = row
+// and idled 13 of 32 lanes), and the whole phase is one barrier round instead of one per 8-column chunk.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tc_common.cuh"
+
+namespace dcgru {
+namespace f16 {
+using namespace tc;
+
+constexpr int SB = 4;                 // samples per 128-row tile
+constexpr int RP = 32;                // rows per sample (nodes 0..N-1, rest zero)
+constexpr int RG = 3;                 // 8-row groups of a sample that can be non-zero (N <= 24)
+constexpr int IMG_ROWS = SB * RG * 8; // 96 image rows per (tile, t, plane)
+constexpr int NPAD = 20;              // node count the FMA loops are unrolled for
+constexpr int PLANE = 16 * 1024;      // one plane (hi or lo) of a 128-row chunk
+constexpr int SLOT = 2 * PLANE;       // chunk slot: hi | lo
+constexpr int PT_STRIDE = NPAD * NPAD;   // floats per (sample, term) block of transposed polynomials
+
+// kind::f16 (A, B = fp16), fp32 accumulate, both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// both operands MN-major (dw_mm16: the GEMM's K index is the image row)
+__host__ __device__ constexpr uint32_t make_idesc_f16_mn(int M, int N) {
+    return make_idesc_f16(M, N) | (1u << 15) | (1u << 16);
+}
+// K-major SWIZZLE_128B operand: 8-row atoms of 1024 bytes, next atom SBO = 1024 further (dense)
+__device__ __forceinline__ uint64_t make_desc_k128(uint32_t saddr) {
+    return make_smem_desc(saddr, 16, 1024) | ((uint64_t)2 << 61);
+}
+// MN-major SWIZZLE_128B operand: rows of 64 mn values (128 B), 8 k-rows = one 1024-byte atom; next 8 k-rows SBO
+// further, next 64 mn values LBO further
+__device__ __forceinline__ uint64_t make_desc_mn128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return make_smem_desc(saddr, lbo_bytes, sbo_bytes) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// byte offset of (row, k) inside one plane of a chunk (k in [0, 64))
+__device__ __forceinline__ uint32_t k128_off(int row, int k) {
+    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ (row & 7)) << 4) | ((k & 7) << 1)));
+}
+
+// ---- fp32 -> (hi, lo) fp16 pairs ----------------------------------------------------------------------------------
+__device__ __forceinline__ float clamp_h(float x) { return fminf(fmaxf(x, -65000.f), 65000.f); }
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    a = clamp_h(a); b = clamp_h(b);
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// host + device scalar version (weight packing)
+__device__ __forceinline__ void split1(float a, __half& hi, __half& lo) {
+    a = clamp_h(a);
+    hi = __float2half_rn(a);
+    lo = __float2half_rn(a - __half2float(hi));
+}
+// 8 consecutive k of one row (one 16-byte swizzle unit) from 8 floats
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+    split2(v[0], v[1], hi.x, lo.x); split2(v[2], v[3], hi.y, lo.y);
+    split2(v[4], v[5], hi.z, lo.z); split2(v[6], v[7], hi.w, lo.w);
+}
+
+// ---- diffusion of two columns by one lane -------------------------------------------------------------------------
+// acc[n][0..1] = sum_{j < N} PT[j][n] * z[j][0..1];  z points at (node row 0, this lane's first column) of an fp32
+// shared-memory tile with row stride zld floats; PT = this lane's [j][NPAD] block (rows of P^T, zero beyond N).
+__device__ __forceinline__ void diffuse2(const float* z, int zld, int N, const float* PT, float (&acc)[NPAD][2]) {
+#pragma unroll
+    for (int n = 0; n < NPAD; ++n) { acc[n][0] = 0.f; acc[n][1] = 0.f; }
+#pragma unroll 1
+    for (int j = 0; j < N; ++j) {
+        const float2 zz = *reinterpret_cast<const float2*>(z + j * zld);
+        const float4* pr = reinterpret_cast<const float4*>(PT + j * NPAD);
+#pragma unroll
+        for (int q = 0; q < NPAD / 4; ++q) {
+            const float4 pv = pr[q];
+            acc[4 * q + 0][0] = fmaf(pv.x, zz.x, acc[4 * q + 0][0]); acc[4 * q + 0][1] = fmaf(pv.x, zz.y, acc[4 * q + 0][1]);
+            acc[4 * q + 1][0] = fmaf(pv.y, zz.x, acc[4 * q + 1][0]); acc[4 * q + 1][1] = fmaf(pv.y, zz.y, acc[4 * q + 1][1]);
+            acc[4 * q + 2][0] = fmaf(pv.z, zz.x, acc[4 * q + 2][0]); acc[4 * q + 2][1] = fmaf(pv.z, zz.y, acc[4 * q + 2][1]);
+            acc[4 * q + 3][0] = fmaf(pv.w, zz.x, acc[4 * q + 3][0]); acc[4 * q + 3][1] = fmaf(pv.w, zz.y, acc[4 * q + 3][1]);
+        }
+    }
+}
+// rows n < N of acc -> chunk slot (hi plane at `slot`, lo plane PLANE further), tile row = row0 + n, k = 2 * lane
+__device__ __forceinline__ void store_cols2(uint8_t* slot, int row0, int lane, int N, const float (&acc)[NPAD][2], float scale) {
+#pragma unroll
+    for (int n = 0; n < NPAD; ++n) {
+        if (n < N) {
+            uint32_t hi, lo;
+            split2(acc[n][0] * scale, acc[n][1] * scale, hi, lo);
+            const uint32_t off = k128_off(row0 + n, 2 * lane);
+            *reinterpret_cast<uint32_t*>(slot + off) = hi;
+            *reinterpret_cast<uint32_t*>(slot + PLANE + off) = lo;
+        }
+    }
+}
+
+// transposed polynomials of one tile into shared memory: PT[(s * nterm + m) * PT_STRIDE + j * NPAD + n]
+//   forward  (transpose = 0): PT[j][n] = P[b][m][n][j]   (out[n] = sum_j P[n][j] z[j])
+//   backward (transpose = 1): PT[j][n] = P[b][m][j][n]   (out[n] = sum_j P[j][n] z[j] = (P^T z)[n])
+// Entries beyond N stay zero (the caller zeroes the block once).  Called by `nthreads` threads with index `tid`.
+__device__ __forceinline__ void load_pt(float* PTs, const float* P, int b0, int B, int N, int nterm, int transpose,
+                                        int tid, int nthreads) {
+    const int per = nterm * N * N;
+    for (int idx = tid; idx < SB * per; idx += nthreads) {
+        const int s = idx / per, r = idx - s * per;
+        const int m = r / (N * N), e = r - m * N * N;
+        const int a = e / N, c = e - a * N;                 // P[b][m][a][c]
+        const int b = b0 + s;
+        float v = 0.f;
+        if (b < B) v = P[((size_t)b * nterm + m) * N * N + e];
+        const int j = transpose ? a : c, n = transpose ? c : a;
+        PTs[(s * nterm + m) * PT_STRIDE + j * NPAD + n] = v;
+    }
+}
+
+// global (2-D box) <- shared, tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void tma_store_2d(const void* tmap, int c0, int c1, const void* smem_src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];\n"
+                 ::"l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(smem_src)) : "memory");
+}
+
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+
+}  // namespace f16
+}  // namespace dcgru

@@ -23,13 +23,18 @@ static EncodeTiledFn encode_fn() {
 
 cudaError_t make_tmap_f32(CUtensorMap* out, const void* base, int rank, const unsigned long long* dims,
                           const unsigned long long* strides_bytes, const unsigned* box, CUtensorMapSwizzle swizzle) {
+    return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, swizzle);
+}
+
+cudaError_t make_tmap(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank, const unsigned long long* dims,
+                      const unsigned long long* strides_bytes, const unsigned* box, CUtensorMapSwizzle swizzle) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return cudaErrorNotSupported;
     cuuint64_t gd[5], gs[5];
     cuuint32_t bx[5], es[5];
     for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (int i = 1; i < rank; ++i) gs[i - 1] = strides_bytes[i];
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+    CUresult r = fn(out, dtype, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;

@@ -10,4 +10,8 @@ namespace dcgru {
 cudaError_t make_tmap_f32(CUtensorMap* out, const void* base, int rank, const unsigned long long* dims,
                           const unsigned long long* strides_bytes, const unsigned* box, CUtensorMapSwizzle swizzle);
 
+// same for any element type (fp16 operand images of the second-generation kernels)
+cudaError_t make_tmap(CUtensorMap* out, CUtensorMapDataType dtype, const void* base, int rank, const unsigned long long* dims,
+                      const unsigned long long* strides_bytes, const unsigned* box, CUtensorMapSwizzle swizzle);
+
 }  // namespace dcgru

@@ -337,9 +337,34 @@ int dcgru_corr_supports(int32_t batch, int32_t seq_len, int32_t num_nodes, int32
     return 0;
 }
 
+// second-generation path (2xFP16: bulk_dp.cu + rnn_fwd.cu [+ rnn_bwd.cu + dw_mm16.cu]); DCGRU_G2=0 keeps the 3xTF32 kernels
+static bool g2_enabled() {
+    const char* e = getenv("DCGRU_G2");
+    return tc_enabled() && e && e[0] == '1';
+}
+static bool g2_fwd_supported(const dcgru_cell_desc* d) {
+    const int M = Mof(d);
+    const DevInfo& di = devinfo();
+    return g2_enabled() && rnn_fwd_supported(d->num_nodes, d->hid_dim, M, di.smem) &&
+           bulk_dp_supported(d->num_nodes, d->input_dim, M, 3 * d->hid_dim, di.smem);
+}
+struct G2FwdWs { size_t off_wx, off_wh, off_bias, off_xp, total; };
+static G2FwdWs g2_fwd_ws(const dcgru_cell_desc* d, int B, int T) {
+    G2FwdWs w;
+    const int M = Mof(d);
+    size_t o = 0;
+    w.off_wx = o; o = align_up(o + bulk_wimg_bytes(d->input_dim, M, 3 * d->hid_dim));
+    w.off_wh = o; o = align_up(o + rnn_fwd_wimg_bytes(M));
+    w.off_bias = o; o = align_up(o + (size_t)3 * d->hid_dim * 4);
+    w.off_xp = o; o = align_up(o + (size_t)T * B * d->num_nodes * 3 * d->hid_dim * 4);
+    w.total = o;
+    return w;
+}
+
 // operand image of the tensor-core forward kernel (0: the configuration has no such path)
 static size_t gsave_bytes_for(const dcgru_cell_desc* d, int B, int T) {
     if (!tc_enabled()) return 0;
+    if (g2_fwd_supported(d)) return 0;          // (the second-generation backward is not wired in yet)
     { const char* e = getenv("DCGRU_DISABLE_GSAVE"); if (e && e[0] == '1') return 0; }
     const int M = Mof(d);
     const DevInfo& di = devinfo();
@@ -358,7 +383,9 @@ size_t dcgru_encoder_layer_gsave_bytes(const dcgru_cell_desc* d, int32_t batch, 
 
 size_t dcgru_encoder_layer_fwd_workspace(const dcgru_cell_desc* d, int32_t batch, int32_t seq_len) {
     if (check_desc(d) || batch < 1 || seq_len < 1) return 0;
-    return align_up(seq_fwd_tc_wimg_bytes(d->input_dim)) + 256 + 16384;   // + debug stamps (DCGRU_DBG & 4)
+    size_t n = align_up(seq_fwd_tc_wimg_bytes(d->input_dim)) + 256 + 16384;   // + debug stamps (DCGRU_DBG & 4)
+    if (g2_fwd_supported(d)) { const size_t g = g2_fwd_ws(d, batch, seq_len).total; if (g > n) n = g; }
+    return n;
 }
 
 int dcgru_encoder_layer_fwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq_len, const float* x,
@@ -374,6 +401,25 @@ int dcgru_encoder_layer_fwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
         (x_stride_t % 4) || (x_stride_b % 4))
         return fail("x/h0/h_seq/weights must be 16-byte aligned with strides multiple of 4 floats");
     cudaStream_t st = (cudaStream_t)stream;
+    // second-generation tensor-core path (tcgen05, 2xFP16): hoisted x-part GEMM over all steps, then the recurrence
+    if (g2_fwd_supported(d) && !gsave && workspace && aligned16(workspace) &&
+        workspace_bytes >= g2_fwd_ws(d, batch, seq_len).total) {
+        const G2FwdWs ws = g2_fwd_ws(d, batch, seq_len);
+        const DevInfo& di = devinfo();
+        const int H = d->hid_dim, N = d->num_nodes, fin = d->input_dim;
+        uint8_t* wsb = reinterpret_cast<uint8_t*>(workspace);
+        float* xp = reinterpret_cast<float*>(wsb + ws.off_xp);
+        float* bias = reinterpret_cast<float*>(wsb + ws.off_bias);                       // [bg | bc]
+        CUDA_TRY(cudaMemcpyAsync(bias, w->bg, (size_t)2 * H * 4, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(bias + 2 * H, w->bc, (size_t)H * 4, cudaMemcpyDeviceToDevice, st));
+        LAUNCH("pack_w16", launch_pack_w16(w->Wg, w->Wc, fin, H, M, 0, 3 * H, g16_nq(fin, M), wsb + ws.off_wx, st));
+        LAUNCH("xproj", launch_bulk_dp(batch, seq_len, N, fin, M, 3 * H, 0, x, x_stride_t, x_stride_b, P, wsb + ws.off_wx, bias,
+                                       xp, (long long)batch * N * 3 * H, (long long)N * 3 * H, 3 * H, 1.f, nullptr, nullptr, 0,
+                                       0, di.sms, di.smem, st));
+        LAUNCH("rnn_fwd", launch_rnn_fwd(batch, seq_len, N, fin, M, d->activation, xp, h0, P, w->Wg, w->Wc, wsb + ws.off_wh,
+                                         h_seq, ruc, nullptr, 0, 0, st));
+        return 0;
+    }
     // tensor-core path (tcgen05, 3xTF32): K=2 / one support / 64 units -- the reference's default cell
     if (tc_enabled() && workspace && aligned16(workspace) &&
         workspace_bytes >= align_up(seq_fwd_tc_wimg_bytes(d->input_dim)) + 16384 &&

@@ -123,4 +123,10 @@ cudaError_t launch_bulk_dp(int B, int T, int N, int Cin, int M, int Nout, int tr
                            long long os_b, int out_ld, float out_scale, const float* scale_ptr, void* img, int img_cols,
                            int img_col0, int nsms, int smem_limit, cudaStream_t st);
 
+size_t rnn_fwd_wimg_bytes(int M);
+bool rnn_fwd_supported(int N, int H, int M, int smem_limit);
+cudaError_t launch_rnn_fwd(int B, int T, int N, int fin, int M, int act, const float* xp, const float* h0, const float* P,
+                           const float* Wg, const float* Wc, void* wimg, float* hseq, float* ruc, void* img, int img_cols,
+                           int img_col0, cudaStream_t st);
+
 }  // namespace dcgru

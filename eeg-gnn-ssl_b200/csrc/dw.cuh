@@ -124,6 +124,7 @@ cudaError_t launch_bulk_dp(int B, int T, int N, int Cin, int M, int Nout, int tr
                            int img_col0, int nsms, int smem_limit, cudaStream_t st);
 
 size_t rnn_fwd_wimg_bytes(int M);
+cudaError_t rnn_fwd_read_dbg(long long* out, int n);
 bool rnn_fwd_supported(int N, int H, int M, int smem_limit);
 cudaError_t launch_rnn_fwd(int B, int T, int N, int fin, int M, int act, const float* xp, const float* h0, const float* P,
                            const float* Wg, const float* Wc, void* wimg, float* hseq, float* ruc, void* img, int img_cols,

@@ -95,20 +95,69 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
 // ---- diffusion of two columns by one lane -------------------------------------------------------------------------
 // acc[n][0..1] = sum_{j < N} PT[j][n] * z[j][0..1];  z points at (node row 0, this lane's first column) of an fp32
 // shared-memory tile with row stride zld floats; PT = this lane's [j][NPAD] block (rows of P^T, zero beyond N).
+// The inner product runs on packed fp32 pairs (fma.rn.f32x2 -> FFMA2, sm_100): a register pair holds the outputs of
+// two adjacent nodes (n, n+1) for one column, the P^T pair comes straight out of the 16-byte shared-memory read and the
+// source value is the instruction's broadcast scalar operand -- 20 FFMA2 instead of 40 FFMA per source row.
 __device__ __forceinline__ void diffuse2(const float* z, int zld, int N, const float* PT, float (&acc)[NPAD][2]) {
+    unsigned long long a64[NPAD / 2][2];
 #pragma unroll
-    for (int n = 0; n < NPAD; ++n) { acc[n][0] = 0.f; acc[n][1] = 0.f; }
-#pragma unroll 1
+    for (int i = 0; i < NPAD / 2; ++i) { a64[i][0] = 0ull; a64[i][1] = 0ull; }
+#pragma unroll 2
     for (int j = 0; j < N; ++j) {
         const float2 zz = *reinterpret_cast<const float2*>(z + j * zld);
-        const float4* pr = reinterpret_cast<const float4*>(PT + j * NPAD);
+        unsigned long long zx, zy;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(zx) : "f"(zz.x));
+        asm("mov.b64 %0, {%1, %1};" : "=l"(zy) : "f"(zz.y));
+        const ulonglong2* pr = reinterpret_cast<const ulonglong2*>(PT + j * NPAD);
 #pragma unroll
         for (int q = 0; q < NPAD / 4; ++q) {
-            const float4 pv = pr[q];
-            acc[4 * q + 0][0] = fmaf(pv.x, zz.x, acc[4 * q + 0][0]); acc[4 * q + 0][1] = fmaf(pv.x, zz.y, acc[4 * q + 0][1]);
-            acc[4 * q + 1][0] = fmaf(pv.y, zz.x, acc[4 * q + 1][0]); acc[4 * q + 1][1] = fmaf(pv.y, zz.y, acc[4 * q + 1][1]);
-            acc[4 * q + 2][0] = fmaf(pv.z, zz.x, acc[4 * q + 2][0]); acc[4 * q + 2][1] = fmaf(pv.z, zz.y, acc[4 * q + 2][1]);
-            acc[4 * q + 3][0] = fmaf(pv.w, zz.x, acc[4 * q + 3][0]); acc[4 * q + 3][1] = fmaf(pv.w, zz.y, acc[4 * q + 3][1]);
+            const ulonglong2 pv = pr[q];
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a64[2 * q][0]) : "l"(pv.x), "l"(zx));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a64[2 * q][1]) : "l"(pv.x), "l"(zy));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a64[2 * q + 1][0]) : "l"(pv.y), "l"(zx));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a64[2 * q + 1][1]) : "l"(pv.y), "l"(zy));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NPAD / 2; ++i) {
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[2 * i][0]), "=f"(acc[2 * i + 1][0]) : "l"(a64[i][0]));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[2 * i][1]), "=f"(acc[2 * i + 1][1]) : "l"(a64[i][1]));
+    }
+}
+// one column per lane (32-column half tasks: every warp works on the same term, so a term's chunk is complete -- and its
+// MMAs can start -- while the next term is still being diffused)
+__device__ __forceinline__ void diffuse1(const float* z, int zld, int N, const float* PT, float (&acc)[NPAD]) {
+    unsigned long long a64[NPAD / 2];
+#pragma unroll
+    for (int i = 0; i < NPAD / 2; ++i) a64[i] = 0ull;
+#pragma unroll 2
+    for (int j = 0; j < N; ++j) {
+        const float zv = z[j * zld];
+        unsigned long long zx;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(zx) : "f"(zv));
+        const ulonglong2* pr = reinterpret_cast<const ulonglong2*>(PT + j * NPAD);
+#pragma unroll
+        for (int q = 0; q < NPAD / 4; ++q) {
+            const ulonglong2 pv = pr[q];
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a64[2 * q]) : "l"(pv.x), "l"(zx));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a64[2 * q + 1]) : "l"(pv.y), "l"(zx));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NPAD / 2; ++i)
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[2 * i]), "=f"(acc[2 * i + 1]) : "l"(a64[i]));
+}
+// rows n < N of acc (one column k per lane) -> chunk slot; rows N..nzero-1 are written as zeros
+__device__ __forceinline__ void store_col1(uint8_t* slot, int row0, int k, int N, int nzero, const float (&acc)[NPAD], float scale) {
+#pragma unroll
+    for (int n = 0; n < RG * 8; ++n) {
+        if (n < nzero) {
+            const float v = (n < NPAD && n < N) ? clamp_h(acc[n < NPAD ? n : 0] * scale) : 0.f;
+            const __half h = __float2half_rn(v);
+            const __half l = __float2half_rn(v - __half2float(h));
+            const uint32_t off = k128_off(row0 + n, k);
+            *reinterpret_cast<__half*>(slot + off) = h;
+            *reinterpret_cast<__half*>(slot + PLANE + off) = l;
         }
     }
 }

@@ -36,10 +36,10 @@ constexpr int RF_OFF_A = 0;                         // 3 chunk slots
 constexpr int RF_OFF_W = 3 * SLOT;
 constexpr int RF_OFF_ZH = RF_OFF_W + RF_NW * RF_WSLOT;
 constexpr int RF_OFF_PT = RF_OFF_ZH + 128 * RF_ZLD * 4;
-constexpr int RF_ACC1 = 192, RF_STASH = 384;        // TMEM columns: accumulators at 0 / 192, state stash at 384
+constexpr int RF_ACC1 = 192, RF_STASH = 384, RF_RSTASH = 448;   // TMEM columns: accumulators at 0 / 192, h stash, r stash
 
 struct RnnFwdParams {
-    int B, T, N, M, act, dump, img_col0;
+    int B, T, N, M, act, dump, img_col0, dbg;
     const float* xp;            // (T,B,N,3H)
     const float* h0;            // (B,N*H)
     const float* P;             // (B,M-1,N,N)
@@ -47,6 +47,9 @@ struct RnnFwdParams {
     float* hseq;                // (T,B,N*H)
     float* ruc;                 // (T,B,N,3H) or nullptr
 };
+
+// timing experiment (DCGRU_DBG & 16): clock64 stamps of CTA 0 -- worker thread 0: [t][0..9], issuer: [t][10..15]
+__device__ long long rf_dbg[64 * 16 + 64 * 8];   // + per-step stamps inside the first diffusion term (offset 1024)
 
 __device__ __forceinline__ void rf_worker_bar() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 
@@ -69,8 +72,8 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
     if (warp == 0) tmem_alloc<512>(&tmem_slot);
     if (tid == 0) {
         mbar_init(&bar_afull[0], RF_NWORK / 32);
-        mbar_init(&bar_afull[1], SB);
-        mbar_init(&bar_afull[2], SB);
+        mbar_init(&bar_afull[1], RF_NWORK / 32);
+        mbar_init(&bar_afull[2], RF_NWORK / 32);
         for (int i = 0; i < 3; ++i) { mbar_init(&bar_aempty[i], 1); mbar_init(&bar_stored[i], 1); }
         for (int i = 0; i < RF_NW; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&bar_xpfull[i], 4); mbar_init(&bar_accfree[i], RF_NWORK / 32); }
@@ -98,7 +101,10 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
             for (int t = 0; t < T; ++t) {
                 const int acc_i = t & 1;
                 const uint32_t dacc = taddr + acc_i * RF_ACC1;
+                const bool rec = p.dbg && blockIdx.x == 0 && t < 64;
+                if (rec) rf_dbg[t * 16 + 10] = clock64();
                 mbar_wait(&bar_xpfull[acc_i], (t >> 1) & 1);            // XP_t sits in the accumulator
+                if (rec) rf_dbg[t * 16 + 11] = clock64();
                 for (int ph = 0; ph < 2; ++ph) {
                     const uint32_t d = dacc + (ph ? 2 * RF_H : 0), idesc = ph ? idc : idg;
                     for (int m = 0; m < M; ++m) {
@@ -125,6 +131,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
                         pc += 2;
                     }
                     umma_commit(ph ? &bar_cand : &bar_gate);
+                    if (rec) rf_dbg[t * 16 + 12 + ph] = clock64();
                 }
             }
         }
@@ -256,26 +263,26 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
             if (lane == 0) mbar_arrive(&bar_afull[0]);
             ++fills[0];
         };
-        // diffusion tasks of one phase: term m of sample s -> slot 1 + ((m-1) & 1)
+        // diffusion of one phase: every warp takes (sample quad, column half) of EVERY term m >= 1, in term order, so
+        // chunk m is complete -- and its MMAs run -- while term m+1 is being diffused; slot = 1 + ((m-1) & 1)
+        int dbg_t = 0, dbg_ph = 0;
         auto diffuse_phase = [&]() {
             for (int m = 1; m < M; ++m) {
                 const int slot = 1 + ((m - 1) & 1);
-                const int s = (warp - ((m - 1) * SB)) & 7;
-                if (s < SB) {
-                    acquire(slot, true);
-                    float acc[NPAD][2];
-                    diffuse2(ZH + (s * RP) * RF_ZLD + 2 * lane, RF_ZLD, N, PTs + (s * (M - 1) + (m - 1)) * PT_STRIDE, acc);
-                    uint8_t* sl = Aslots + slot * SLOT;
-                    store_cols2(sl, s * RP, lane, N, acc, 1.f);
-                    for (int n = N; n < RG * 8; ++n) {                  // the dumped pad rows must be zero (staging aliases them)
-                        const uint32_t off = k128_off(s * RP + n, 2 * lane);
-                        *reinterpret_cast<uint32_t*>(sl + off) = 0u;
-                        *reinterpret_cast<uint32_t*>(sl + PLANE + off) = 0u;
-                    }
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&bar_afull[slot]);
-                }
+                const bool rec2 = p.dbg && blockIdx.x == 0 && tid == 0 && m == 1 && dbg_t < 64;
+                long long* ds = rf_dbg + 1024 + dbg_t * 8 + dbg_ph * 4;
+                if (rec2) ds[0] = clock64();
+                acquire(slot, true);
+                if (rec2) ds[1] = clock64();
+                float acc[NPAD];
+                diffuse1(ZH + (quad * RP) * RF_ZLD + half * 32 + lane, RF_ZLD, N, PTs + (quad * (M - 1) + (m - 1)) * PT_STRIDE, acc);
+                // (rows N..23 are dumped to the operand image and aliased by the staging tiles: rewrite them as zeros)
+                if (rec2) ds[2] = clock64();
+                store_col1(Aslots + slot * SLOT, quad * RP, half * 32 + lane, N, RG * 8, acc, 1.f);
+                if (rec2) ds[3] = clock64();
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_afull[slot]);
                 ++fills[slot];
             }
         };
@@ -295,10 +302,16 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
         for (int t = 0; t < T; ++t) {
             const uint32_t dacc = taddr + lane_base + (t & 1) * RF_ACC1;
             float* hout = p.hseq + (size_t)t * p.B * NH;
+            const bool rec = p.dbg && blockIdx.x == 0 && tid == 0 && t < 64;
+            long long* es = rf_dbg + t * 16;
+            if (rec) es[0] = clock64();
             // ---- gate ------------------------------------------------------------------------------------------------
+            dbg_t = t; dbg_ph = 0;
             diffuse_phase();
+            if (rec) es[1] = clock64();
             mbar_wait(&bar_gate, t & 1);
             tc_fence_after();
+            if (rec) es[2] = clock64();
             {   // epilogue 1: r = sigmoid(gate[:, 0:H]) -> r*h.  (r itself is re-derived from the accumulator in
                 // epilogue 2 for the ruc store: the candidate MMAs do not touch these columns)
                 float rk[32], v[32];
@@ -315,21 +328,41 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
                 acquire(0, false);                                      // (bar_gate covers the MMAs that read slot 0)
                 put_state(v);                                           // ZH <- r*h, slot 0 <- hi/lo(r*h)
                 publish_slot0();
+                if (p.ruc) tmem_st32(taddr + lane_base + RF_RSTASH + half * 32, rk);   // r waits in TMEM for the stores of epilogue 2
             }
+            if (rec) es[3] = clock64();
             rf_worker_bar();                                            // r*h of every row is visible
+            if (rec) es[4] = clock64();
             // ---- candidate ---------------------------------------------------------------------------------------------
+            dbg_ph = 1;
             diffuse_phase();
+            if (rec) es[5] = clock64();
             mbar_wait(&bar_cand, t & 1);
             tc_fence_after();
+            if (rec) es[6] = clock64();
             {
                 float cv[32], uv[32], hp[32];
                 tmem_ld32(dacc + 2 * RF_H + half * 32, cv);
                 tmem_ld32(dacc + RF_H + half * 32, uv);
                 tmem_ld32(taddr + lane_base + RF_STASH + half * 32, hp);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_accfree[t & 1]);        // the accumulator may take XP_{t+2}
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const float c = (p.act == 0) ? fast_tanh(cv[j]) : fmaxf(cv[j], 0.f);
-                    const float u = fast_sigmoid(uv[j]);
+                    float c, u;
+                    if (p.act == 0) {
+                        // tanh(a) = 1 - 2/(1+e^{2a}), sigmoid(b) = 1/(1+e^{-b}) with ONE reciprocal for both (the MUFU pipe,
+                        // 16 lanes/clk/SM, is what bounds the epilogues): 1/A = B/(AB), 1/B = A/(AB); the clamps keep AB finite
+                        const float ea = __expf(2.f * fminf(fmaxf(cv[j], -15.f), 15.f)), eb = __expf(-fminf(fmaxf(uv[j], -30.f), 30.f));
+                        const float A = 1.f + ea, Bq = 1.f + eb;
+                        const float rinv = __fdividef(1.f, A * Bq);
+                        c = 1.f - 2.f * (Bq * rinv);
+                        u = A * rinv;
+                    } else {
+                        c = fmaxf(cv[j], 0.f);
+                        u = fast_sigmoid(uv[j]);
+                    }
                     cv[j] = c; uv[j] = u;
                     hp[j] = rvalid ? u * hp[j] + (1.f - u) * c : 0.f;
                 }
@@ -337,6 +370,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
                 put_state(hp);                                          // ZH <- h_t, slot 0 <- hi/lo(h_t): term 0 of the next gate
                 publish_slot0();
                 tmem_st32(taddr + lane_base + RF_STASH + half * 32, hp);
+                if (rec) es[7] = clock64();
                 // the staging tiles alias slots 1-2: their last chunks must have been read by the MMAs (bar_cand) and dumped
                 if (dump && M > 1) {
                     if (fills[1] >= 1) mbar_wait(&bar_stored[1], (fills[1] - 1) & 1);
@@ -347,16 +381,13 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
                     float* ruc = p.ruc + (size_t)t * p.B * NH * 3;
                     stage_store(uv, ruc, 3 * RF_H, RF_H + half * 32);
                     stage_store(cv, ruc, 3 * RF_H, 2 * RF_H + half * 32);
-                    tmem_ld32(dacc + half * 32, uv);                    // gate pre-activation of r, still in the accumulator
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) uv[j] = fast_sigmoid(uv[j]);
+                    tmem_ld32(taddr + lane_base + RF_RSTASH + half * 32, uv);
                     stage_store(uv, ruc, 3 * RF_H, half * 32);
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_accfree[t & 1]);        // the accumulator may take XP_{t+2}
             }
+            if (rec) es[8] = clock64();
             rf_worker_bar();                                            // h_t of every row is visible; staging is free again
+            if (rec) es[9] = clock64();
         }
     }
     tc_fence_before();
@@ -364,6 +395,9 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
     if (warp == 0) tmem_dealloc<512>(taddr);
 }
 
+cudaError_t rnn_fwd_read_dbg(long long* out, int n) {
+    return cudaMemcpyFromSymbol(out, rf_dbg, sizeof(long long) * (n < 1536 ? n : 1536));
+}
 size_t rnn_fwd_wimg_bytes(int M) { return (size_t)2 * M * (RF_WSLOT + RF_WSLOT / 2); }
 int rnn_fwd_smem_bytes(int M) { return RF_OFF_PT + SB * (M - 1) * PT_STRIDE * 4 + 1024; }
 bool rnn_fwd_supported(int N, int H, int M, int smem_limit) {
@@ -381,6 +415,7 @@ cudaError_t launch_rnn_fwd(int B, int T, int N, int fin, int M, int act, const f
     RnnFwdParams p;
     memset(&p, 0, sizeof p);
     p.B = B; p.T = T; p.N = N; p.M = M; p.act = act; p.dump = img != nullptr; p.img_col0 = img_col0;
+    { const char* e = getenv("DCGRU_DBG"); p.dbg = e ? (atoi(e) & 16) : 0; }
     p.xp = xp; p.h0 = h0; p.P = P; p.wimg = reinterpret_cast<const uint8_t*>(wimg); p.hseq = hseq; p.ruc = ruc;
     CUtensorMap tm;
     memset(&tm, 0, sizeof tm);

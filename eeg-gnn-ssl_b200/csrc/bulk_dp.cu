@@ -37,6 +37,7 @@ struct BulkParams {
     int ntile, item0_stride;              // items = ntile * T, split evenly over the grid
     int NQ, NW, piece_bytes;
     const float* src; long long ss_t, ss_b;
+    const __half* src16;                  // alternative source: fp16 operand image [tile*T+t][hi|lo][96][Cin] (values scaled by *scale_ptr)
     const float* P;
     const uint8_t* wimg;
     const float* bias;
@@ -66,6 +67,8 @@ __global__ void __launch_bounds__(BK_THREADS, 1) bulk_dp_kernel(const BulkParams
     float* PTs = reinterpret_cast<float*>(smem + p.off_pt);
     float* PTid = reinterpret_cast<float*>(smem + p.off_id);
     const int srow = N * Cin;                                   // floats per sample of the source tile
+    const bool src16 = p.src16 != nullptr;
+    const __half* X16 = reinterpret_cast<const __half*>(smem + p.off_x);     // [hi|lo][96][Cin] when the source is an image
 
     if (warp == 0) tmem_alloc<512>(&tmem_slot);
     if (tid == 0) {
@@ -79,7 +82,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) bulk_dp_kernel(const BulkParams
     }
     // chunk slots, source tile and polynomial blocks start as zeros: pad rows / pad nodes are never written again
     for (int i = tid; i < BK_NS * SLOT / 16; i += BK_THREADS) reinterpret_cast<uint4*>(Aslots)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < SB * srow; i += BK_THREADS) XT[i] = 0.f;
+    if (!src16) for (int i = tid; i < SB * srow; i += BK_THREADS) XT[i] = 0.f;
     for (int i = tid; i < SB * (M - 1) * PT_STRIDE; i += BK_THREADS) PTs[i] = 0.f;
     for (int i = tid; i < PT_STRIDE; i += BK_THREADS) PTid[i] = (i / NPAD == i % NPAD) ? 1.f : 0.f;
     fence_async_smem();
@@ -134,10 +137,16 @@ __global__ void __launch_bounds__(BK_THREADS, 1) bulk_dp_kernel(const BulkParams
                 const long it = it0 + k;
                 const int tile = (int)(it / p.T), t = (int)(it - (long)tile * p.T);
                 if (k >= 1) mbar_wait(&bar_xfree, (k - 1) & 1);
-                int nvalid = p.B - tile * SB; if (nvalid > SB) nvalid = SB;
-                mbar_expect_tx(&bar_xfull, (uint32_t)(nvalid * srow * 4));
-                for (int s = 0; s < nvalid; ++s)
-                    bulk_g2s(XT + s * srow, p.src + (size_t)t * p.ss_t + (size_t)(tile * SB + s) * p.ss_b, (uint32_t)(srow * 4), &bar_xfull);
+                if (src16) {                                      // one slab of the image: both planes, all 96 rows
+                    const uint32_t bytes = (uint32_t)(2 * IMG_ROWS * Cin * 2);
+                    mbar_expect_tx(&bar_xfull, bytes);
+                    bulk_g2s(XT, p.src16 + (size_t)it * (2 * IMG_ROWS * Cin), bytes, &bar_xfull);
+                } else {
+                    int nvalid = p.B - tile * SB; if (nvalid > SB) nvalid = SB;
+                    mbar_expect_tx(&bar_xfull, (uint32_t)(nvalid * srow * 4));
+                    for (int s = 0; s < nvalid; ++s)
+                        bulk_g2s(XT + s * srow, p.src + (size_t)t * p.ss_t + (size_t)(tile * SB + s) * p.ss_b, (uint32_t)(srow * 4), &bar_xfull);
+                }
                 for (int q = 0; q < 2 * NQ; ++q, ++pc) {
                     const int ws = pc % NW;
                     if (pc >= (unsigned)NW) mbar_wait(&bar_wempty[ws], ((pc / NW) - 1) & 1);
@@ -236,17 +245,20 @@ __global__ void __launch_bounds__(BK_THREADS, 1) bulk_dp_kernel(const BulkParams
                 int m = 0, c = 0;
                 if (kvalid) { m = kk / Cin; c = kk - m * Cin; }
                 const float* z = XT + s * srow + c;
+                const __half* zh = X16 + (s * (RG * 8)) * Cin + c;                  // image rows s*24 + n
+                const __half* zl = zh + IMG_ROWS * Cin;
                 float acc[NPAD][2];
                 if (__all_sync(0xffffffffu, m == 0)) {          // identity term (or padding): plain copy
 #pragma unroll
                     for (int n = 0; n < NPAD; ++n) {
                         float2 zz = make_float2(0.f, 0.f);
-                        if (kvalid && n < N) zz = *reinterpret_cast<const float2*>(z + n * Cin);
+                        if (kvalid && n < N) zz = src16 ? ld_hilo2(zh + n * Cin, zl + n * Cin) : *reinterpret_cast<const float2*>(z + n * Cin);
                         acc[n][0] = zz.x; acc[n][1] = zz.y;
                     }
                 } else {
                     const float* pt = (m == 0) ? PTid : PTs + (s * (M - 1) + (m - 1)) * PT_STRIDE;
-                    diffuse2(z, Cin, N, pt, acc);
+                    if (src16) diffuse2f([&](int j) { return ld_hilo2(zh + j * Cin, zl + j * Cin); }, N, pt, acc);
+                    else diffuse2(z, Cin, N, pt, acc);
                     if (!kvalid) {
 #pragma unroll
                         for (int n = 0; n < NPAD; ++n) { acc[n][0] = 0.f; acc[n][1] = 0.f; }
@@ -323,9 +335,9 @@ int g16_ntile(int B) { return (B + SB - 1) / SB; }
 size_t g16_image_bytes(int B, int T, int cols) { return (size_t)g16_ntile(B) * T * 2 * IMG_ROWS * cols * 2; }
 size_t bulk_wimg_bytes(int cin, int M, int nout) { return (size_t)g16_nq(cin, M) * 2 * nout * 128; }
 
-static bool bulk_layout(int N, int Cin, int M, int Nout, int smem_limit, BulkParams* p) {
+static bool bulk_layout(int N, int Cin, int M, int Nout, int smem_limit, bool src16, BulkParams* p) {
     p->piece_bytes = Nout * 128;
-    const int xbytes = ((SB * N * Cin * 4 + 1023) / 1024) * 1024;
+    const int xbytes = (((src16 ? 2 * IMG_ROWS * Cin * 2 : SB * N * Cin * 4) + 1023) / 1024) * 1024;
     const int ptbytes = ((SB * (M - 1) * PT_STRIDE * 4 + 15) / 16) * 16;
     for (int nw = 8; nw >= 2; --nw) {
         int off = BK_NS * SLOT;
@@ -339,21 +351,22 @@ static bool bulk_layout(int N, int Cin, int M, int Nout, int smem_limit, BulkPar
 }
 static int bulk_smem(const BulkParams& p) { return p.off_id + PT_STRIDE * 4 + 1024; }
 
-bool bulk_dp_supported(int N, int Cin, int M, int Nout, int smem_limit) {
+bool bulk_dp_supported(int N, int Cin, int M, int Nout, bool src16, int smem_limit) {
     BulkParams p;
-    if (N > NPAD || Cin % 4 || (N * Cin) % 4 || M < 1 || g16_nq(Cin, M) > BK_MAXQ) return false;
+    if (N > NPAD || Cin % 8 || M < 1 || g16_nq(Cin, M) > BK_MAXQ) return false;
     if (Nout != 64 && Nout != 192) return false;
-    return bulk_layout(N, Cin, M, Nout, smem_limit, &p);
+    return bulk_layout(N, Cin, M, Nout, smem_limit, src16, &p);
 }
 
 // out (+)= ... see the header comment.  img: operand image base or nullptr; img_cols: floats.. fp16 values per image row
 cudaError_t launch_bulk_dp(int B, int T, int N, int Cin, int M, int Nout, int transposeP, const float* src, long long ss_t,
-                           long long ss_b, const float* P, const void* wimg, const float* bias, float* out, long long os_t,
+                           long long ss_b, const void* src16, const float* P, const void* wimg, const float* bias, float* out, long long os_t,
                            long long os_b, int out_ld, float out_scale, const float* scale_ptr, void* img, int img_cols,
                            int img_col0, int nsms, int smem_limit, cudaStream_t st) {
     BulkParams p;
     memset(&p, 0, sizeof p);
-    if (!bulk_layout(N, Cin, M, Nout, smem_limit, &p)) return cudaErrorInvalidConfiguration;
+    if (!bulk_layout(N, Cin, M, Nout, smem_limit, src16 != nullptr, &p)) return cudaErrorInvalidConfiguration;
+    p.src16 = reinterpret_cast<const __half*>(src16);
     p.B = B; p.T = T; p.N = N; p.Cin = Cin; p.M = M; p.Nout = Nout; p.transposeP = transposeP;
     p.ntile = g16_ntile(B); p.NQ = g16_nq(Cin, M);
     p.src = src; p.ss_t = ss_t; p.ss_b = ss_b; p.P = P; p.wimg = reinterpret_cast<const uint8_t*>(wimg); p.bias = bias;

@@ -346,7 +346,7 @@ static bool g2_fwd_supported(const dcgru_cell_desc* d) {
     const int M = Mof(d);
     const DevInfo& di = devinfo();
     return g2_enabled() && rnn_fwd_supported(d->num_nodes, d->hid_dim, M, di.smem) &&
-           bulk_dp_supported(d->num_nodes, d->input_dim, M, 3 * d->hid_dim, di.smem);
+           bulk_dp_supported(d->num_nodes, d->input_dim, M, 3 * d->hid_dim, false, di.smem);
 }
 struct G2FwdWs { size_t off_wx, off_wh, off_bias, off_xp, total; };
 static G2FwdWs g2_fwd_ws(const dcgru_cell_desc* d, int B, int T) {
@@ -357,6 +357,22 @@ static G2FwdWs g2_fwd_ws(const dcgru_cell_desc* d, int B, int T) {
     w.off_wh = o; o = align_up(o + rnn_fwd_wimg_bytes(M));
     w.off_bias = o; o = align_up(o + (size_t)3 * d->hid_dim * 4);
     w.off_xp = o; o = align_up(o + (size_t)T * B * d->num_nodes * 3 * d->hid_dim * 4);
+    w.total = o;
+    return w;
+}
+
+static bool g2_bwd_supported(const dcgru_cell_desc* d) {
+    return g2_fwd_supported(d) && rnn_bwd_supported(d->num_nodes, d->hid_dim, Mof(d), devinfo().smem);
+}
+struct G2BwdWs { size_t off_wb, off_wdx, off_img, off_scale, total; };
+static G2BwdWs g2_bwd_ws(const dcgru_cell_desc* d, int B, int T) {
+    G2BwdWs w;
+    const int M = Mof(d), H = d->hid_dim;
+    size_t o = 0;
+    w.off_wb = o; o = align_up(o + rnn_bwd_wimg_bytes(M));
+    w.off_wdx = o; o = align_up(o + bulk_wimg_bytes(3 * H, M, d->input_dim));
+    w.off_img = o; o = align_up(o + g16_image_bytes(B, T, 3 * H));
+    w.off_scale = o; o = align_up(o + 256);
     w.total = o;
     return w;
 }
@@ -413,7 +429,7 @@ int dcgru_encoder_layer_fwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
         CUDA_TRY(cudaMemcpyAsync(bias, w->bg, (size_t)2 * H * 4, cudaMemcpyDeviceToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(bias + 2 * H, w->bc, (size_t)H * 4, cudaMemcpyDeviceToDevice, st));
         LAUNCH("pack_w16", launch_pack_w16(w->Wg, w->Wc, fin, H, M, 0, 3 * H, g16_nq(fin, M), wsb + ws.off_wx, st));
-        LAUNCH("xproj", launch_bulk_dp(batch, seq_len, N, fin, M, 3 * H, 0, x, x_stride_t, x_stride_b, P, wsb + ws.off_wx, bias,
+        LAUNCH("xproj", launch_bulk_dp(batch, seq_len, N, fin, M, 3 * H, 0, x, x_stride_t, x_stride_b, nullptr, P, wsb + ws.off_wx, bias,
                                        xp, (long long)batch * N * 3 * H, (long long)N * 3 * H, 3 * H, 1.f, nullptr, nullptr, 0,
                                        0, di.sms, di.smem, st));
         LAUNCH("rnn_fwd", launch_rnn_fwd(batch, seq_len, N, fin, M, d->activation, xp, h0, P, w->Wg, w->Wc, wsb + ws.off_wh,
@@ -452,7 +468,7 @@ int dcgru_encoder_layer_fwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
 static size_t enc_bwd_ws(const dcgru_cell_desc* d, int B, int T, bool carve, void* ws, float** WgT, float** WcT,
                          float** dA, float** part, float** partb, int* nsplit, int* njobs, DwJob* jobs,
                          float** ptbuf = nullptr, float** daimg = nullptr, float** mmpart = nullptr,
-                         float** cspart = nullptr) {
+                         float** cspart = nullptr, float** g2base = nullptr) {
     const int H = d->hid_dim, M = Mof(d), CM = (d->input_dim + H) * M;
     CellDwPlan dp = plan_cell_dw(d->input_dim, H, M, B, T, jobs);
     int nj = dp.njobs, ns = dp.nsplit;
@@ -473,6 +489,11 @@ static size_t enc_bwd_ws(const dcgru_cell_desc* d, int B, int T, bool carve, voi
     if (carve) {
         *WgT = a; *WcT = b; *dA = e; *part = f; *partb = g; *nsplit = ns; *njobs = nj; *ptbuf = pt;
         *daimg = im; *mmpart = mp; *cspart = cp;
+    }
+    // second-generation backward (rnn_bwd.cu): weight images, dA operand image, gradient scale
+    if (g2_bwd_supported(d)) {
+        float* g2 = c.take(g2_bwd_ws(d, B, T).total / 4);
+        if (carve && g2base) *g2base = g2;
     }
     return c.off;
 }
@@ -545,8 +566,9 @@ int dcgru_encoder_layer_bwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
     int nsplit, njobs;
     DwParams q;
     memset(&q, 0, sizeof q);
+    float* g2base = nullptr;
     enc_bwd_ws(d, batch, seq_len, true, workspace, &WgT, &WcT, &dA, &part, &partb, &nsplit, &njobs, q.jobs, &ptbuf,
-               &daimg, &mmpart, &cspart);
+               &daimg, &mmpart, &cspart, &g2base);
     DwmmParams mm;
     bool use_mm = false;
     if (gsave) {
@@ -567,7 +589,28 @@ int dcgru_encoder_layer_bwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
     p.cell[0] = CellWT{WgT, WcT, fin};
     p.P = P; p.h0 = h0; p.hseq = h_seq; p.ruc = ruc; p.d_hseq = d_hseq; p.d_hlast = d_hlast;
     p.dx = dx; p.dh0 = dh0; p.dA = dA;
-    if (tc_enabled() && seq_bwd_tc_supported(d->num_nodes, H, M, devinfo().smem)) {
+    const bool g2_dx_ok = !dx || bulk_dp_supported(d->num_nodes, 3 * H, M, fin, true, devinfo().smem);
+    if (g2_bwd_supported(d) && g2base && !gsave && g2_dx_ok) {
+        // second-generation BPTT (2xFP16): gradient scale -> recurrent kernel (dA operand image) -> bulk dX GEMM
+        const G2BwdWs ws = g2_bwd_ws(d, batch, seq_len);
+        const DevInfo& di = devinfo();
+        const int N = d->num_nodes;
+        uint8_t* wsb = reinterpret_cast<uint8_t*>(g2base);
+        float* scale = reinterpret_cast<float*>(wsb + ws.off_scale);
+        const size_t nh = (size_t)batch * N * H;
+        LAUNCH("grad_scale", launch_grad_scale(d_hseq, d_hseq ? (size_t)seq_len * nh : 0, d_hlast, d_hlast ? nh : 0,
+                                               reinterpret_cast<unsigned*>(scale + 8), scale, st));
+        LAUNCH("rnn_bwd", launch_rnn_bwd(batch, seq_len, N, fin, M, d->activation, h0, h_seq, ruc, P, w->Wg, w->Wc, d_hseq,
+                                         d_hlast, wsb + ws.off_wb, scale, dh0, wsb + ws.off_img, st));
+        if (dx) {
+            LAUNCH("pack_w16", launch_pack_w16(w->Wg, w->Wc, fin, H, M, 1, fin, g16_nq(3 * H, M), wsb + ws.off_wdx, st));
+            LAUNCH("dx16", launch_bulk_dp(batch, seq_len, N, 3 * H, M, fin, 1, nullptr, 0, 0, wsb + ws.off_img, P, wsb + ws.off_wdx,
+                                          nullptr, dx, (long long)batch * N * fin, (long long)N * fin, fin, 1.f, scale, nullptr, 0,
+                                          0, di.sms, di.smem, st));
+        }
+        // bridge to the first-generation weight-gradient kernels: row-major fp32 dA from the image
+        LAUNCH("img_to_rows", launch_img_to_rows(wsb + ws.off_img, batch, seq_len, N, 3 * H, scale, dA, st));
+    } else if (tc_enabled() && seq_bwd_tc_supported(d->num_nodes, H, M, devinfo().smem)) {
         // recurrent part on the tensor cores; the input gradient is not recurrent -> bulk pass over all steps
         float* wimg_b = ptbuf + ((dw_tc_pt_floats(batch, M) + 63) / 64) * 64;
         LAUNCH("seq_bwd_tc", launch_seq_bwd_tc(batch, seq_len, d->num_nodes, fin, d->activation, h0, h_seq, ruc, P,
@@ -623,12 +666,12 @@ int dcgru_debug_bulk_dp(int32_t mode, int32_t B, int32_t T, int32_t N, int32_t f
     if (H != 64) return fail("hid_dim=%d unsupported by the 2xFP16 kernels", H);
     const int Cin = mode == 0 ? fin : 3 * H, Nout = mode == 0 ? 3 * H : fin;
     const DevInfo& di = devinfo();
-    if (!bulk_dp_supported(N, Cin, M, Nout, di.smem)) return fail("bulk_dp: unsupported shape (N=%d Cin=%d M=%d Nout=%d)", N, Cin, M, Nout);
+    if (!bulk_dp_supported(N, Cin, M, Nout, false, di.smem)) return fail("bulk_dp: unsupported shape (N=%d Cin=%d M=%d Nout=%d)", N, Cin, M, Nout);
     if (workspace_bytes < dcgru_debug_bulk_dp_workspace(mode, fin, H, M)) return fail("workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     LAUNCH("pack_w16", launch_pack_w16(Wg, Wc, fin, H, M, mode == 0 ? 0 : 1, Nout, g16_nq(Cin, M), workspace, st));
     LAUNCH(mode == 0 ? "xproj" : "dx16",
-           launch_bulk_dp(B, T, N, Cin, M, Nout, mode == 0 ? 0 : 1, src, (long long)B * N * Cin, (long long)N * Cin, P, workspace,
+           launch_bulk_dp(B, T, N, Cin, M, Nout, mode == 0 ? 0 : 1, src, (long long)B * N * Cin, (long long)N * Cin, nullptr, P, workspace,
                           bias, out, (long long)B * N * Nout, (long long)N * Nout, Nout, 1.f, nullptr, img, img_cols, img_col0,
                           di.sms, di.smem, st));
     return 0;

@@ -115,11 +115,11 @@ int g16_kkp(int fin, int H, int M);
 int g16_ntile(int B);
 size_t g16_image_bytes(int B, int T, int cols);
 size_t bulk_wimg_bytes(int cin, int M, int nout);
-bool bulk_dp_supported(int N, int Cin, int M, int Nout, int smem_limit);
+bool bulk_dp_supported(int N, int Cin, int M, int Nout, bool src16, int smem_limit);
 cudaError_t launch_pack_w16(const float* Wg, const float* Wc, int fin, int H, int M, int mode, int nrows, int nq,
                             void* img, cudaStream_t st);
 cudaError_t launch_bulk_dp(int B, int T, int N, int Cin, int M, int Nout, int transposeP, const float* src, long long ss_t,
-                           long long ss_b, const float* P, const void* wimg, const float* bias, float* out, long long os_t,
+                           long long ss_b, const void* src16, const float* P, const void* wimg, const float* bias, float* out, long long os_t,
                            long long os_b, int out_ld, float out_scale, const float* scale_ptr, void* img, int img_cols,
                            int img_col0, int nsms, int smem_limit, cudaStream_t st);
 
@@ -129,5 +129,13 @@ bool rnn_fwd_supported(int N, int H, int M, int smem_limit);
 cudaError_t launch_rnn_fwd(int B, int T, int N, int fin, int M, int act, const float* xp, const float* h0, const float* P,
                            const float* Wg, const float* Wc, void* wimg, float* hseq, float* ruc, void* img, int img_cols,
                            int img_col0, cudaStream_t st);
+
+size_t rnn_bwd_wimg_bytes(int M);
+bool rnn_bwd_supported(int N, int H, int M, int smem_limit);
+cudaError_t launch_grad_scale(const float* a, size_t na, const float* b, size_t nb, unsigned* scratch, float* scale, cudaStream_t st);
+cudaError_t launch_rnn_bwd(int B, int T, int N, int fin, int M, int act, const float* h0, const float* hseq, const float* ruc,
+                           const float* P, const float* Wg, const float* Wc, const float* d_hseq, const float* d_hlast,
+                           void* wimg, const float* scale_ptr, float* dh0, void* daimg, cudaStream_t st);
+cudaError_t launch_img_to_rows(const void* img, int B, int T, int N, int cols, const float* scale_ptr, float* out, cudaStream_t st);
 
 }  // namespace dcgru

@@ -70,6 +70,17 @@ __device__ __forceinline__ uint32_t k128_off(int row, int k) {
     return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 3) ^ (row & 7)) << 4) | ((k & 7) << 1)));
 }
 
+// 32 lanes x 8 consecutive columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+}
+
 // ---- fp32 -> (hi, lo) fp16 pairs ----------------------------------------------------------------------------------
 __device__ __forceinline__ float clamp_h(float x) { return fminf(fmaxf(x, -65000.f), 65000.f); }
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
@@ -98,13 +109,14 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
 // The inner product runs on packed fp32 pairs (fma.rn.f32x2 -> FFMA2, sm_100): a register pair holds the outputs of
 // two adjacent nodes (n, n+1) for one column, the P^T pair comes straight out of the 16-byte shared-memory read and the
 // source value is the instruction's broadcast scalar operand -- 20 FFMA2 instead of 40 FFMA per source row.
-__device__ __forceinline__ void diffuse2(const float* z, int zld, int N, const float* PT, float (&acc)[NPAD][2]) {
+template <class ZF>
+__device__ __forceinline__ void diffuse2f(ZF zf, int N, const float* PT, float (&acc)[NPAD][2]) {
     unsigned long long a64[NPAD / 2][2];
 #pragma unroll
     for (int i = 0; i < NPAD / 2; ++i) { a64[i][0] = 0ull; a64[i][1] = 0ull; }
 #pragma unroll 2
     for (int j = 0; j < N; ++j) {
-        const float2 zz = *reinterpret_cast<const float2*>(z + j * zld);
+        const float2 zz = zf(j);
         unsigned long long zx, zy;
         asm("mov.b64 %0, {%1, %1};" : "=l"(zx) : "f"(zz.x));
         asm("mov.b64 %0, {%1, %1};" : "=l"(zy) : "f"(zz.y));
@@ -123,6 +135,14 @@ __device__ __forceinline__ void diffuse2(const float* z, int zld, int N, const f
         asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[2 * i][0]), "=f"(acc[2 * i + 1][0]) : "l"(a64[i][0]));
         asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[2 * i][1]), "=f"(acc[2 * i + 1][1]) : "l"(a64[i][1]));
     }
+}
+__device__ __forceinline__ void diffuse2(const float* z, int zld, int N, const float* PT, float (&acc)[NPAD][2]) {
+    diffuse2f([&](int j) { return *reinterpret_cast<const float2*>(z + j * zld); }, N, PT, acc);
+}
+// same from an fp16 hi / lo source (rows of an operand image): z = hi + lo is the fp32 value to 2^-22
+__device__ __forceinline__ float2 ld_hilo2(const __half* hi, const __half* lo) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(hi)), b = __half22float2(*reinterpret_cast<const __half2*>(lo));
+    return make_float2(a.x + b.x, a.y + b.y);
 }
 // one column per lane (32-column half tasks: every warp works on the same term, so a term's chunk is complete -- and its
 // MMAs can start -- while the next term is still being diffused)

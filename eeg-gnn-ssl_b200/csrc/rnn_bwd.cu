@@ -1,0 +1,466 @@
+// BPTT of the recurrent part of one encoder layer on the tensor cores (tcgen05, 2xFP16): all T steps in reverse for a
+// tile of 4 samples per CTA (autograd of model/cell.py:182-210 driven by model/model.py:93-96).
+// Per step (dh = gradient of h_t, carried in registers; thread = (row, column half)):
+//   E1 : dh += d_hseq[t];  du = dh*(h_{t-1}-c), dc = dh*(1-u), dA_c = dc*act'(c), dA_u = du*u(1-u), dh' = dh*u
+//   B1 : d(r*h) = sum_m (P_m^T dA_c) @ Wc_h,m^T                                   (K = M*H, N = H)
+//   E2 : dr = d(rh)*h_{t-1}, dA_r = dr*r(1-r), dh' += d(rh)*r
+//   B2 : dh_{t-1} = dh' + sum_m (P_m^T [dA_r | dA_u]) @ Wg_h,m^T                   (K = 2*M*H, N = H)
+// The transposed diffusion is applied on the INPUT side (P^T commutes with the column contraction), which makes the
+// backward structurally the forward: fp32 diffusion of a shared-memory tile by one warp per (sample, column half),
+// hi/lo fp16 chunks in a 3-slot ring (f16_common.cuh), kind::f16 MMAs accumulating in TMEM.  The u part of B2 does not
+// depend on B1, so its chunks are diffused while B1's MMAs complete.
+// The term-0 chunks [dA_c], [dA_u], [dA_r] (scaled, hi/lo) are exactly the rows of the dA operand image that the
+// weight-gradient GEMM (dw_mm16.cu), the input-gradient GEMM (bulk_dp.cu) and the bias gradient read: the dump warp
+// stores them with tensor-map TMA; nothing else is written per step.
+// Saved forward state (r, u, c, h_{t-1}) and the upstream gradient are prefetched one step ahead into TMEM by four
+// loader warps (thread = row), so the epilogues never wait for global memory.
+// Gradient scaling: every fp16 operand derived from the gradient is multiplied by s = *scale_ptr, a power of two chosen
+// from the upstream gradient's magnitude (grad_scale_kernel), and the accumulators are multiplied by 1/s when read.
+//   warps 0-7 workers (epilogues + diffusion), warp 8 MMA issuer, warp 9 weight loader, warp 10 image dump,
+//   warps 11-14 state loaders
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "dw.cuh"
+#include "f16_common.cuh"
+#include "tmap.cuh"
+
+namespace dcgru {
+using namespace f16;
+
+constexpr int RB_H = 64;
+constexpr int RB_THREADS = 480;
+constexpr int RB_NWORK = 256;
+constexpr int RB_LD = RB_H + 4;                      // fp32 source tiles: row stride in floats
+constexpr int RB_NW = 4;                             // weight ring slots
+constexpr int RB_WPIECE = RB_H * 128;                // one plane of a chunk's weights: 64 rows x 128 B
+constexpr int RB_OFF_W = 3 * SLOT;
+constexpr int RB_OFF_SA = RB_OFF_W + RB_NW * RB_WPIECE;
+constexpr int RB_OFF_SB = RB_OFF_SA + 128 * RB_LD * 4;
+constexpr int RB_OFF_PT = RB_OFF_SB + 128 * RB_LD * 4;
+// TMEM columns
+constexpr int RB_ACC1 = 0, RB_ACC2 = 64, RB_U = 128, RB_C = 192, RB_HP = 256, RB_DUP = 320, RB_R = 384;
+
+struct RnnBwdParams {
+    int B, T, N, M, act, dump;
+    const float* h0; const float* hseq; const float* ruc;
+    const float* P;
+    const float* d_hseq; const float* d_hlast;
+    const uint8_t* wimg;          // B1 planes [m][hi|lo], then B2 planes [2m+g][hi|lo] (g = 0: r, 1: u), 8 KB each
+    const float* scale_ptr;
+    float* dh0;
+};
+
+// chunk i of a step (0 <= i < 3M): kind 0 = c (-> acc1), 1 = u, 2 = r (-> acc2); term m
+__device__ __forceinline__ void rb_chunk(int i, int M, int& kind, int& m) {
+    if (i == 0) { kind = 0; m = 0; }
+    else if (i == 1) { kind = 1; m = 0; }
+    else if (i <= M) { kind = 0; m = i - 1; }
+    else if (i < 2 * M) { kind = 1; m = i - M; }
+    else { kind = 2; m = i - 2 * M; }
+}
+
+__device__ __forceinline__ void rb_worker_bar() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+
+__global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdParams p, const __grid_constant__ CUtensorMap tm_img) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ uint64_t bar_afull[3], bar_aempty[3], bar_stored[3], bar_wfull[RB_NW], bar_wempty[RB_NW];
+    __shared__ uint64_t bar_gafull, bar_gbfull, bar_gafree, bar_gbfree, bar_b1, bar_b2;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = p.N, M = p.M, T = p.T;
+    const int tile = blockIdx.x, b0 = tile * SB;
+    const int nch = 3 * M;
+    uint8_t* Aslots = smem;
+    uint8_t* Wring = smem + RB_OFF_W;
+    float* SA = reinterpret_cast<float*>(smem + RB_OFF_SA);
+    float* SBt = reinterpret_cast<float*>(smem + RB_OFF_SB);
+    float* PTs = reinterpret_cast<float*>(smem + RB_OFF_PT);
+    const bool dump = p.dump != 0;
+    const size_t NH = (size_t)N * RB_H;
+
+    if (warp == 0) tmem_alloc<512>(&tmem_slot);
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) { mbar_init(&bar_afull[i], RB_NWORK / 32); mbar_init(&bar_aempty[i], 1); mbar_init(&bar_stored[i], 1); }
+        for (int i = 0; i < RB_NW; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], 1); }
+        mbar_init(&bar_gafull, 4); mbar_init(&bar_gbfull, 4);
+        mbar_init(&bar_gafree, RB_NWORK / 32); mbar_init(&bar_gbfree, RB_NWORK / 32);
+        mbar_init(&bar_b1, 1); mbar_init(&bar_b2, 1);
+        mbar_fence_init();
+    }
+    for (int i = tid; i < 3 * SLOT / 16; i += RB_THREADS) reinterpret_cast<uint4*>(Aslots)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 2 * 128 * RB_LD; i += RB_THREADS) SA[i] = 0.f;          // SA and SB are adjacent
+    for (int i = tid; i < SB * (M - 1) * PT_STRIDE; i += RB_THREADS) PTs[i] = 0.f;
+    __syncthreads();
+    load_pt(PTs, p.P, b0, p.B, N, M - 1, 1, tid, RB_THREADS);                     // rows of P: (P^T z)[n] = sum_j P[j][n] z[j]
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t taddr = tmem_slot;
+
+    if (warp == 8) {
+        // =================================== MMA issuer =================================================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_f16(128, RB_H);
+            const uint32_t a_base = smem_u32(Aslots), w_base = smem_u32(Wring);
+            const int last_c = (M == 1) ? 0 : M;
+            unsigned pc = 0, seq = 0;
+            for (int k = 0; k < T; ++k) {
+                for (int i = 0; i < nch; ++i, ++seq) {
+                    int kind, m;
+                    rb_chunk(i, M, kind, m);
+                    const int slot = seq % 3;
+                    const uint32_t ah = a_base + slot * SLOT, al = ah + PLANE;
+                    const uint32_t d = taddr + (kind == 0 ? RB_ACC1 : RB_ACC2);
+                    const uint32_t first = (i <= 1) ? 0u : 1u;
+                    const int ws0 = pc % RB_NW, ws1 = (pc + 1) % RB_NW;
+                    mbar_wait2(&bar_afull[slot], (seq / 3) & 1, &bar_wfull[ws0], (pc / RB_NW) & 1);
+                    tc_fence_after();
+                    const uint32_t bh = w_base + ws0 * RB_WPIECE, bl = w_base + ws1 * RB_WPIECE;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        umma_f16(d, make_desc_k128(al + 32 * ks), make_desc_k128(bh + 32 * ks), idesc, (ks == 0) ? first : 1u);
+                        umma_f16(d, make_desc_k128(ah + 32 * ks), make_desc_k128(bh + 32 * ks), idesc, 1u);
+                    }
+                    umma_commit(&bar_wempty[ws0]);
+                    mbar_wait(&bar_wfull[ws1], ((pc + 1) / RB_NW) & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_f16(d, make_desc_k128(ah + 32 * ks), make_desc_k128(bl + 32 * ks), idesc, 1u);
+                    umma_commit(&bar_wempty[ws1]);
+                    umma_commit(&bar_aempty[slot]);
+                    pc += 2;
+                    if (i == last_c) umma_commit(&bar_b1);
+                }
+                umma_commit(&bar_b2);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 9) {
+        // =================================== weight loader ==============================================================
+        if (lane == 0) {
+            unsigned pc = 0;
+            for (int k = 0; k < T; ++k)
+                for (int i = 0; i < nch; ++i) {
+                    int kind, m;
+                    rb_chunk(i, M, kind, m);
+                    const int piece0 = (kind == 0) ? 2 * m : 2 * M + 2 * (2 * m + (kind == 1 ? 1 : 0));
+                    for (int pl = 0; pl < 2; ++pl, ++pc) {
+                        const int ws = pc % RB_NW;
+                        if (pc >= RB_NW) mbar_wait(&bar_wempty[ws], ((pc / RB_NW) - 1) & 1);
+                        mbar_expect_tx(&bar_wfull[ws], RB_WPIECE);
+                        bulk_g2s(Wring + ws * RB_WPIECE, p.wimg + (size_t)(piece0 + pl) * RB_WPIECE, RB_WPIECE, &bar_wfull[ws]);
+                    }
+                }
+        }
+        __syncwarp();
+    } else if (warp == 10) {
+        // =================================== dA-image dump ================================================================
+        if (dump) {
+            const int plane = lane >> 2, s = lane & 3;
+            if (lane == 0) tma_prefetch_desc(&tm_img);
+            unsigned seq = 0;
+            for (int k = 0; k < T; ++k) {
+                const int t = T - 1 - k;
+                const long slab = (long)tile * T + t;
+                for (int i = 0; i < nch; ++i, ++seq) {
+                    const int slot = seq % 3;
+                    mbar_wait(&bar_afull[slot], (seq / 3) & 1);
+                    const int col = (i == 0) ? 2 * RB_H : (i == 1 ? RB_H : (i == 2 * M ? 0 : -1));   // image columns r | u | c
+                    if (col >= 0) {
+                        if (lane < 2 * SB) {
+                            tma_store_2d(&tm_img, col, (int)((slab * 2 + plane) * IMG_ROWS + s * (RG * 8)),
+                                         Aslots + slot * SLOT + plane * PLANE + s * (RP * 128));
+                            bulk_commit();
+                        }
+                        bulk_wait_read();
+                        __syncwarp();
+                    }
+                    if (lane == 0) mbar_arrive(&bar_stored[slot]);
+                }
+            }
+            bulk_wait_all();
+        }
+        __syncwarp();
+    } else if (warp >= 11) {
+        // =================================== state loaders: thread = row ==================================================
+        const int quad = warp & 3, row = 32 * quad + lane;
+        const int s = row >> 5, n = row & 31, b = b0 + s;
+        const bool valid = n < N && b < p.B;
+        const uint32_t tb = taddr + ((uint32_t)(32 * quad) << 16);
+        const size_t rbase = valid ? ((size_t)b * N + n) : 0;
+        auto load_cols = [&](const float* src, uint32_t tcol) {          // 64 floats of this row -> TMEM columns
+#pragma unroll 1
+            for (int cb = 0; cb < RB_H; cb += 32) {
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid && src) q = __ldcs(reinterpret_cast<const float4*>(src + cb) + j);
+                    v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+                }
+                tmem_st32(tb + tcol + cb, v);
+            }
+        };
+        for (int k = 0; k < T; ++k) {
+            const int t = T - 1 - k;
+            const float* ruc = p.ruc + ((size_t)t * p.B * N + rbase) * 3 * RB_H;
+            const float* hp = (t > 0) ? p.hseq + (size_t)(t - 1) * p.B * NH + rbase * RB_H : p.h0 + rbase * RB_H;
+            if (k >= 1) mbar_wait(&bar_gafree, (k - 1) & 1);
+            tc_fence_after();
+            load_cols(ruc + RB_H, RB_U);
+            load_cols(ruc + 2 * RB_H, RB_C);
+            load_cols(p.d_hseq ? p.d_hseq + (size_t)t * p.B * NH + rbase * RB_H : nullptr, RB_DUP);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_gafull);
+            if (k >= 1) mbar_wait(&bar_gbfree, (k - 1) & 1);
+            tc_fence_after();
+            load_cols(ruc, RB_R);
+            load_cols(hp, RB_HP);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_gbfull);
+        }
+    } else {
+        // =================================== workers =====================================================================
+        const int quad = warp & 3, half = warp >> 2;
+        const int row = 32 * quad + lane;
+        const int b_ = b0 + quad;
+        const bool rvalid = lane < N && b_ < p.B;
+        const uint32_t tb = taddr + ((uint32_t)(32 * quad) << 16) + half * 32;
+        const float gs = __ldg(p.scale_ptr), inv_gs = 1.f / gs;
+        unsigned seq = 0;                                               // chunks started (identical in every thread)
+        auto acquire = [&]() -> uint8_t* {                              // slot of chunk #seq, once its previous content was consumed
+            const int slot = seq % 3;
+            if (seq >= 3) {
+                mbar_wait(&bar_aempty[slot], ((seq / 3) - 1) & 1);
+                if (dump) mbar_wait(&bar_stored[slot], ((seq / 3) - 1) & 1);
+            }
+            return Aslots + slot * SLOT;
+        };
+        auto publish = [&]() {
+            const int slot = seq % 3;
+            tc_fence_before();
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_afull[slot]);
+            ++seq;
+        };
+        auto put8 = [&](uint8_t* sl, int col, const float (&v)[8]) {   // 8 columns of this row -> chunk (scaled, hi / lo)
+            float w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w[j] = v[j] * gs;
+            uint4 hi, lo;
+            split8(w, hi, lo);
+            const uint32_t off = k128_off(row, col);
+            *reinterpret_cast<uint4*>(sl + off) = hi;
+            *reinterpret_cast<uint4*>(sl + PLANE + off) = lo;
+        };
+        auto put8f = [&](float* S, int col, const float (&v)[8]) {
+            float4* d = reinterpret_cast<float4*>(S + row * RB_LD + col);
+            d[0] = make_float4(v[0], v[1], v[2], v[3]);
+            d[1] = make_float4(v[4], v[5], v[6], v[7]);
+        };
+        auto diffuse_chunk = [&](const float* S, int m) {
+            uint8_t* sl = acquire();
+            float acc[NPAD];
+            diffuse1(S + (quad * RP) * RB_LD + half * 32 + lane, RB_LD, N, PTs + (quad * (M - 1) + (m - 1)) * PT_STRIDE, acc);
+            store_col1(sl, quad * RP, half * 32 + lane, N, RG * 8, acc, gs);
+            publish();
+        };
+        float dhp[32];                                                  // dh*u (+ d(rh)*r): the elementwise part of dh_{t-1}
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rvalid && p.d_hlast) q = *reinterpret_cast<const float4*>(p.d_hlast + ((size_t)b_ * N + lane) * RB_H + half * 32 + 4 * j);
+            dhp[4 * j] = q.x; dhp[4 * j + 1] = q.y; dhp[4 * j + 2] = q.z; dhp[4 * j + 3] = q.w;
+        }
+        for (int k = 0; k < T; ++k) {
+            // ---- E1 ----------------------------------------------------------------------------------------------------
+            mbar_wait2(&bar_gafull, k & 1, &bar_gbfull, k & 1);
+            if (k >= 1) mbar_wait(&bar_b2, (k - 1) & 1);                // dh_t's GEMM part (B2 of step t+1) is in acc2
+            tc_fence_after();
+            uint8_t* slc = acquire();                                   // chunk [dA_c]
+            ++seq;
+            uint8_t* slu = acquire();                                   // chunk [dA_u]
+            --seq;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                float u[8], c[8], hp[8], g[8];
+                tmem_ld8(tb + RB_U + 8 * cc, u);
+                tmem_ld8(tb + RB_C + 8 * cc, c);
+                tmem_ld8(tb + RB_HP + 8 * cc, hp);
+                tmem_ld8(tb + RB_DUP + 8 * cc, g);
+                if (k >= 1) {
+                    float a2[8];
+                    tmem_ld8(tb + RB_ACC2 + 8 * cc, a2);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) g[j] += a2[j] * inv_gs;
+                }
+                float dac[8], dau[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float dh = rvalid ? dhp[8 * cc + j] + g[j] : 0.f;
+                    const float du = dh * (hp[j] - c[j]);
+                    const float dc = dh * (1.f - u[j]);
+                    dac[j] = (p.act == 0) ? dc * (1.f - c[j] * c[j]) : (c[j] > 0.f ? dc : 0.f);
+                    dau[j] = du * u[j] * (1.f - u[j]);
+                    dhp[8 * cc + j] = dh * u[j];
+                }
+                put8f(SA, half * 32 + 8 * cc, dac);
+                put8f(SBt, half * 32 + 8 * cc, dau);
+                put8(slc, half * 32 + 8 * cc, dac);
+                put8(slu, half * 32 + 8 * cc, dau);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_gafree);                    // u, c, d_hseq[t] consumed
+            publish();                                                  // [dA_c]
+            publish();                                                  // [dA_u]
+            rb_worker_bar();                                            // SA / SB of every row are visible
+            // ---- diffusion for B1, then the u half of B2 (independent of B1: fills B1's MMA latency) ---------------------
+            for (int m = 1; m < M; ++m) diffuse_chunk(SA, m);
+            for (int m = 1; m < M; ++m) diffuse_chunk(SBt, m);
+            mbar_wait(&bar_b1, k & 1);
+            tc_fence_after();
+            // ---- E2 ----------------------------------------------------------------------------------------------------
+            uint8_t* slr = acquire();                                   // chunk [dA_r]
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                float a1[8], hp[8], r[8], dar[8];
+                tmem_ld8(tb + RB_ACC1 + 8 * cc, a1);
+                tmem_ld8(tb + RB_HP + 8 * cc, hp);
+                tmem_ld8(tb + RB_R + 8 * cc, r);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float drh = rvalid ? a1[j] * inv_gs : 0.f;
+                    dar[j] = drh * hp[j] * r[j] * (1.f - r[j]);
+                    dhp[8 * cc + j] += drh * r[j];
+                }
+                put8f(SA, half * 32 + 8 * cc, dar);                     // (bar_b1: every warp is past its reads of SA = dA_c)
+                put8(slr, half * 32 + 8 * cc, dar);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_gbfree);                    // r, h_{t-1} consumed
+            publish();                                                  // [dA_r]
+            rb_worker_bar();
+            for (int m = 1; m < M; ++m) diffuse_chunk(SA, m);
+        }
+        // ---- dh0 = dh' + B2 of the last processed step (t = 0) ------------------------------------------------------------
+        mbar_wait(&bar_b2, (T - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            float a2[8];
+            tmem_ld8(tb + RB_ACC2 + 8 * cc, a2);
+            if (rvalid) {
+                float4* d = reinterpret_cast<float4*>(p.dh0 + ((size_t)b_ * N + lane) * RB_H + half * 32 + 8 * cc);
+                d[0] = make_float4(dhp[8 * cc] + a2[0] * inv_gs, dhp[8 * cc + 1] + a2[1] * inv_gs, dhp[8 * cc + 2] + a2[2] * inv_gs, dhp[8 * cc + 3] + a2[3] * inv_gs);
+                d[1] = make_float4(dhp[8 * cc + 4] + a2[4] * inv_gs, dhp[8 * cc + 5] + a2[5] * inv_gs, dhp[8 * cc + 6] + a2[6] * inv_gs, dhp[8 * cc + 7] + a2[7] * inv_gs);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(taddr);
+}
+
+// ---- gradient scale: s = 2^e with max|g| * s in [8, 16) (1 when the gradient is all zero / not finite) ---------------------
+__global__ void grad_absmax_kernel(const float* a, size_t na, const float* b, size_t nb, unsigned* out) {
+    float m = 0.f;
+    const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a) for (size_t i = i0; i < na; i += stride) m = fmaxf(m, fabsf(a[i]));
+    if (b) for (size_t i = i0; i < nb; i += stride) m = fmaxf(m, fabsf(b[i]));
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));          // non-negative floats order like their bit patterns
+}
+__global__ void grad_scale_kernel(unsigned* maxbits, float* scale) {
+    const float m = __uint_as_float(*maxbits);
+    float s = 1.f;
+    if (m > 0.f && m < 3.0e38f) {
+        int e;
+        frexpf(m, &e);                                                  // m = f * 2^e, f in [0.5, 1)
+        int sh = 4 - e;                                                 // max * s in [8, 16)
+        sh = sh > 100 ? 100 : (sh < -100 ? -100 : sh);
+        s = ldexpf(1.f, sh);
+    }
+    *scale = s;
+    *maxbits = 0u;
+}
+// scale[0] <- s, computed on the stream from the two upstream gradients (either may be nullptr); scratch: one unsigned, zeroed here
+cudaError_t launch_grad_scale(const float* a, size_t na, const float* b, size_t nb, unsigned* scratch, float* scale, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(unsigned), st);
+    if (e != cudaSuccess) return e;
+    grad_absmax_kernel<<<296, 256, 0, st>>>(a, na, b, nb, scratch);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    grad_scale_kernel<<<1, 1, 0, st>>>(scratch, scale);
+    return cudaGetLastError();
+}
+
+size_t rnn_bwd_wimg_bytes(int M) { return (size_t)(2 * M + 4 * M) * RB_WPIECE; }
+int rnn_bwd_smem_bytes(int M) { return RB_OFF_PT + SB * (M - 1) * PT_STRIDE * 4 + 1024; }
+bool rnn_bwd_supported(int N, int H, int M, int smem_limit) {
+    return H == RB_H && N <= NPAD && M >= 1 && M <= 7 && rnn_bwd_smem_bytes(M) + 1024 <= smem_limit;
+}
+
+// dA image: [tile*T + t][hi|lo][96][3H] fp16, columns r | u | c, values scaled by *scale_ptr
+cudaError_t launch_rnn_bwd(int B, int T, int N, int fin, int M, int act, const float* h0, const float* hseq, const float* ruc,
+                           const float* P, const float* Wg, const float* Wc, const float* d_hseq, const float* d_hlast,
+                           void* wimg, const float* scale_ptr, float* dh0, void* daimg, cudaStream_t st) {
+    cudaError_t e = launch_pack_w16(Wg, Wc, fin, RB_H, M, 4, RB_H, M, wimg, st);
+    if (e != cudaSuccess) return e;
+    e = launch_pack_w16(Wg, Wc, fin, RB_H, M, 5, RB_H, 2 * M, reinterpret_cast<uint8_t*>(wimg) + (size_t)2 * M * RB_WPIECE, st);
+    if (e != cudaSuccess) return e;
+    RnnBwdParams p;
+    memset(&p, 0, sizeof p);
+    p.B = B; p.T = T; p.N = N; p.M = M; p.act = act; p.dump = daimg != nullptr;
+    p.h0 = h0; p.hseq = hseq; p.ruc = ruc; p.P = P; p.d_hseq = d_hseq; p.d_hlast = d_hlast;
+    p.wimg = reinterpret_cast<const uint8_t*>(wimg); p.scale_ptr = scale_ptr; p.dh0 = dh0;
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof tm);
+    const int ntile = g16_ntile(B);
+    if (daimg) {
+        const unsigned long long dims[2] = {(unsigned long long)3 * RB_H, (unsigned long long)ntile * T * 2 * IMG_ROWS};
+        const unsigned long long str[2] = {2, (unsigned long long)3 * RB_H * 2};
+        const unsigned box[2] = {64, RG * 8};
+        e = make_tmap(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, daimg, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (e != cudaSuccess) return e;
+    }
+    const int smem = rnn_bwd_smem_bytes(M);
+    e = cudaFuncSetAttribute(rnn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    rnn_bwd_kernel<<<ntile, RB_THREADS, smem, st>>>(p, tm);
+    return cudaGetLastError();
+}
+
+}  // namespace dcgru
+
+namespace dcgru {
+// operand image [tile*T+t][hi|lo][96][cols] (scaled by *scale_ptr) -> row-major fp32 (T,B,N,cols): diagnostics, and the
+// bridge to the first-generation weight-gradient kernels
+__global__ void img_to_rows_kernel(const __half* img, int B, int T, int N, int cols, const float* scale_ptr, float* out) {
+    const float inv = 1.f / scale_ptr[0];
+    const size_t total = (size_t)T * B * N * cols;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % cols);
+        size_t r = idx / cols;
+        const int n = (int)(r % N); r /= N;
+        const int b = (int)(r % B);
+        const int t = (int)(r / B);
+        const size_t slab = (size_t)(b / f16::SB) * T + t;
+        const size_t o = ((slab * 2) * f16::IMG_ROWS + (b % f16::SB) * (f16::RG * 8) + n) * cols + c;
+        out[idx] = (__half2float(img[o]) + __half2float(img[o + (size_t)f16::IMG_ROWS * cols])) * inv;
+    }
+}
+cudaError_t launch_img_to_rows(const void* img, int B, int T, int N, int cols, const float* scale_ptr, float* out, cudaStream_t st) {
+    img_to_rows_kernel<<<1184, 256, 0, st>>>(reinterpret_cast<const __half*>(img), B, T, N, cols, scale_ptr, out);
+    return cudaGetLastError();
+}
+}  // namespace dcgru

@@ -364,7 +364,7 @@ static G2FwdWs g2_fwd_ws(const dcgru_cell_desc* d, int B, int T) {
 static bool g2_bwd_supported(const dcgru_cell_desc* d) {
     return g2_fwd_supported(d) && rnn_bwd_supported(d->num_nodes, d->hid_dim, Mof(d), devinfo().smem);
 }
-struct G2BwdWs { size_t off_wb, off_wdx, off_img, off_scale, total; };
+struct G2BwdWs { size_t off_wb, off_wdx, off_img, off_scale, off_part, off_cs, total; };
 static G2BwdWs g2_bwd_ws(const dcgru_cell_desc* d, int B, int T) {
     G2BwdWs w;
     const int M = Mof(d), H = d->hid_dim;
@@ -373,14 +373,23 @@ static G2BwdWs g2_bwd_ws(const dcgru_cell_desc* d, int B, int T) {
     w.off_wdx = o; o = align_up(o + bulk_wimg_bytes(3 * H, M, d->input_dim));
     w.off_img = o; o = align_up(o + g16_image_bytes(B, T, 3 * H));
     w.off_scale = o; o = align_up(o + 256);
+    w.off_part = o; o = align_up(o + dw_mm16_part_floats(devinfo().sms) * 4);
+    w.off_cs = o; o = align_up(o + colsum16_part_floats(H) * 4);
     w.total = o;
     return w;
+}
+static bool g2_gsave_enabled() {
+    const char* e = getenv("DCGRU_DISABLE_GSAVE");
+    return !(e && e[0] == '1');
 }
 
 // operand image of the tensor-core forward kernel (0: the configuration has no such path)
 static size_t gsave_bytes_for(const dcgru_cell_desc* d, int B, int T) {
     if (!tc_enabled()) return 0;
-    if (g2_fwd_supported(d)) return 0;          // (the second-generation backward is not wired in yet)
+    if (g2_fwd_supported(d)) {                  // second generation: fp16 image [tile*T+t][hi|lo][96][KKP]
+        if (!g2_bwd_supported(d) || !g2_gsave_enabled() || dw_mm16_smem_bytes() + 2048 > devinfo().smem) return 0;
+        return g16_image_bytes(B, T, g16_kkp(d->input_dim, d->hid_dim, Mof(d)));
+    }
     { const char* e = getenv("DCGRU_DISABLE_GSAVE"); if (e && e[0] == '1') return 0; }
     const int M = Mof(d);
     const DevInfo& di = devinfo();
@@ -418,8 +427,15 @@ int dcgru_encoder_layer_fwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
         return fail("x/h0/h_seq/weights must be 16-byte aligned with strides multiple of 4 floats");
     cudaStream_t st = (cudaStream_t)stream;
     // second-generation tensor-core path (tcgen05, 2xFP16): hoisted x-part GEMM over all steps, then the recurrence
-    if (g2_fwd_supported(d) && !gsave && workspace && aligned16(workspace) &&
+    if (g2_fwd_supported(d) && workspace && aligned16(workspace) &&
         workspace_bytes >= g2_fwd_ws(d, batch, seq_len).total) {
+        const int kkp = g16_kkp(d->input_dim, d->hid_dim, M), kxp = g16_kxp(d->input_dim, M);
+        if (gsave) {
+            const size_t need = gsave_bytes_for(d, batch, seq_len);
+            if (need == 0) return fail("this configuration has no operand image: pass gsave = NULL");
+            if (gsave_bytes < need) return fail("gsave too small (%zu < %zu bytes)", gsave_bytes, need);
+            if (!aligned16(gsave)) return fail("gsave must be 16-byte aligned");
+        }
         const G2FwdWs ws = g2_fwd_ws(d, batch, seq_len);
         const DevInfo& di = devinfo();
         const int H = d->hid_dim, N = d->num_nodes, fin = d->input_dim;
@@ -430,10 +446,10 @@ int dcgru_encoder_layer_fwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
         CUDA_TRY(cudaMemcpyAsync(bias + 2 * H, w->bc, (size_t)H * 4, cudaMemcpyDeviceToDevice, st));
         LAUNCH("pack_w16", launch_pack_w16(w->Wg, w->Wc, fin, H, M, 0, 3 * H, g16_nq(fin, M), wsb + ws.off_wx, st));
         LAUNCH("xproj", launch_bulk_dp(batch, seq_len, N, fin, M, 3 * H, 0, x, x_stride_t, x_stride_b, nullptr, P, wsb + ws.off_wx, bias,
-                                       xp, (long long)batch * N * 3 * H, (long long)N * 3 * H, 3 * H, 1.f, nullptr, nullptr, 0,
+                                       xp, (long long)batch * N * 3 * H, (long long)N * 3 * H, 3 * H, 1.f, nullptr, gsave, kkp,
                                        0, di.sms, di.smem, st));
         LAUNCH("rnn_fwd", launch_rnn_fwd(batch, seq_len, N, fin, M, d->activation, xp, h0, P, w->Wg, w->Wc, wsb + ws.off_wh,
-                                         h_seq, ruc, nullptr, 0, 0, st));
+                                         h_seq, ruc, gsave, kkp, kxp, st));
         return 0;
     }
     // tensor-core path (tcgen05, 3xTF32): K=2 / one support / 64 units -- the reference's default cell
@@ -481,7 +497,7 @@ static size_t enc_bwd_ws(const dcgru_cell_desc* d, int B, int T, bool carve, voi
     float* pt = c.take(((dw_tc_pt_floats(B, M) + 63) / 64) * 64 + 2 * (seq_bwd_tc_wimg_bytes() / 4 + 64));   // P^T + BPTT weight image + dX weight image
     // operand-image path (dw_mm.cu): dA image, per-CTA partials, column-sum partials
     float *im = nullptr, *mp = nullptr, *cp = nullptr;
-    if (gsave_bytes_for(d, B, T) > 0) {
+    if (gsave_bytes_for(d, B, T) > 0 && !g2_bwd_supported(d)) {
         im = c.take(seq_bwd_tc_daimg_bytes(B, T) / 4);
         mp = c.take(dwmm_part_floats(devinfo().sms));
         cp = c.take(colsum_part_floats(H));
@@ -571,7 +587,7 @@ int dcgru_encoder_layer_bwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
                &daimg, &mmpart, &cspart, &g2base);
     DwmmParams mm;
     bool use_mm = false;
-    if (gsave) {
+    if (gsave && !g2_bwd_supported(d)) {
         const size_t need = gsave_bytes_for(d, batch, seq_len);
         if (need == 0 || !daimg) return fail("this configuration has no operand image: pass gsave = NULL");
         if (gsave_bytes < need) return fail("gsave too small (%zu < %zu bytes)", gsave_bytes, need);
@@ -590,7 +606,12 @@ int dcgru_encoder_layer_bwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
     p.P = P; p.h0 = h0; p.hseq = h_seq; p.ruc = ruc; p.d_hseq = d_hseq; p.d_hlast = d_hlast;
     p.dx = dx; p.dh0 = dh0; p.dA = dA;
     const bool g2_dx_ok = !dx || bulk_dp_supported(d->num_nodes, 3 * H, M, fin, true, devinfo().smem);
-    if (g2_bwd_supported(d) && g2base && !gsave && g2_dx_ok) {
+    if (g2_bwd_supported(d) && g2base && g2_dx_ok) {
+        if (gsave) {
+            const size_t need = gsave_bytes_for(d, batch, seq_len);
+            if (need == 0) return fail("this configuration has no operand image: pass gsave = NULL");
+            if (gsave_bytes < need) return fail("gsave too small (%zu < %zu bytes)", gsave_bytes, need);
+        }
         // second-generation BPTT (2xFP16): gradient scale -> recurrent kernel (dA operand image) -> bulk dX GEMM
         const G2BwdWs ws = g2_bwd_ws(d, batch, seq_len);
         const DevInfo& di = devinfo();
@@ -608,7 +629,15 @@ int dcgru_encoder_layer_bwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
                                           nullptr, dx, (long long)batch * N * fin, (long long)N * fin, fin, 1.f, scale, nullptr, 0,
                                           0, di.sms, di.smem, st));
         }
-        // bridge to the first-generation weight-gradient kernels: row-major fp32 dA from the image
+        if (gsave) {
+            // weight gradient: GEMM over the two fp16 operand images; bias gradient: column sums of the dA image
+            LAUNCH("dw_mm16", launch_dw_mm16(fin, H, M, batch, seq_len, gsave, wsb + ws.off_img, reinterpret_cast<float*>(wsb + ws.off_part),
+                                             scale, di.sms, g->dWg, g->dWc, st));
+            LAUNCH("colsum16", launch_colsum16(wsb + ws.off_img, batch, seq_len, H, reinterpret_cast<float*>(wsb + ws.off_cs), scale,
+                                               g->dbg, g->dbc, st));
+            return 0;
+        }
+        // no operand image: bridge to the first-generation (recompute) weight-gradient kernels through a row-major fp32 dA
         LAUNCH("img_to_rows", launch_img_to_rows(wsb + ws.off_img, batch, seq_len, N, 3 * H, scale, dA, st));
     } else if (tc_enabled() && seq_bwd_tc_supported(d->num_nodes, H, M, devinfo().smem)) {
         // recurrent part on the tensor cores; the input gradient is not recurrent -> bulk pass over all steps

@@ -138,4 +138,12 @@ cudaError_t launch_rnn_bwd(int B, int T, int N, int fin, int M, int act, const f
                            void* wimg, const float* scale_ptr, float* dh0, void* daimg, cudaStream_t st);
 cudaError_t launch_img_to_rows(const void* img, int B, int T, int N, int cols, const float* scale_ptr, float* out, cudaStream_t st);
 
+size_t dw_mm16_part_floats(int nsms);
+size_t colsum16_part_floats(int H);
+int dw_mm16_smem_bytes();
+cudaError_t launch_dw_mm16(int fin, int H, int M, int B, int T, const void* G, const void* DA, float* part, const float* scale_ptr,
+                           int nsms, float* dWg, float* dWc, cudaStream_t st);
+cudaError_t launch_colsum16(const void* daimg, int B, int T, int H, float* partial, const float* scale_ptr, float* dbg, float* dbc,
+                            cudaStream_t st);
+
 }  // namespace dcgru

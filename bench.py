@@ -481,13 +481,15 @@ def kernel_families(cfg):
     for l in range(cfg["L"]):
         fin_l = F_IN if l == 0 else cfg["H"]
         full, hpart, xpart = tb * f_cols(fin_l + cfg["H"]), tb * f_cols(cfg["H"]), tb * f_cols(fin_l)
-        for nm in ("seq_fwd", "seq_fwd_tc", "dw", "dw_tc", "dw_mm"):
+        for nm in ("seq_fwd", "seq_fwd_tc", "dw", "dw_tc", "dw_mm", "dw_mm16"):
             fam.setdefault(nm, []).append(full)
         fam.setdefault("seq_bwd", []).append(full if l > 0 else hpart)
-        fam.setdefault("seq_bwd_tc", []).append(hpart)
+        for nm in ("seq_bwd_tc", "rnn_fwd", "rnn_bwd"):              # recurrent (h) columns only
+            fam.setdefault(nm, []).append(hpart)
+        fam.setdefault("xproj", []).append(xpart)                    # hoisted x-part of the forward
         if l > 0:
-            fam.setdefault("dx_tc", []).append(xpart)
-            fam.setdefault("dx", []).append(xpart)
+            for nm in ("dx_tc", "dx", "dx16"):
+                fam.setdefault(nm, []).append(xpart)
     return fam
 
 

@@ -13,7 +13,7 @@ SYMBOLS = [
     "dcgru_timing_enable", "dcgru_timing_collect", "dcgru_tc_selftest", "dcgru_debug_encoder_bwd_offsets",
     "dcgru_debug_dwmm_stamps", "dcgru_debug_dwmm_plan", "dcgru_tc_probe",
     "dcgru_clip_adam_workspace", "dcgru_clip_adam_step",
-    "dcgru_debug_bulk_dp_workspace", "dcgru_debug_bulk_dp", "dcgru_debug_rnn_fwd_stamps",
+    "dcgru_debug_bulk_dp_workspace", "dcgru_debug_bulk_dp", "dcgru_debug_rnn_fwd_stamps", "dcgru_debug_rnn_bwd_stamps",
 ]
 
 MAX_LAYERS = 4
@@ -72,6 +72,7 @@ def lib():
     L.dcgru_tc_probe.argtypes = [vp, i32, vp, i32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, i32, i32, i32, i32, vp, i32, vp]
     L.dcgru_debug_dwmm_stamps.argtypes = [C.POINTER(C.c_longlong), i32]
     L.dcgru_debug_rnn_fwd_stamps.argtypes = [C.POINTER(C.c_longlong), i32]
+    L.dcgru_debug_rnn_bwd_stamps.argtypes = [C.POINTER(C.c_longlong), i32]
     L.dcgru_clip_adam_workspace.argtypes = [sz]
     L.dcgru_clip_adam_workspace.restype = sz
     L.dcgru_clip_adam_step.argtypes = [vp, vp, vp, vp, sz, vp, vp, f32, f32, f32, f32, f32, f32, vp, vp, sz, vp]

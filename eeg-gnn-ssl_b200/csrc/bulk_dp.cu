@@ -56,8 +56,10 @@ __global__ void __launch_bounds__(BK_THREADS, 1) bulk_dp_kernel(const BulkParams
     __shared__ uint64_t bar_afull[BK_MAXQ], bar_aempty[BK_NS], bar_stored[BK_NS], bar_wfull[8], bar_wempty[8];
     __shared__ uint64_t bar_xfull, bar_xfree, bar_accfull[2], bar_accfree[2];
     __shared__ uint32_t tmem_slot;
+    __shared__ __align__(16) float sbias[192];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = p.N, Cin = p.Cin, M = p.M, NQ = p.NQ, NW = p.NW;
+    if (tid < 192) sbias[tid] = (p.bias && tid < p.Nout) ? p.bias[tid] : 0.f;
     const long nitems = (long)p.ntile * p.T;
     const long it0 = nitems * blockIdx.x / gridDim.x, it1 = nitems * (blockIdx.x + 1) / gridDim.x;
     const int nloc = (int)(it1 - it0);
@@ -205,8 +207,9 @@ __global__ void __launch_bounds__(BK_THREADS, 1) bulk_dp_kernel(const BulkParams
                     for (int j = 0; j < 32; j += 4) {
                         float4 o;
                         const int c = half * ncol + cb + j;
-                        o.x = v[j] * oscale; o.y = v[j + 1] * oscale; o.z = v[j + 2] * oscale; o.w = v[j + 3] * oscale;
-                        if (p.bias) { o.x += __ldg(p.bias + c); o.y += __ldg(p.bias + c + 1); o.z += __ldg(p.bias + c + 2); o.w += __ldg(p.bias + c + 3); }
+                        const float4 bq = *reinterpret_cast<const float4*>(sbias + c);
+                        o.x = fmaf(v[j], oscale, bq.x); o.y = fmaf(v[j + 1], oscale, bq.y);
+                        o.z = fmaf(v[j + 2], oscale, bq.z); o.w = fmaf(v[j + 3], oscale, bq.w);
                         *reinterpret_cast<float4*>(orow + cb + j) = o;
                     }
                 }
@@ -353,7 +356,7 @@ static int bulk_smem(const BulkParams& p) { return p.off_id + PT_STRIDE * 4 + 10
 
 bool bulk_dp_supported(int N, int Cin, int M, int Nout, bool src16, int smem_limit) {
     BulkParams p;
-    if (N > NPAD || Cin % 8 || M < 1 || g16_nq(Cin, M) > BK_MAXQ) return false;
+    if (N > NPAD || Cin % (src16 ? 8 : 4) || M < 1 || g16_nq(Cin, M) > BK_MAXQ) return false;
     if (Nout != 64 && Nout != 192) return false;
     return bulk_layout(N, Cin, M, Nout, smem_limit, src16, &p);
 }

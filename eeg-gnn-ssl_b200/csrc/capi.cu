@@ -527,6 +527,10 @@ int dcgru_debug_rnn_fwd_stamps(long long* out, int32_t n) {
     CUDA_TRY(rnn_fwd_read_dbg(out, n));
     return 0;
 }
+int dcgru_debug_rnn_bwd_stamps(long long* out, int32_t n) {
+    CUDA_TRY(rnn_bwd_read_dbg(out, n));
+    return 0;
+}
 
 // plan of the weight-gradient GEMM as plain integers (host logic only: testable without a device):
 // out[0] = number of sets, out[1] = K blocks, then per set 4 + 6*ntile ints:

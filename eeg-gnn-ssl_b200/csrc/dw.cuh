@@ -131,6 +131,7 @@ cudaError_t launch_rnn_fwd(int B, int T, int N, int fin, int M, int act, const f
                            int img_col0, cudaStream_t st);
 
 size_t rnn_bwd_wimg_bytes(int M);
+cudaError_t rnn_bwd_read_dbg(long long* out, int n);
 bool rnn_bwd_supported(int N, int H, int M, int smem_limit);
 cudaError_t launch_grad_scale(const float* a, size_t na, const float* b, size_t nb, unsigned* scratch, float* scale, cudaStream_t st);
 cudaError_t launch_rnn_bwd(int B, int T, int N, int fin, int M, int act, const float* h0, const float* hseq, const float* ruc,

@@ -200,23 +200,34 @@ __global__ void dw_mm16_reduce_kernel(const Dw16Params p, int fin, int H, int M,
 }
 
 // ---- db: column sums of the dA image (hi + lo), two fixed-order stages --------------------------------------------------
-constexpr int CS16_CTAS = 592;
-__global__ void __launch_bounds__(96) colsum16_kernel(const __half* img, long nslab, float* partial) {
-    // thread = column pair; a CTA owns a contiguous range of slabs
-    const long s0 = nslab * blockIdx.x / gridDim.x, s1 = nslab * (blockIdx.x + 1) / gridDim.x;
-    float ax = 0.f, ay = 0.f;
-    for (long s = s0; s < s1; ++s) {
-        const __half2* base = reinterpret_cast<const __half2*>(img + (size_t)s * 2 * IMG_ROWS * 192) + threadIdx.x;
-        float bx = 0.f, by = 0.f;
-#pragma unroll 8
-        for (int r = 0; r < 2 * IMG_ROWS; ++r) {                      // both planes: hi rows then lo rows
-            const float2 v = __half22float2(base[(size_t)r * 96]);
-            bx += v.x; by += v.y;
-        }
-        ax += bx; ay += by;
+constexpr int CS16_CTAS = 1184;
+// thread = (8-column group, row slot): 16-byte loads (8 fp16), 8 row slots per CTA, several rows in flight per thread
+__global__ void __launch_bounds__(192) colsum16_kernel(const __half* img, long nrows, float* partial) {
+    __shared__ float red[8][192];
+    const int cg = threadIdx.x % 24, slot = threadIdx.x / 24;         // 24 groups of 8 columns, 8 slots
+    const long r0 = nrows * blockIdx.x / gridDim.x, r1 = nrows * (blockIdx.x + 1) / gridDim.x;
+    const uint4* src = reinterpret_cast<const uint4*>(img) + cg;      // row pitch = 192 halfs = 24 uint4
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = 0.f;
+    auto add = [&](const uint4& q) {
+        const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); a[2 * j] += f.x; a[2 * j + 1] += f.y; }
+    };
+    long r = r0 + slot;
+    for (; r + 24 < r1; r += 32) {
+        const uint4 q0 = __ldcs(src + (size_t)r * 24), q1 = __ldcs(src + (size_t)(r + 8) * 24), q2 = __ldcs(src + (size_t)(r + 16) * 24),
+                    q3 = __ldcs(src + (size_t)(r + 24) * 24);
+        add(q0); add(q1); add(q2); add(q3);
     }
-    partial[(size_t)blockIdx.x * 192 + 2 * threadIdx.x] = ax;
-    partial[(size_t)blockIdx.x * 192 + 2 * threadIdx.x + 1] = ay;
+    for (; r < r1; r += 8) add(__ldcs(src + (size_t)r * 24));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[slot][8 * cg + j] = a[j];
+    __syncthreads();
+    float s = 0.f;
+    for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+    partial[(size_t)blockIdx.x * 192 + threadIdx.x] = s;
 }
 __global__ void colsum16_final_kernel(const float* partial, int n, int H, const float* scale_ptr, float* dbg, float* dbc) {
     const int c = threadIdx.x;
@@ -317,7 +328,7 @@ cudaError_t launch_dw_mm16(int fin, int H, int M, int B, int T, const void* G, c
 cudaError_t launch_colsum16(const void* daimg, int B, int T, int H, float* partial, const float* scale_ptr, float* dbg, float* dbc,
                             cudaStream_t st) {
     if (H != 64) return cudaErrorInvalidValue;
-    colsum16_kernel<<<CS16_CTAS, 96, 0, st>>>(reinterpret_cast<const __half*>(daimg), (long)g16_ntile(B) * T, partial);
+    colsum16_kernel<<<CS16_CTAS, 192, 0, st>>>(reinterpret_cast<const __half*>(daimg), (long)g16_ntile(B) * T * 2 * IMG_ROWS, partial);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     colsum16_final_kernel<<<1, 3 * H, 0, st>>>(partial, CS16_CTAS, H, scale_ptr, dbg, dbc);

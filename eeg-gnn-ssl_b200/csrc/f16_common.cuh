@@ -181,13 +181,15 @@ __device__ __forceinline__ void store_col1(uint8_t* slot, int row0, int k, int N
         }
     }
 }
-// rows n < N of acc -> chunk slot (hi plane at `slot`, lo plane PLANE further), tile row = row0 + n, k = 2 * lane
-__device__ __forceinline__ void store_cols2(uint8_t* slot, int row0, int lane, int N, const float (&acc)[NPAD][2], float scale) {
+// rows n < N of acc -> chunk slot (hi plane at `slot`, lo plane PLANE further), tile row = row0 + n, k = 2 * lane;
+// rows N..nzero-1 are written as zeros (nzero = 0: leave them alone)
+__device__ __forceinline__ void store_cols2(uint8_t* slot, int row0, int lane, int N, const float (&acc)[NPAD][2], float scale,
+                                            int nzero = 0) {
 #pragma unroll
-    for (int n = 0; n < NPAD; ++n) {
-        if (n < N) {
-            uint32_t hi, lo;
-            split2(acc[n][0] * scale, acc[n][1] * scale, hi, lo);
+    for (int n = 0; n < RG * 8; ++n) {
+        if (n < N || n < nzero) {
+            uint32_t hi = 0u, lo = 0u;
+            if (n < NPAD && n < N) split2(acc[n < NPAD ? n : 0][0] * scale, acc[n < NPAD ? n : 0][1] * scale, hi, lo);
             const uint32_t off = k128_off(row0 + n, 2 * lane);
             *reinterpret_cast<uint32_t*>(slot + off) = hi;
             *reinterpret_cast<uint32_t*>(slot + PLANE + off) = lo;

@@ -43,7 +43,7 @@ constexpr int RB_OFF_PT = RB_OFF_SB + 128 * RB_LD * 4;
 constexpr int RB_ACC1 = 0, RB_ACC2 = 64, RB_U = 128, RB_C = 192, RB_HP = 256, RB_DUP = 320, RB_R = 384;
 
 struct RnnBwdParams {
-    int B, T, N, M, act, dump;
+    int B, T, N, M, act, dump, dbg;
     const float* h0; const float* hseq; const float* ruc;
     const float* P;
     const float* d_hseq; const float* d_hlast;
@@ -60,6 +60,9 @@ __device__ __forceinline__ void rb_chunk(int i, int M, int& kind, int& m) {
     else if (i < 2 * M) { kind = 1; m = i - M; }
     else { kind = 2; m = i - 2 * M; }
 }
+
+// timing experiment (DCGRU_DBG & 32): clock64 stamps of CTA 0, worker thread 0: [step][0..9]
+__device__ long long rb_dbg[64 * 16];
 
 __device__ __forceinline__ void rb_worker_bar() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 
@@ -266,12 +269,23 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
             d[0] = make_float4(v[0], v[1], v[2], v[3]);
             d[1] = make_float4(v[4], v[5], v[6], v[7]);
         };
-        auto diffuse_chunk = [&](const float* S, int m) {
-            uint8_t* sl = acquire();
-            float acc[NPAD];
-            diffuse1(S + (quad * RP) * RB_LD + half * 32 + lane, RB_LD, N, PTs + (quad * (M - 1) + (m - 1)) * PT_STRIDE, acc);
-            store_col1(sl, quad * RP, half * 32 + lane, N, RG * 8, acc, gs);
-            publish();
+        // diffusion chunks: one warp per (sample, term), 64 columns, two per lane (see rnn_fwd.cu); a group of terms
+        // [m0, m1) is spread over the 8 warps, 4 tasks per chunk, each arriving with count 2
+        auto diffuse_group = [&](const float* S) {
+            for (int m = 1; m < M; ++m) {
+                const int s = (warp - ((m - 1) * SB)) & 7;
+                if (s < SB) {
+                    uint8_t* sl = acquire();
+                    float acc[NPAD][2];
+                    diffuse2(S + (s * RP) * RB_LD + 2 * lane, RB_LD, N, PTs + (s * (M - 1) + (m - 1)) * PT_STRIDE, acc);
+                    store_cols2(sl, s * RP, lane, N, acc, gs, RG * 8);
+                    tc_fence_before();
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_n(&bar_afull[seq % 3], 2);
+                }
+                ++seq;
+            }
         };
         float dhp[32];                                                  // dh*u (+ d(rh)*r): the elementwise part of dh_{t-1}
 #pragma unroll
@@ -282,9 +296,14 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
         }
         for (int k = 0; k < T; ++k) {
             // ---- E1 ----------------------------------------------------------------------------------------------------
+            const bool rec = p.dbg && blockIdx.x == 0 && tid == 0 && k < 64;
+            long long* es = rb_dbg + k * 16;
+            if (rec) es[0] = clock64();
             mbar_wait2(&bar_gafull, k & 1, &bar_gbfull, k & 1);
+            if (rec) es[1] = clock64();
             if (k >= 1) mbar_wait(&bar_b2, (k - 1) & 1);                // dh_t's GEMM part (B2 of step t+1) is in acc2
             tc_fence_after();
+            if (rec) es[2] = clock64();
             uint8_t* slc = acquire();                                   // chunk [dA_c]
             ++seq;
             uint8_t* slu = acquire();                                   // chunk [dA_u]
@@ -322,12 +341,17 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
             if (lane == 0) mbar_arrive(&bar_gafree);                    // u, c, d_hseq[t] consumed
             publish();                                                  // [dA_c]
             publish();                                                  // [dA_u]
+            if (rec) es[3] = clock64();
             rb_worker_bar();                                            // SA / SB of every row are visible
+            if (rec) es[4] = clock64();
             // ---- diffusion for B1, then the u half of B2 (independent of B1: fills B1's MMA latency) ---------------------
-            for (int m = 1; m < M; ++m) diffuse_chunk(SA, m);
-            for (int m = 1; m < M; ++m) diffuse_chunk(SBt, m);
+            diffuse_group(SA);
+            if (rec) es[5] = clock64();
+            diffuse_group(SBt);
+            if (rec) es[6] = clock64();
             mbar_wait(&bar_b1, k & 1);
             tc_fence_after();
+            if (rec) es[7] = clock64();
             // ---- E2 ----------------------------------------------------------------------------------------------------
             uint8_t* slr = acquire();                                   // chunk [dA_r]
 #pragma unroll
@@ -349,8 +373,10 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_gbfree);                    // r, h_{t-1} consumed
             publish();                                                  // [dA_r]
+            if (rec) es[8] = clock64();
             rb_worker_bar();
-            for (int m = 1; m < M; ++m) diffuse_chunk(SA, m);
+            diffuse_group(SA);
+            if (rec) es[9] = clock64();
         }
         // ---- dh0 = dh' + B2 of the last processed step (t = 0) ------------------------------------------------------------
         mbar_wait(&bar_b2, (T - 1) & 1);
@@ -372,11 +398,27 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
 }
 
 // ---- gradient scale: s = 2^e with max|g| * s in [8, 16) (1 when the gradient is all zero / not finite) ---------------------
-__global__ void grad_absmax_kernel(const float* a, size_t na, const float* b, size_t nb, unsigned* out) {
+__global__ void __launch_bounds__(256) grad_absmax_kernel(const float* a, size_t na, const float* b, size_t nb, unsigned* out) {
     float m = 0.f;
     const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (a) for (size_t i = i0; i < na; i += stride) m = fmaxf(m, fabsf(a[i]));
-    if (b) for (size_t i = i0; i < nb; i += stride) m = fmaxf(m, fabsf(b[i]));
+    auto scan = [&](const float* q, size_t n) {                        // 16-byte loads, 4 in flight per thread (n % 4 == 0, 16-byte aligned)
+        const float4* q4 = reinterpret_cast<const float4*>(q);
+        const size_t n4 = n / 4;
+        size_t i = i0;
+        for (; i + 3 * stride < n4; i += 4 * stride) {
+            const float4 v0 = __ldcs(q4 + i), v1 = __ldcs(q4 + i + stride), v2 = __ldcs(q4 + i + 2 * stride), v3 = __ldcs(q4 + i + 3 * stride);
+            m = fmaxf(m, fmaxf(fmaxf(fmaxf(fabsf(v0.x), fabsf(v0.y)), fmaxf(fabsf(v0.z), fabsf(v0.w))),
+                               fmaxf(fmaxf(fabsf(v1.x), fabsf(v1.y)), fmaxf(fabsf(v1.z), fabsf(v1.w)))));
+            m = fmaxf(m, fmaxf(fmaxf(fmaxf(fabsf(v2.x), fabsf(v2.y)), fmaxf(fabsf(v2.z), fabsf(v2.w))),
+                               fmaxf(fmaxf(fabsf(v3.x), fabsf(v3.y)), fmaxf(fabsf(v3.z), fabsf(v3.w)))));
+        }
+        for (; i < n4; i += stride) {
+            const float4 v = __ldcs(q4 + i);
+            m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        }
+    };
+    if (a) scan(a, na);
+    if (b) scan(b, nb);
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));          // non-negative floats order like their bit patterns
 }
@@ -397,13 +439,16 @@ __global__ void grad_scale_kernel(unsigned* maxbits, float* scale) {
 cudaError_t launch_grad_scale(const float* a, size_t na, const float* b, size_t nb, unsigned* scratch, float* scale, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(unsigned), st);
     if (e != cudaSuccess) return e;
-    grad_absmax_kernel<<<296, 256, 0, st>>>(a, na, b, nb, scratch);
+    grad_absmax_kernel<<<1184, 256, 0, st>>>(a, na, b, nb, scratch);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     grad_scale_kernel<<<1, 1, 0, st>>>(scratch, scale);
     return cudaGetLastError();
 }
 
+cudaError_t rnn_bwd_read_dbg(long long* out, int n) {
+    return cudaMemcpyFromSymbol(out, rb_dbg, sizeof(long long) * (n < 1024 ? n : 1024));
+}
 size_t rnn_bwd_wimg_bytes(int M) { return (size_t)(2 * M + 4 * M) * RB_WPIECE; }
 int rnn_bwd_smem_bytes(int M) { return RB_OFF_PT + SB * (M - 1) * PT_STRIDE * 4 + 1024; }
 bool rnn_bwd_supported(int N, int H, int M, int smem_limit) {
@@ -421,6 +466,7 @@ cudaError_t launch_rnn_bwd(int B, int T, int N, int fin, int M, int act, const f
     RnnBwdParams p;
     memset(&p, 0, sizeof p);
     p.B = B; p.T = T; p.N = N; p.M = M; p.act = act; p.dump = daimg != nullptr;
+    { const char* e = getenv("DCGRU_DBG"); p.dbg = e ? (atoi(e) & 32) : 0; }
     p.h0 = h0; p.hseq = hseq; p.ruc = ruc; p.P = P; p.d_hseq = d_hseq; p.d_hlast = d_hlast;
     p.wimg = reinterpret_cast<const uint8_t*>(wimg); p.scale_ptr = scale_ptr; p.dh0 = dh0;
     CUtensorMap tm;

@@ -263,26 +263,24 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
             if (lane == 0) mbar_arrive(&bar_afull[0]);
             ++fills[0];
         };
-        // diffusion of one phase: every warp takes (sample quad, column half) of EVERY term m >= 1, in term order, so
-        // chunk m is complete -- and its MMAs run -- while term m+1 is being diffused; slot = 1 + ((m-1) & 1)
-        int dbg_t = 0, dbg_ph = 0;
+        // diffusion of one phase: one warp per (sample, term): 64 columns, two per lane (each P^T row read from shared memory
+        // feeds 40 FMAs: with one column per lane the loop was bound by the LDS issue rate at ~55 FMA/clk/SM, measured
+        // with scripts/micro/fma_rate.cu).  M = 3: terms 1 and 2 run side by side on warps 0-3 / 4-7; M = 5: two rounds,
+        // the MMAs of round one overlap the diffusion of round two.  A task arrives with count 2 (4 tasks = 8 arrivals).
         auto diffuse_phase = [&]() {
             for (int m = 1; m < M; ++m) {
                 const int slot = 1 + ((m - 1) & 1);
-                const bool rec2 = p.dbg && blockIdx.x == 0 && tid == 0 && m == 1 && dbg_t < 64;
-                long long* ds = rf_dbg + 1024 + dbg_t * 8 + dbg_ph * 4;
-                if (rec2) ds[0] = clock64();
-                acquire(slot, true);
-                if (rec2) ds[1] = clock64();
-                float acc[NPAD];
-                diffuse1(ZH + (quad * RP) * RF_ZLD + half * 32 + lane, RF_ZLD, N, PTs + (quad * (M - 1) + (m - 1)) * PT_STRIDE, acc);
-                // (rows N..23 are dumped to the operand image and aliased by the staging tiles: rewrite them as zeros)
-                if (rec2) ds[2] = clock64();
-                store_col1(Aslots + slot * SLOT, quad * RP, half * 32 + lane, N, RG * 8, acc, 1.f);
-                if (rec2) ds[3] = clock64();
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_afull[slot]);
+                const int s = (warp - ((m - 1) * SB)) & 7;
+                if (s < SB) {
+                    acquire(slot, true);
+                    float acc[NPAD][2];
+                    diffuse2(ZH + (s * RP) * RF_ZLD + 2 * lane, RF_ZLD, N, PTs + (s * (M - 1) + (m - 1)) * PT_STRIDE, acc);
+                    // (rows N..23 are dumped to the operand image and aliased by the staging tiles: rewrite them as zeros)
+                    store_cols2(Aslots + slot * SLOT, s * RP, lane, N, acc, 1.f, RG * 8);
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_n(&bar_afull[slot], 2);
+                }
                 ++fills[slot];
             }
         };
@@ -306,7 +304,6 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
             long long* es = rf_dbg + t * 16;
             if (rec) es[0] = clock64();
             // ---- gate ------------------------------------------------------------------------------------------------
-            dbg_t = t; dbg_ph = 0;
             diffuse_phase();
             if (rec) es[1] = clock64();
             mbar_wait(&bar_gate, t & 1);
@@ -334,7 +331,6 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
             rf_worker_bar();                                            // r*h of every row is visible
             if (rec) es[4] = clock64();
             // ---- candidate ---------------------------------------------------------------------------------------------
-            dbg_ph = 1;
             diffuse_phase();
             if (rec) es[5] = clock64();
             mbar_wait(&bar_cand, t & 1);

@@ -201,6 +201,7 @@ int dcgru_decoder_bwd(const dcgru_cell_desc *d, int32_t num_layers, int32_t batc
  *         img (may be NULL): fp16 operand image [tile*T+t][hi|lo][96][img_cols], columns from img_col0
  * mode 1: out (T,B,N,fin) = sum_m P_m^T (src_t W_x,m^T), src = dA (T,B,N,3H)   (its BPTT)                   */
 int dcgru_debug_rnn_fwd_stamps(long long *out, int32_t n);   /* clock64 timeline of CTA 0 (DCGRU_DBG & 16) */
+int dcgru_debug_rnn_bwd_stamps(long long *out, int32_t n);   /* same for the BPTT kernel (DCGRU_DBG & 32) */
 size_t dcgru_debug_bulk_dp_workspace(int32_t mode, int32_t input_dim, int32_t hid_dim, int32_t num_matrices);
 int dcgru_debug_bulk_dp(int32_t mode, int32_t batch, int32_t seq_len, int32_t num_nodes, int32_t input_dim,
                         int32_t hid_dim, int32_t num_matrices, const float *src, const float *P,

@@ -55,7 +55,7 @@ CONFIGS = {
 }
 N_NODES, F_IN = 19, 100
 METRIC = "EEG clips/sec (fwd+bwd, T=60, N=19)"
-DTYPE = "f32 (3xTF32 on tcgen05, fp32 accumulate)"
+DTYPE = "f32 (2xFP16 split operands on tcgen05 kind::f16, 3 MMAs per product, fp32 accumulate: 22-bit significands)"
 
 
 def fcell(c, h, s, k):
@@ -563,13 +563,13 @@ def main():
     roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback",
-                "frac_of_3xtf32_attainable": achieved / (peak / 6.0),
+                "frac_of_split_attainable": achieved / (peak / 3.0),
                 "tensor_pipe_active_pct": tensor_pct,
-                "profile_source": "profiles/ (ncu --set full of scripts/time_kernels.py at the same shapes; see "
-                                  "profiles/README.md for commit and command)",
-                "note": "kernels compute in fp32-equivalent 3xTF32 on tcgen05 (3 TF32 MMAs per product at half the bf16 "
-                        "rate: the attainable peak of this arithmetic is 1/6 of the bf16 peak); FLOPs are the "
-                        "as-written count of SURVEY 8(d)",
+                "profile_source": "profiles/ncu_*_r02.txt (ncu --set full --clock-control none on `bench.py --config 2 --steps 2 "
+                                  "--no-extra --no-cpu-baseline`; see profiles/README.md for commit and command)",
+                "note": "kernels compute in fp32-equivalent 2xFP16 on tcgen05 (3 kind::f16 MMAs per product at the bf16 rate: "
+                        "the attainable peak of this arithmetic is 1/3 of the bf16 peak); FLOPs are the as-written count of "
+                        "SURVEY 8(d); H=128 cells and the decoder run on the fp32 FMA kernels",
                 "all_kernels_tflops": total_alg / (total_kms * 1e-3) / 1e12,
                 "whole_step_tflops": step_tflops, "whole_step_frac": step_tflops / peak}
 

@@ -337,10 +337,11 @@ int dcgru_corr_supports(int32_t batch, int32_t seq_len, int32_t num_nodes, int32
     return 0;
 }
 
-// second-generation path (2xFP16: bulk_dp.cu + rnn_fwd.cu [+ rnn_bwd.cu + dw_mm16.cu]); DCGRU_G2=0 keeps the 3xTF32 kernels
+// second-generation path (2xFP16: bulk_dp.cu, rnn_fwd.cu, rnn_bwd.cu, dw_mm16.cu) is the default for H = 64 cells;
+// DCGRU_G2=0 selects the first-generation 3xTF32 kernels (H = 64, M = 3 only), DCGRU_DISABLE_TC=1 the fp32 FMA kernels
 static bool g2_enabled() {
     const char* e = getenv("DCGRU_G2");
-    return tc_enabled() && e && e[0] == '1';
+    return tc_enabled() && !(e && e[0] == '0');
 }
 static bool g2_fwd_supported(const dcgru_cell_desc* d) {
     const int M = Mof(d);

@@ -81,6 +81,41 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
     for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
 }
 
+// the same without the wait: issue several loads back to back, then tmem_wait_ld() once (the registers are valid after it)
+__device__ __forceinline__ void tmem_ld8_nw(uint32_t taddr, float (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "r"(taddr) : "memory");
+}
+// TMEM loads are paid per INSTRUCTION (measured: an epilogue made of x8 loads spent ~1k cycles per 8-column chunk with
+// nothing else in it; eight warps share the load path), so the epilogues use the widest shapes the register budget allows
+__device__ __forceinline__ void tmem_ld16_nw(uint32_t taddr, float (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),
+          "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nw(uint32_t taddr, float (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),
+          "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]),
+          "=f"(v[16]), "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]),
+          "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+// registers -> TMEM, 32 lanes x 8 consecutive columns, no wait (tmem_wait_st() before the data is consumed elsewhere)
+__device__ __forceinline__ void tmem_st8_nw(uint32_t taddr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n"
+                 ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
 // ---- fp32 -> (hi, lo) fp16 pairs ----------------------------------------------------------------------------------
 __device__ __forceinline__ float clamp_h(float x) { return fminf(fmaxf(x, -65000.f), 65000.f); }
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
@@ -222,8 +257,27 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, int c0, int c1, c
                  ::"l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(smem_src)) : "memory");
 }
 
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+// Gate activations on the MUFU pipe with the flush-to-zero forms written out in PTX: __expf / __fdividef without
+// -ftz expand into denormal fix-up code (FSETP / FSEL / extra FMULs: ~44 instructions per (tanh, sigmoid) pair in the
+// first version of the epilogue, which made it the longest phase of a step).  ex2.approx / rcp.approx are accurate
+// to ~2^-22 relative; the clamps keep every intermediate finite (sigmoid(-30) = 9e-14, tanh(15) = 1 - 2e-13).
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+constexpr float LOG2E = 1.4426950408889634f;
+__device__ __forceinline__ float fast_sigmoid(float x) {
+    return rcp_ftz(1.f + ex2_ftz(-LOG2E * fminf(fmaxf(x, -30.f), 30.f)));
+}
+__device__ __forceinline__ float fast_tanh(float x) {
+    return fmaf(-2.f, rcp_ftz(1.f + ex2_ftz((2.f * LOG2E) * fminf(fmaxf(x, -15.f), 15.f))), 1.f);
+}
+// c = tanh(a), u = sigmoid(b) with ONE reciprocal: 1/A = B/(AB), 1/B = A/(AB)  (A = 1 + e^{2a}, B = 1 + e^{-b}; AB < 1e27)
+__device__ __forceinline__ void tanh_sigmoid(float a, float b, float& c, float& u) {
+    const float A = 1.f + ex2_ftz((2.f * LOG2E) * fminf(fmaxf(a, -15.f), 15.f));
+    const float Bq = 1.f + ex2_ftz(-LOG2E * fminf(fmaxf(b, -30.f), 30.f));
+    const float rinv = rcp_ftz(A * Bq);
+    c = fmaf(-2.f * Bq, rinv, 1.f);
+    u = A * rinv;
+}
 
 }  // namespace f16
 }  // namespace dcgru

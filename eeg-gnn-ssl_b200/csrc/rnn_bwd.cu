@@ -309,32 +309,37 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
             uint8_t* slu = acquire();                                   // chunk [dA_u]
             --seq;
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                float u[8], c[8], hp[8], g[8];
-                tmem_ld8(tb + RB_U + 8 * cc, u);
-                tmem_ld8(tb + RB_C + 8 * cc, c);
-                tmem_ld8(tb + RB_HP + 8 * cc, hp);
-                tmem_ld8(tb + RB_DUP + 8 * cc, g);
+            for (int cc = 0; cc < 2; ++cc) {                            // 16 columns at a time (TMEM loads are paid per instruction)
+                float u[16], c[16], hp[16], g[16], a2[16];
+                tmem_ld16_nw(tb + RB_U + 16 * cc, u);
+                tmem_ld16_nw(tb + RB_C + 16 * cc, c);
+                tmem_ld16_nw(tb + RB_HP + 16 * cc, hp);
+                tmem_ld16_nw(tb + RB_DUP + 16 * cc, g);
+                if (k >= 1) tmem_ld16_nw(tb + RB_ACC2 + 16 * cc, a2);
+                tmem_wait_ld();
                 if (k >= 1) {
-                    float a2[8];
-                    tmem_ld8(tb + RB_ACC2 + 8 * cc, a2);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) g[j] += a2[j] * inv_gs;
+                    for (int j = 0; j < 16; ++j) g[j] += a2[j] * inv_gs;
                 }
-                float dac[8], dau[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float dh = rvalid ? dhp[8 * cc + j] + g[j] : 0.f;
-                    const float du = dh * (hp[j] - c[j]);
-                    const float dc = dh * (1.f - u[j]);
-                    dac[j] = (p.act == 0) ? dc * (1.f - c[j] * c[j]) : (c[j] > 0.f ? dc : 0.f);
-                    dau[j] = du * u[j] * (1.f - u[j]);
-                    dhp[8 * cc + j] = dh * u[j];
+                for (int h8 = 0; h8 < 2; ++h8) {
+                    float dac[8], dau[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int e = 8 * h8 + j;
+                        const float dh = rvalid ? dhp[16 * cc + e] + g[e] : 0.f;
+                        const float du = dh * (hp[e] - c[e]);
+                        const float dc = dh * (1.f - u[e]);
+                        dac[j] = (p.act == 0) ? dc * (1.f - c[e] * c[e]) : (c[e] > 0.f ? dc : 0.f);
+                        dau[j] = du * u[e] * (1.f - u[e]);
+                        dhp[16 * cc + e] = dh * u[e];
+                    }
+                    const int col = half * 32 + 16 * cc + 8 * h8;
+                    put8f(SA, col, dac);
+                    put8f(SBt, col, dau);
+                    put8(slc, col, dac);
+                    put8(slu, col, dau);
                 }
-                put8f(SA, half * 32 + 8 * cc, dac);
-                put8f(SBt, half * 32 + 8 * cc, dau);
-                put8(slc, half * 32 + 8 * cc, dac);
-                put8(slu, half * 32 + 8 * cc, dau);
             }
             tc_fence_before();
             __syncwarp();
@@ -355,19 +360,26 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
             // ---- E2 ----------------------------------------------------------------------------------------------------
             uint8_t* slr = acquire();                                   // chunk [dA_r]
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                float a1[8], hp[8], r[8], dar[8];
-                tmem_ld8(tb + RB_ACC1 + 8 * cc, a1);
-                tmem_ld8(tb + RB_HP + 8 * cc, hp);
-                tmem_ld8(tb + RB_R + 8 * cc, r);
+            for (int cc = 0; cc < 2; ++cc) {
+                float a1[16], hp[16], r[16];
+                tmem_ld16_nw(tb + RB_ACC1 + 16 * cc, a1);
+                tmem_ld16_nw(tb + RB_HP + 16 * cc, hp);
+                tmem_ld16_nw(tb + RB_R + 16 * cc, r);
+                tmem_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float drh = rvalid ? a1[j] * inv_gs : 0.f;
-                    dar[j] = drh * hp[j] * r[j] * (1.f - r[j]);
-                    dhp[8 * cc + j] += drh * r[j];
+                for (int h8 = 0; h8 < 2; ++h8) {
+                    float dar[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int e = 8 * h8 + j;
+                        const float drh = rvalid ? a1[e] * inv_gs : 0.f;
+                        dar[j] = drh * hp[e] * r[e] * (1.f - r[e]);
+                        dhp[16 * cc + e] += drh * r[e];
+                    }
+                    const int col = half * 32 + 16 * cc + 8 * h8;
+                    put8f(SA, col, dar);                                // (bar_b1: every warp is past its reads of SA = dA_c)
+                    put8(slr, col, dar);
                 }
-                put8f(SA, half * 32 + 8 * cc, dar);                     // (bar_b1: every warp is past its reads of SA = dA_c)
-                put8(slr, half * 32 + 8 * cc, dar);
             }
             tc_fence_before();
             __syncwarp();

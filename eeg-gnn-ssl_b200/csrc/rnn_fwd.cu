@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
             for (int t = 0; t < T; ++t) {
                 const int acc_i = t & 1;
                 const uint32_t dacc = taddr + acc_i * RF_ACC1;
-                const bool rec = p.dbg && blockIdx.x == 0 && t < 64;
+                const bool rec = (p.dbg & 16) && blockIdx.x == 0 && t < 64;
                 if (rec) rf_dbg[t * 16 + 10] = clock64();
                 mbar_wait(&bar_xpfull[acc_i], (t >> 1) & 1);            // XP_t sits in the accumulator
                 if (rec) rf_dbg[t * 16 + 11] = clock64();
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
             for (int t = 0; t < T; ++t)
                 for (int q = 0; q < per_step; ++q, ++pc) {
                     const int ws = pc % RF_NW;
-                    if (pc >= RF_NW) mbar_wait(&bar_wempty[ws], ((pc / RF_NW) - 1) & 1);
+                    if (pc >= RF_NW) mbar_wait_relaxed(&bar_wempty[ws], ((pc / RF_NW) - 1) & 1);
                     const bool gate = q < 2 * M;
                     const uint32_t bytes = gate ? RF_WSLOT : RF_WSLOT / 2;
                     const uint8_t* src = gate ? p.wimg + (size_t)q * RF_WSLOT : wc + (size_t)(q - 2 * M) * (RF_WSLOT / 2);
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
                 for (int ci = 0; ci < 2 * M; ++ci) {
                     const int m = ci < M ? ci : ci - M;
                     const int slot = m == 0 ? 0 : 1 + ((m - 1) & 1);
-                    mbar_wait(&bar_afull[slot], fills[slot] & 1);
+                    mbar_wait_relaxed(&bar_afull[slot], fills[slot] & 1);
                     ++fills[slot];
                     if (lane < 2 * SB) {
                         tma_store_2d(&tm_img, p.img_col0 + 64 * ci, (int)((slab * 2 + plane) * IMG_ROWS + s * (RG * 8)),
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
         const uint32_t lane_base = (uint32_t)(32 * quad) << 16;
         for (int t = 0; t < T; ++t) {
             const int acc_i = t & 1;
-            if (t >= 2) mbar_wait(&bar_accfree[acc_i], ((t >> 1) - 1) & 1);
+            if (t >= 2) mbar_wait_relaxed(&bar_accfree[acc_i], ((t >> 1) - 1) & 1, 512);
             tc_fence_after();
             const float4* src = reinterpret_cast<const float4*>(p.xp + (((size_t)t * p.B + (valid ? b : 0)) * N + (valid ? n : 0)) * (3 * RF_H));
 #pragma unroll 1
@@ -257,6 +257,16 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
                 *reinterpret_cast<uint4*>(Aslots + PLANE + off) = lo;
             }
         };
+        auto put_state8 = [&](int col, const float (&v)[8]) {          // 8 columns of this row
+            float4* z4 = reinterpret_cast<float4*>(ZH + row * RF_ZLD + col);
+            z4[0] = make_float4(v[0], v[1], v[2], v[3]);
+            z4[1] = make_float4(v[4], v[5], v[6], v[7]);
+            uint4 hi, lo;
+            split8(v, hi, lo);
+            const uint32_t off = k128_off(row, col);
+            *reinterpret_cast<uint4*>(Aslots + off) = hi;
+            *reinterpret_cast<uint4*>(Aslots + PLANE + off) = lo;
+        };
         auto publish_slot0 = [&]() {
             fence_async_smem();
             __syncwarp();
@@ -300,7 +310,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
         for (int t = 0; t < T; ++t) {
             const uint32_t dacc = taddr + lane_base + (t & 1) * RF_ACC1;
             float* hout = p.hseq + (size_t)t * p.B * NH;
-            const bool rec = p.dbg && blockIdx.x == 0 && tid == 0 && t < 64;
+            const bool rec = (p.dbg & 16) && blockIdx.x == 0 && tid == 0 && t < 64;
             long long* es = rf_dbg + t * 16;
             if (rec) es[0] = clock64();
             // ---- gate ------------------------------------------------------------------------------------------------
@@ -309,8 +319,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
             mbar_wait(&bar_gate, t & 1);
             tc_fence_after();
             if (rec) es[2] = clock64();
-            {   // epilogue 1: r = sigmoid(gate[:, 0:H]) -> r*h.  (r itself is re-derived from the accumulator in
-                // epilogue 2 for the ruc store: the candidate MMAs do not touch these columns)
+            {   // epilogue 1: r = sigmoid(gate[:, 0:H]) -> r*h  (one 32-column TMEM load per thread: loads are paid per instruction)
                 float rk[32], v[32];
                 tmem_ld32(dacc + half * 32, rk);
                 const float4* z4 = reinterpret_cast<const float4*>(ZH + row * RF_ZLD + half * 32);
@@ -336,29 +345,21 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
             mbar_wait(&bar_cand, t & 1);
             tc_fence_after();
             if (rec) es[6] = clock64();
-            {
+            {   // epilogue 2: 64 columns, each warp half takes 32.  Everything it needs is on chip: the candidate and update-gate
+                // pre-activations in the accumulator, h_{t-1} and r in the TMEM stashes.
                 float cv[32], uv[32], hp[32];
-                tmem_ld32(dacc + 2 * RF_H + half * 32, cv);
-                tmem_ld32(dacc + RF_H + half * 32, uv);
-                tmem_ld32(taddr + lane_base + RF_STASH + half * 32, hp);
+                tmem_ld32_nw(dacc + 2 * RF_H + half * 32, cv);
+                tmem_ld32_nw(dacc + RF_H + half * 32, uv);
+                tmem_ld32_nw(taddr + lane_base + RF_STASH + half * 32, hp);
+                tmem_wait_ld();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_accfree[t & 1]);        // the accumulator may take XP_{t+2}
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     float c, u;
-                    if (p.act == 0) {
-                        // tanh(a) = 1 - 2/(1+e^{2a}), sigmoid(b) = 1/(1+e^{-b}) with ONE reciprocal for both (the MUFU pipe,
-                        // 16 lanes/clk/SM, is what bounds the epilogues): 1/A = B/(AB), 1/B = A/(AB); the clamps keep AB finite
-                        const float ea = __expf(2.f * fminf(fmaxf(cv[j], -15.f), 15.f)), eb = __expf(-fminf(fmaxf(uv[j], -30.f), 30.f));
-                        const float A = 1.f + ea, Bq = 1.f + eb;
-                        const float rinv = __fdividef(1.f, A * Bq);
-                        c = 1.f - 2.f * (Bq * rinv);
-                        u = A * rinv;
-                    } else {
-                        c = fmaxf(cv[j], 0.f);
-                        u = fast_sigmoid(uv[j]);
-                    }
+                    if (p.act == 0) tanh_sigmoid(cv[j], uv[j], c, u);
+                    else { c = fmaxf(cv[j], 0.f); u = fast_sigmoid(uv[j]); }
                     cv[j] = c; uv[j] = u;
                     hp[j] = rvalid ? u * hp[j] + (1.f - u) * c : 0.f;
                 }
@@ -411,7 +412,7 @@ cudaError_t launch_rnn_fwd(int B, int T, int N, int fin, int M, int act, const f
     RnnFwdParams p;
     memset(&p, 0, sizeof p);
     p.B = B; p.T = T; p.N = N; p.M = M; p.act = act; p.dump = img != nullptr; p.img_col0 = img_col0;
-    { const char* e = getenv("DCGRU_DBG"); p.dbg = e ? (atoi(e) & 16) : 0; }
+    { const char* e = getenv("DCGRU_DBG"); p.dbg = e ? (atoi(e) & (16 | 64 | 128 | 256 | 512)) : 0; }
     p.xp = xp; p.h0 = h0; p.P = P; p.wimg = reinterpret_cast<const uint8_t*>(wimg); p.hseq = hseq; p.ruc = ruc;
     CUtensorMap tm;
     memset(&tm, 0, sizeof tm);

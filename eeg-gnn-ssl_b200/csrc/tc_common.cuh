@@ -136,16 +136,37 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
-// bounded spin: a lost arrival traps instead of hanging the GPU
+// bounded wait: a lost arrival traps instead of hanging the GPU.  try_wait carries a suspend-time hint (ns): the
+// hardware parks the warp until the phase completes instead of returning after a short internal time-out.  Without
+// the hint a dozen waiting warps re-issued try_wait back to back -- mbarrier instructions execute on the XU pipe (16
+// lanes/clk/SM, shared with MUFU and the fp16 conversions): ncu showed it 100 % busy over the whole rnn_fwd kernel and
+// 36 % of all executed warp instructions were SYNCS/BRA of these loops, which starved the epilogues.
+constexpr uint32_t MBAR_SUSPEND_NS = 1000000u;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done = 0;
-    for (uint32_t it = 0; it < (1u << 26); ++it) {
+    for (uint32_t it = 0; it < (1u << 22); ++it) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(MBAR_SUSPEND_NS) : "memory");
+        if (done) return;
+    }
+    asm volatile("trap;\n");
+}
+
+// for warps that are far off the critical path (ring loaders that run steps ahead, the image dump): poll with plain
+// test_wait and sleep in between, so that the waiting does not compete with the working warps for issue slots
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned ns = 256) {
+    uint32_t done = 0;
+    for (uint32_t it = 0; it < (1u << 24); ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}\n"
             : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
         if (done) return;
+        __nanosleep(ns);
     }
     asm volatile("trap;\n");
 }
@@ -223,14 +244,14 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t l
 __device__ __forceinline__ void mbar_wait2(uint64_t* b0, uint32_t p0, uint64_t* b1, uint32_t p1) {
     const uint32_t a0 = smem_u32(b0), a1 = smem_u32(b1);
     uint32_t d0 = 0, d1 = 0;
-    for (uint32_t it = 0; it < (1u << 26); ++it) {
+    for (uint32_t it = 0; it < (1u << 22); ++it) {
         asm volatile(
             "{\n\t.reg .pred p, q;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%2], %3;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 q, [%4], %5;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%2], %3, %6;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 q, [%4], %5, %6;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t"
             "selp.u32 %1, 1, 0, q;\n\t}\n"
-            : "=r"(d0), "=r"(d1) : "r"(a0), "r"(p0), "r"(a1), "r"(p1) : "memory");
+            : "=r"(d0), "=r"(d1) : "r"(a0), "r"(p0), "r"(a1), "r"(p1), "r"(MBAR_SUSPEND_NS) : "memory");
         if (d0 & d1) return;
     }
     asm volatile("trap;\n");
@@ -238,16 +259,16 @@ __device__ __forceinline__ void mbar_wait2(uint64_t* b0, uint32_t p0, uint64_t* 
 __device__ __forceinline__ void mbar_wait3(uint64_t* b0, uint32_t p0, uint64_t* b1, uint32_t p1, uint64_t* b2, uint32_t p2) {
     const uint32_t a0 = smem_u32(b0), a1 = smem_u32(b1), a2 = smem_u32(b2);
     uint32_t d0 = 0, d1 = 0, d2 = 0;
-    for (uint32_t it = 0; it < (1u << 26); ++it) {
+    for (uint32_t it = 0; it < (1u << 22); ++it) {
         asm volatile(
             "{\n\t.reg .pred p, q, r;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%3], %4;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 q, [%5], %6;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 r, [%7], %8;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%3], %4, %9;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 q, [%5], %6, %9;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 r, [%7], %8, %9;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t"
             "selp.u32 %1, 1, 0, q;\n\t"
             "selp.u32 %2, 1, 0, r;\n\t}\n"
-            : "=r"(d0), "=r"(d1), "=r"(d2) : "r"(a0), "r"(p0), "r"(a1), "r"(p1), "r"(a2), "r"(p2) : "memory");
+            : "=r"(d0), "=r"(d1), "=r"(d2) : "r"(a0), "r"(p0), "r"(a1), "r"(p1), "r"(a2), "r"(p2), "r"(MBAR_SUSPEND_NS) : "memory");
         if (d0 & d1 & d2) return;
     }
     asm volatile("trap;\n");

@@ -2,7 +2,7 @@
 usage: python scripts/dbg_rnn_fwd.py [M: 3|5] [fin]"""
 import ctypes as C, os, sys, numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ["DCGRU_DBG"] = "16"
+os.environ["DCGRU_DBG"] = os.environ.get("DCGRU_DBG", "16")
 os.environ["DCGRU_G2"] = "1"
 from eeg_gnn_ssl_b200 import _lib, ops
 from eeg_gnn_ssl_b200.model.cell import DCGRUCell
@@ -28,4 +28,5 @@ print("step | worker: start gate-diffused gate-MMA-done epi1-done barrier cand-d
 for t in range(T):
     print(t, *(int(v - t0) for v in d[t, :10]), "|", *(int(v - t0) for v in d[t, 10:14]))
 print("per-step deltas (worker), step 5:", [int(d[5, i + 1] - d[5, i]) for i in range(9)], "total", int(d[6, 0] - d[5, 0]))
-print("first diffusion term of step 5 (gate | cand): acquire, diffuse1, store ->", [int(e2[5, i + 1] - e2[5, i]) for i in range(3)], [int(e2[5, 4 + i + 1] - e2[5, 4 + i]) for i in range(3)])
+print("epilogue 2 of step 5 (from cand-MMA-done): tmem loads, math, acquire slot0, put_state, publish, [stash+] h store ->",
+      [int(e2[5, 0] - d[5, 6])] + [int(e2[5, i + 1] - e2[5, i]) for i in range(5)])

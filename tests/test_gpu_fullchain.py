@@ -131,12 +131,15 @@ def _cls_case(dev, B, T, H, K, L, ft, classes, lens, seed):
     return run_ours, ref64, ref32
 
 
-@pytest.mark.parametrize("path", ["tc_image", "tc_recompute", "fma"])
+@pytest.mark.parametrize("path", ["tc_image", "tc_recompute", "tc_g1_image", "tc_g1_recompute", "fma"])
 def test_config2_T60_vs_oracle(dev, monkeypatch, path):
-    """60 recurrent steps, 2 layers, distance graph: every kernel path against the fp64 oracle"""
-    if path == "tc_recompute":
+    """60 recurrent steps, 2 layers, distance graph: every kernel path against the fp64 oracle
+    (default = second-generation 2xFP16 kernels + fp16 operand images; tc_g1_* = first-generation 3xTF32 kernels)"""
+    if path.endswith("recompute"):
         monkeypatch.setenv("DCGRU_DISABLE_GSAVE", "1")
-    elif path == "fma":
+    if path.startswith("tc_g1"):
+        monkeypatch.setenv("DCGRU_G2", "0")
+    if path == "fma":
         monkeypatch.setenv("DCGRU_DISABLE_TC", "1")
     B, T = 24, 60
     run_ours, ref64, ref32 = _cls_case(dev, B, T, 64, 2, 2, "laplacian", 1, [T] * B, seed=11)

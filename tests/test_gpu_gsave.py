@@ -11,6 +11,13 @@ import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def first_generation_path(monkeypatch):
+    """this file pins the FIRST-generation (3xTF32) operand images through the C ABI; the second-generation (2xFP16)
+    stages have their own file, tests/test_gpu_g2.py"""
+    monkeypatch.setenv("DCGRU_G2", "0")
 N, H, K = 19, 64, 2
 SB, IMG_ROWS = 4, 96            # samples per CTA; image rows per (cta, t, hi|lo) = 4 samples x 24 rows (tc_common.cuh)
 

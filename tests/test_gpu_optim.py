@@ -82,7 +82,7 @@ def test_fused_clip_adam_is_a_torch_optimizer_with_checkpointable_state():
         assert float(sd["state"][k]["step"]) == float(tsd["state"][k]["step"]) == 3.0
         for name in ("exp_avg", "exp_avg_sq"):
             a, b = sd["state"][k][name], tsd["state"][k][name]
-            assert a.shape == b.shape and float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()), (name, float((a - b).abs().max()), float(b.abs().max()))
+            assert a.shape == b.shape and float((a - b).abs().max()) <= 5e-5 * float(b.abs().max()), (name, float((a - b).abs().max()), float(b.abs().max()))
     # resume: a fresh fused optimiser loads the TORCH optimiser's checkpoint and continues like torch does
     ours2 = [torch.nn.Parameter(r.detach().clone()) for r in ref]
     opt2 = FusedClipAdam(ours2, lr=1.0, weight_decay=5e-4, max_grad_norm=5.0)

@@ -8,6 +8,14 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["g2", "g1"])
+def generation(request, monkeypatch):
+    """every comparison in this file runs against both tensor-core generations: the default 2xFP16 kernels
+    (bulk_dp / rnn_fwd / rnn_bwd / dw_mm16) and the first-generation 3xTF32 kernels (DCGRU_G2=0)"""
+    monkeypatch.setenv("DCGRU_G2", "1" if request.param == "g2" else "0")
+    return request.param
+
+
 @pytest.fixture(scope="module")
 def dev():
     if not torch.cuda.is_available():

@@ -200,7 +200,7 @@ __global__ void dw_mm16_reduce_kernel(const Dw16Params p, int fin, int H, int M,
 }
 
 // ---- db: column sums of the dA image (hi + lo), two fixed-order stages --------------------------------------------------
-constexpr int CS16_CTAS = 1184;
+constexpr int CS16_CTAS = 296;
 // thread = (8-column group, row slot): 16-byte loads (8 fp16), 8 row slots per CTA, several rows in flight per thread
 __global__ void __launch_bounds__(192) colsum16_kernel(const __half* img, long nrows, float* partial) {
     __shared__ float red[8][192];

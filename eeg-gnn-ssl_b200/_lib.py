@@ -14,6 +14,8 @@ SYMBOLS = [
     "dcgru_debug_dwmm_stamps", "dcgru_debug_dwmm_plan", "dcgru_tc_probe",
     "dcgru_clip_adam_workspace", "dcgru_clip_adam_step",
     "dcgru_debug_bulk_dp_workspace", "dcgru_debug_bulk_dp", "dcgru_debug_rnn_fwd_stamps", "dcgru_debug_rnn_bwd_stamps",
+    "dcgru_cls_head_fwd", "dcgru_cls_head_bwd_workspace", "dcgru_cls_head_bwd",
+    "dcgru_encoder_layer_bwd_sel_workspace", "dcgru_encoder_layer_bwd_sel",
 ]
 
 MAX_LAYERS = 4
@@ -80,13 +82,22 @@ def lib():
     L.dcgru_debug_bulk_dp_workspace.argtypes = [i32, i32, i32, i32]
     L.dcgru_debug_bulk_dp_workspace.restype = sz
     L.dcgru_debug_bulk_dp.argtypes = [i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp, sz, vp]
+    L.dcgru_cls_head_fwd.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.dcgru_cls_head_bwd_workspace.argtypes = [i32, i32, i32]
+    L.dcgru_cls_head_bwd_workspace.restype = sz
+    L.dcgru_cls_head_bwd.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.dcgru_encoder_layer_bwd_sel_workspace.argtypes = [pd, i32, i32]
+    L.dcgru_encoder_layer_bwd_sel_workspace.restype = sz
+    L.dcgru_encoder_layer_bwd_sel.argtypes = [pd, i32, i32, vp, i64, i64, vp, vp, pp, vp, vp, vp, vp, vp, vp, vp, pg,
+                                              vp, sz, vp, sz, vp]
     L.dcgru_timing_enable.argtypes = [C.c_int]
     L.dcgru_timing_collect.argtypes = [C.c_char_p, sz]
     for name in SYMBOLS:
         if name not in ("dcgru_last_error", "dcgru_encoder_layer_bwd_workspace", "dcgru_encoder_layer_fwd_workspace",
                         "dcgru_encoder_layer_gsave_bytes", "dcgru_clip_adam_workspace",
                         "dcgru_decoder_fwd_workspace", "dcgru_decoder_bwd_workspace",
-                        "dcgru_debug_bulk_dp_workspace"):
+                        "dcgru_debug_bulk_dp_workspace", "dcgru_cls_head_bwd_workspace",
+                        "dcgru_encoder_layer_bwd_sel_workspace"):
             getattr(L, name).restype = C.c_int
     _lib = L
     return L

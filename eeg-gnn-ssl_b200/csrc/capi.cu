@@ -568,12 +568,17 @@ int dcgru_debug_encoder_bwd_offsets(const dcgru_cell_desc* d, int32_t batch, int
     return 0;
 }
 
-int dcgru_encoder_layer_bwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq_len, const float* x,
-                            int64_t x_stride_t, int64_t x_stride_b, const float* h0, const float* P,
-                            const dcgru_cell_params* w, const float* h_seq, const float* ruc,
-                            const float* d_hseq, const float* d_hlast, float* dx, float* dh0,
-                            const dcgru_cell_grads* g, const void* gsave, size_t gsave_bytes,
-                            void* workspace, size_t workspace_bytes, void* stream) {
+// d_hsel / sel_t: the sparse form of d_hseq (sample b's (N*H) slab belongs to step sel_t[b]; dcgru_cls_head_bwd writes it)
+static size_t sel_dense_bytes(const dcgru_cell_desc* d, int B, int T) {
+    return align_up((size_t)T * B * d->num_nodes * d->hid_dim * 4);
+}
+static int encoder_layer_bwd_impl(const dcgru_cell_desc* d, int32_t batch, int32_t seq_len, const float* x,
+                                  int64_t x_stride_t, int64_t x_stride_b, const float* h0, const float* P,
+                                  const dcgru_cell_params* w, const float* h_seq, const float* ruc,
+                                  const float* d_hseq, const float* d_hlast, const float* d_hsel, const int32_t* sel_t,
+                                  float* dx, float* dh0,
+                                  const dcgru_cell_grads* g, const void* gsave, size_t gsave_bytes,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
     if (check_desc(d)) return 1;
     if (batch < 1 || seq_len < 1) return fail("empty batch/sequence");
     if (!x || !h0 || !w || !h_seq || !ruc || !dh0 || !g || !workspace) return fail("null pointer");
@@ -581,8 +586,18 @@ int dcgru_encoder_layer_bwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
     const int M = Mof(d), H = d->hid_dim, fin = d->input_dim, CM = (fin + H) * M;
     if (M > 1 && !P) return fail("null P");
     if (!aligned16(workspace) || !aligned16(h_seq) || !aligned16(ruc)) return fail("unaligned pointer");
-    if (dcgru_encoder_layer_bwd_workspace(d, batch, seq_len) > workspace_bytes) return fail("workspace too small");
+    const size_t base_ws = dcgru_encoder_layer_bwd_workspace(d, batch, seq_len);
+    if ((d_hsel ? align_up(base_ws) + sel_dense_bytes(d, batch, seq_len) : base_ws) > workspace_bytes) return fail("workspace too small");
+    if (d_hsel && d_hseq) return fail("pass either the dense d_hseq or the sparse d_hsel, not both");
+    if (d_hsel && !aligned16(d_hsel)) return fail("unaligned d_hsel");
     cudaStream_t st = (cudaStream_t)stream;
+    const bool g2_path = g2_bwd_supported(d) && (!dx || bulk_dp_supported(d->num_nodes, 3 * H, M, fin, true, devinfo().smem));
+    if (d_hsel && !g2_path) {
+        // the first-generation / fp32 kernels take a dense gradient: expand the slab behind the regular workspace
+        float* dense = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align_up(base_ws));
+        LAUNCH("scatter_sel", launch_scatter_sel(batch, seq_len, d->num_nodes * H, d_hsel, sel_t, dense, st));
+        d_hseq = dense; d_hsel = nullptr; sel_t = nullptr;
+    }
     float *WgT, *WcT, *dA, *part, *partb, *ptbuf, *daimg, *mmpart, *cspart;
     int nsplit, njobs;
     DwParams q;
@@ -610,8 +625,7 @@ int dcgru_encoder_layer_bwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
     p.cell[0] = CellWT{WgT, WcT, fin};
     p.P = P; p.h0 = h0; p.hseq = h_seq; p.ruc = ruc; p.d_hseq = d_hseq; p.d_hlast = d_hlast;
     p.dx = dx; p.dh0 = dh0; p.dA = dA;
-    const bool g2_dx_ok = !dx || bulk_dp_supported(d->num_nodes, 3 * H, M, fin, true, devinfo().smem);
-    if (g2_bwd_supported(d) && g2base && g2_dx_ok) {
+    if (g2_path && g2base) {
         if (gsave) {
             const size_t need = gsave_bytes_for(d, batch, seq_len);
             if (need == 0) return fail("this configuration has no operand image: pass gsave = NULL");
@@ -625,9 +639,9 @@ int dcgru_encoder_layer_bwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
         float* scale = reinterpret_cast<float*>(wsb + ws.off_scale);
         const size_t nh = (size_t)batch * N * H;
         LAUNCH("grad_scale", launch_grad_scale(d_hseq, d_hseq ? (size_t)seq_len * nh : 0, d_hlast, d_hlast ? nh : 0,
-                                               reinterpret_cast<unsigned*>(scale + 8), scale, st));
+                                               d_hsel, d_hsel ? nh : 0, reinterpret_cast<unsigned*>(scale + 8), scale, st));
         LAUNCH("rnn_bwd", launch_rnn_bwd(batch, seq_len, N, fin, M, d->activation, h0, h_seq, ruc, P, w->Wg, w->Wc, d_hseq,
-                                         d_hlast, wsb + ws.off_wb, scale, dh0, wsb + ws.off_img, st));
+                                         d_hlast, d_hsel, sel_t, wsb + ws.off_wb, scale, dh0, wsb + ws.off_img, st));
         if (dx) {
             LAUNCH("pack_w16", launch_pack_w16(w->Wg, w->Wc, fin, H, M, 1, fin, g16_nq(3 * H, M), wsb + ws.off_wdx, st));
             LAUNCH("dx16", launch_bulk_dp(batch, seq_len, N, 3 * H, M, fin, 1, nullptr, 0, 0, wsb + ws.off_img, P, wsb + ws.off_wdx,
@@ -684,6 +698,67 @@ int dcgru_encoder_layer_bwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq
     else
         LAUNCH("dw", launch_dw(q, njobs, otile(3 * H), st));
     LAUNCH("reduce", launch_reduce_cell(part, partb, nsplit, CM, H, g->dWg, g->dbg, g->dWc, g->dbc, st));
+    return 0;
+}
+
+int dcgru_encoder_layer_bwd(const dcgru_cell_desc* d, int32_t batch, int32_t seq_len, const float* x,
+                            int64_t x_stride_t, int64_t x_stride_b, const float* h0, const float* P,
+                            const dcgru_cell_params* w, const float* h_seq, const float* ruc,
+                            const float* d_hseq, const float* d_hlast, float* dx, float* dh0,
+                            const dcgru_cell_grads* g, const void* gsave, size_t gsave_bytes,
+                            void* workspace, size_t workspace_bytes, void* stream) {
+    return encoder_layer_bwd_impl(d, batch, seq_len, x, x_stride_t, x_stride_b, h0, P, w, h_seq, ruc, d_hseq, d_hlast, nullptr,
+                                  nullptr, dx, dh0, g, gsave, gsave_bytes, workspace, workspace_bytes, stream);
+}
+
+size_t dcgru_encoder_layer_bwd_sel_workspace(const dcgru_cell_desc* d, int32_t batch, int32_t seq_len) {
+    if (check_desc(d) || batch < 1 || seq_len < 1) return 0;
+    return align_up(dcgru_encoder_layer_bwd_workspace(d, batch, seq_len)) + sel_dense_bytes(d, batch, seq_len);
+}
+
+int dcgru_encoder_layer_bwd_sel(const dcgru_cell_desc* d, int32_t batch, int32_t seq_len, const float* x,
+                                int64_t x_stride_t, int64_t x_stride_b, const float* h0, const float* P,
+                                const dcgru_cell_params* w, const float* h_seq, const float* ruc,
+                                const float* d_hsel, const int32_t* sel_t, const float* d_hlast, float* dx, float* dh0,
+                                const dcgru_cell_grads* g, const void* gsave, size_t gsave_bytes,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+    if (!d_hsel) return fail("null d_hsel");
+    return encoder_layer_bwd_impl(d, batch, seq_len, x, x_stride_t, x_stride_b, h0, P, w, h_seq, ruc, nullptr, d_hlast, d_hsel,
+                                  sel_t, dx, dh0, g, gsave, gsave_bytes, workspace, workspace_bytes, stream);
+}
+
+// ---- fused classification head (head.cu) ----------------------------------------------------------------------------------
+int dcgru_cls_head_fwd(int32_t batch, int32_t seq_len, int32_t num_nodes, int32_t hid_dim, int32_t num_classes,
+                       const float* h_seq, const int32_t* sel_t, const float* drop_mask, const float* fc_w, const float* fc_b,
+                       float* logits, int32_t* argmax_node, void* stream) {
+    if (batch < 1 || seq_len < 1) return fail("empty batch/sequence");
+    if (!cls_head_supported(num_nodes, hid_dim, num_classes))
+        return fail("cls_head: unsupported shape (N=%d H=%d classes=%d)", num_nodes, hid_dim, num_classes);
+    if (!h_seq || !fc_w || !fc_b || !logits || !argmax_node) return fail("null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    LAUNCH("cls_head_fwd", launch_cls_head_fwd(batch, seq_len, num_nodes, hid_dim, num_classes, h_seq, sel_t, drop_mask, fc_w,
+                                               fc_b, logits, argmax_node, st));
+    return 0;
+}
+
+size_t dcgru_cls_head_bwd_workspace(int32_t batch, int32_t hid_dim, int32_t num_classes) {
+    if (batch < 1 || hid_dim < 1 || num_classes < 1) return 0;
+    return align_up((size_t)batch * num_classes * hid_dim * 4);
+}
+
+int dcgru_cls_head_bwd(int32_t batch, int32_t seq_len, int32_t num_nodes, int32_t hid_dim, int32_t num_classes,
+                       const float* h_seq, const int32_t* sel_t, const float* drop_mask, const float* fc_w,
+                       const int32_t* argmax_node, const float* d_logits, float* d_hsel, float* d_fc_w, float* d_fc_b,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+    if (batch < 1 || seq_len < 1) return fail("empty batch/sequence");
+    if (!cls_head_supported(num_nodes, hid_dim, num_classes))
+        return fail("cls_head: unsupported shape (N=%d H=%d classes=%d)", num_nodes, hid_dim, num_classes);
+    if (!h_seq || !fc_w || !argmax_node || !d_logits || !d_hsel || !d_fc_w || !d_fc_b || !workspace) return fail("null pointer");
+    if (workspace_bytes < dcgru_cls_head_bwd_workspace(batch, hid_dim, num_classes)) return fail("workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    LAUNCH("cls_head_bwd", launch_cls_head_bwd(batch, seq_len, num_nodes, hid_dim, num_classes, h_seq, sel_t, drop_mask, fc_w,
+                                               argmax_node, d_logits, d_hsel, d_fc_w, d_fc_b, reinterpret_cast<float*>(workspace),
+                                               st));
     return 0;
 }
 

@@ -133,10 +133,13 @@ cudaError_t launch_rnn_fwd(int B, int T, int N, int fin, int M, int act, const f
 size_t rnn_bwd_wimg_bytes(int M);
 cudaError_t rnn_bwd_read_dbg(long long* out, int n);
 bool rnn_bwd_supported(int N, int H, int M, int smem_limit);
-cudaError_t launch_grad_scale(const float* a, size_t na, const float* b, size_t nb, unsigned* scratch, float* scale, cudaStream_t st);
+cudaError_t launch_grad_scale(const float* a, size_t na, const float* b, size_t nb, const float* c, size_t nc, unsigned* scratch,
+                              float* scale, cudaStream_t st);
+// d_hsel (B,N*H) / sel_t (B): sparse upstream gradient -- sample b's slab belongs to step sel_t[b] (head.cu); may be nullptr
 cudaError_t launch_rnn_bwd(int B, int T, int N, int fin, int M, int act, const float* h0, const float* hseq, const float* ruc,
                            const float* P, const float* Wg, const float* Wc, const float* d_hseq, const float* d_hlast,
-                           void* wimg, const float* scale_ptr, float* dh0, void* daimg, cudaStream_t st);
+                           const float* d_hsel, const int* sel_t, void* wimg, const float* scale_ptr, float* dh0, void* daimg,
+                           cudaStream_t st);
 cudaError_t launch_img_to_rows(const void* img, int B, int T, int N, int cols, const float* scale_ptr, float* out, cudaStream_t st);
 
 size_t dw_mm16_part_floats(int nsms);
@@ -146,5 +149,15 @@ cudaError_t launch_dw_mm16(int fin, int H, int M, int B, int T, const void* G, c
                            int nsms, float* dWg, float* dWc, cudaStream_t st);
 cudaError_t launch_colsum16(const void* daimg, int B, int T, int H, float* partial, const float* scale_ptr, float* dbg, float* dbc,
                             cudaStream_t st);
+
+
+// ---- fused classification head (head.cu) --------------------------------------------------------------------------------
+bool cls_head_supported(int N, int H, int C);
+cudaError_t launch_cls_head_fwd(int B, int T, int N, int H, int C, const float* hseq, const int* sel_t, const float* drop,
+                                const float* W, const float* bias, float* logits, int* arg, cudaStream_t st);
+cudaError_t launch_cls_head_bwd(int B, int T, int N, int H, int C, const float* hseq, const int* sel_t, const float* drop,
+                                const float* W, const int* arg, const float* dlogits, float* d_hsel, float* dW, float* db,
+                                float* dwpart, cudaStream_t st);
+cudaError_t launch_scatter_sel(int B, int T, int NH, const float* d_hsel, const int* sel_t, float* dense, cudaStream_t st);
 
 }  // namespace dcgru

@@ -47,6 +47,7 @@ struct RnnBwdParams {
     const float* h0; const float* hseq; const float* ruc;
     const float* P;
     const float* d_hseq; const float* d_hlast;
+    const float* d_hsel; const int* sel_t;   // sparse upstream gradient: slab b belongs to step sel_t[b] (head.cu), or nullptr
     const uint8_t* wimg;          // B1 planes [m][hi|lo], then B2 planes [2m+g][hi|lo] (g = 0: r, 1: u), 8 KB each
     const float* scale_ptr;
     float* dh0;
@@ -196,6 +197,8 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
         const bool valid = n < N && b < p.B;
         const uint32_t tb = taddr + ((uint32_t)(32 * quad) << 16);
         const size_t rbase = valid ? ((size_t)b * N + n) : 0;
+        int sel = -1;
+        if (p.d_hsel && valid) { sel = p.sel_t ? p.sel_t[b] : T - 1; sel = sel < 0 ? 0 : (sel >= T ? T - 1 : sel); }
         auto load_cols = [&](const float* src, uint32_t tcol) {          // 64 floats of this row -> TMEM columns
 #pragma unroll 1
             for (int cb = 0; cb < RB_H; cb += 32) {
@@ -217,7 +220,8 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
             tc_fence_after();
             load_cols(ruc + RB_H, RB_U);
             load_cols(ruc + 2 * RB_H, RB_C);
-            load_cols(p.d_hseq ? p.d_hseq + (size_t)t * p.B * NH + rbase * RB_H : nullptr, RB_DUP);
+            load_cols(p.d_hsel ? (sel == t ? p.d_hsel + rbase * RB_H : nullptr)
+                               : (p.d_hseq ? p.d_hseq + (size_t)t * p.B * NH + rbase * RB_H : nullptr), RB_DUP);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_gafull);
@@ -448,12 +452,21 @@ __global__ void grad_scale_kernel(unsigned* maxbits, float* scale) {
     *maxbits = 0u;
 }
 // scale[0] <- s, computed on the stream from the two upstream gradients (either may be nullptr); scratch: one unsigned, zeroed here
-cudaError_t launch_grad_scale(const float* a, size_t na, const float* b, size_t nb, unsigned* scratch, float* scale, cudaStream_t st) {
+cudaError_t launch_grad_scale(const float* a, size_t na, const float* b, size_t nb, const float* c, size_t nc, unsigned* scratch,
+                              float* scale, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(unsigned), st);
     if (e != cudaSuccess) return e;
-    grad_absmax_kernel<<<1184, 256, 0, st>>>(a, na, b, nb, scratch);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    if (a || b || !c) {
+        grad_absmax_kernel<<<1184, 256, 0, st>>>(a, na, b, nb, scratch);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    if (c) {
+        const int grid = (int)((nc / 4 + 255) / 256 < 1184 ? (nc / 4 + 255) / 256 : 1184);
+        grad_absmax_kernel<<<grid < 1 ? 1 : grid, 256, 0, st>>>(c, nc, nullptr, 0, scratch);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
     grad_scale_kernel<<<1, 1, 0, st>>>(scratch, scale);
     return cudaGetLastError();
 }
@@ -470,7 +483,8 @@ bool rnn_bwd_supported(int N, int H, int M, int smem_limit) {
 // dA image: [tile*T + t][hi|lo][96][3H] fp16, columns r | u | c, values scaled by *scale_ptr
 cudaError_t launch_rnn_bwd(int B, int T, int N, int fin, int M, int act, const float* h0, const float* hseq, const float* ruc,
                            const float* P, const float* Wg, const float* Wc, const float* d_hseq, const float* d_hlast,
-                           void* wimg, const float* scale_ptr, float* dh0, void* daimg, cudaStream_t st) {
+                           const float* d_hsel, const int* sel_t, void* wimg, const float* scale_ptr, float* dh0, void* daimg,
+                           cudaStream_t st) {
     cudaError_t e = launch_pack_w16(Wg, Wc, fin, RB_H, M, 4, RB_H, M, wimg, st);
     if (e != cudaSuccess) return e;
     e = launch_pack_w16(Wg, Wc, fin, RB_H, M, 5, RB_H, 2 * M, reinterpret_cast<uint8_t*>(wimg) + (size_t)2 * M * RB_WPIECE, st);
@@ -480,6 +494,7 @@ cudaError_t launch_rnn_bwd(int B, int T, int N, int fin, int M, int act, const f
     p.B = B; p.T = T; p.N = N; p.M = M; p.act = act; p.dump = daimg != nullptr;
     { const char* e = getenv("DCGRU_DBG"); p.dbg = e ? (atoi(e) & 32) : 0; }
     p.h0 = h0; p.hseq = hseq; p.ruc = ruc; p.P = P; p.d_hseq = d_hseq; p.d_hlast = d_hlast;
+    p.d_hsel = d_hsel; p.sel_t = sel_t;
     p.wimg = reinterpret_cast<const uint8_t*>(wimg); p.scale_ptr = scale_ptr; p.dh0 = dh0;
     CUtensorMap tm;
     memset(&tm, 0, sizeof tm);

@@ -47,6 +47,20 @@ class DCRNNEncoder(nn.Module):
             last.append(h_last)
         return torch.stack(last, dim=0), cur
 
+    def forward_head(self, inputs, initial_hidden_state, supports, sel_t, drop_mask, fc):
+        """The classification model's use of the encoder: all layers, then the fused head on the top layer's
+        sequence (inputs / initial_hidden_state as in forward; sel_t (B) int32 = seq_len-1) -> logits (B,C)."""
+        b = inputs.shape[1]
+        cur = inputs.flatten(2) if inputs.dim() == 4 else inputs
+        self.encoding_cells[0].check_supports(supports)
+        p = ops.graph_poly(list(supports), b, self._num_nodes, self._max_diffusion_step)
+        cells = list(self.encoding_cells)
+        for layer, cell in enumerate(cells[:-1]):
+            cur, _ = ops.encoder_layer(cur, initial_hidden_state[layer], p, *cell.flat_params(), cell.desc())
+        top = cells[-1]
+        return ops.encoder_top_head(cur, initial_hidden_state[len(cells) - 1], p, *top.flat_params(), fc.weight, fc.bias,
+                                    top.desc(), sel_t, drop_mask)
+
     def init_hidden(self, batch_size):
         return torch.stack([c.init_hidden(batch_size) for c in self.encoding_cells], dim=0)
 
@@ -131,11 +145,14 @@ class DCRNNModel_classification(nn.Module):
         b = input_seq.shape[0]
         # zeros created on the device (init_hidden() keeps the reference's CPU-tensor contract for callers that use it)
         h0 = torch.zeros(self.num_rnn_layers, b, self.num_nodes * self.rnn_units, device=input_seq.device)
-        _, top = self.encoder(input_seq.transpose(0, 1), h0, supports)          # (T,B,N*H)
-        idx = (seq_lengths.to(top.device).long() - 1).view(1, b, 1).expand(1, b, top.shape[2])
-        last = top.gather(0, idx).squeeze(0).view(b, self.num_nodes, self.rnn_units)
-        logits = self.fc(self.relu(self.dropout(last)))
-        return logits.max(dim=1).values
+        # layers below the top one as usual; the top layer and the head (last relevant step -> dropout -> ReLU -> fc ->
+        # max over nodes, model/model.py:257-270) run as one fused operator (csrc/head.cu): the head's gradient reaches
+        # the BPTT kernel as one (B,N*H) slab instead of a dense (T,B,N*H) tensor
+        drop = None
+        if self.training and self.dropout.p > 0:     # mask drawn by torch (same RNG stream as nn.Dropout), applied in-kernel
+            drop = self.dropout(torch.ones((b, self.num_nodes, self.rnn_units), device=input_seq.device))
+        sel = (seq_lengths.to(input_seq.device) - 1).to(torch.int32)
+        return self.encoder.forward_head(input_seq.transpose(0, 1), h0, supports, sel, drop, self.fc)
 
 
 class DCRNNModel_nextTimePred(nn.Module):

@@ -168,6 +168,87 @@ def encoder_layer(x, h0, p, wg, bg, wc, bc, desc):
     return _EncoderLayerFn.apply(x, h0, p, wg, bg, wc, bc, desc)
 
 
+class _EncoderTopHeadFn(torch.autograd.Function):
+    """logits = head(top_layer(x_seq, h0)): the encoder's last layer and the classification head
+    (gather at seq_len-1 -> dropout -> ReLU -> Linear -> max over nodes, model/model.py:257-270) as one autograd
+    node, so the head's gradient reaches the BPTT kernel as one (B,N*H) slab + the step it belongs to instead
+    of a dense (T,B,N*H) tensor."""
+
+    @staticmethod
+    def forward(ctx, x, h0, p, wg, bg, wc, bc, fc_w, fc_b, desc, sel_t, drop_mask):
+        _need_cuda(x, h0, wg, bg, wc, bc, fc_w, fc_b, drop_mask)
+        t_len, b = x.shape[0], x.shape[1]
+        x, st, sb = _seq_view(x)
+        h0 = h0.contiguous()
+        n, hid = desc.num_nodes, desc.hid_dim
+        ncls = fc_w.shape[0]
+        dev = x.device
+        h_seq = torch.empty((t_len, b, n * hid), device=dev, dtype=torch.float32)
+        need = any(ctx.needs_input_grad)
+        ruc = torch.empty((t_len, b, n, 3 * hid), device=dev, dtype=torch.float32) if need else None
+        wg, bg, wc, bc = wg.contiguous(), bg.contiguous(), wc.contiguous(), bc.contiguous()
+        fc_w, fc_b = fc_w.contiguous(), fc_b.contiguous()
+        if sel_t is not None:
+            sel_t = sel_t.to(device=dev, dtype=torch.int32).contiguous()
+        if drop_mask is not None:
+            drop_mask = drop_mask.contiguous()
+        ws = _params([(wg, bg, wc, bc)])
+        L = _lib.lib()
+        nbytes = L.dcgru_encoder_layer_fwd_workspace(C.byref(desc), b, t_len)
+        ws_buf = torch.empty(max(nbytes, 16), device=dev, dtype=torch.uint8)
+        gbytes = L.dcgru_encoder_layer_gsave_bytes(C.byref(desc), b, t_len) if need else 0
+        gsave = torch.empty(gbytes, device=dev, dtype=torch.uint8) if gbytes else None
+        check(L.dcgru_encoder_layer_fwd(C.byref(desc), b, t_len, _ptr(x), st, sb, _ptr(h0), _ptr(p), ws,
+                                        _ptr(h_seq), _ptr(ruc), _ptr(gsave), gbytes, _ptr(ws_buf), nbytes,
+                                        _stream()), "encoder_layer_fwd")
+        logits = torch.empty((b, ncls), device=dev, dtype=torch.float32)
+        arg = torch.empty((b, ncls), device=dev, dtype=torch.int32)
+        check(L.dcgru_cls_head_fwd(b, t_len, n, hid, ncls, _ptr(h_seq), _ptr(sel_t), _ptr(drop_mask), _ptr(fc_w),
+                                   _ptr(fc_b), _ptr(logits), _ptr(arg), _stream()), "cls_head_fwd")
+        ctx.desc, ctx.strides, ctx.gsave = desc, (st, sb), gsave
+        ctx.save_for_backward(x, h0, p, wg, bg, wc, bc, fc_w, h_seq, ruc, sel_t, drop_mask, arg)
+        return logits
+
+    @staticmethod
+    def backward(ctx, d_logits):
+        x, h0, p, wg, bg, wc, bc, fc_w, h_seq, ruc, sel_t, drop_mask, arg = ctx.saved_tensors
+        desc = ctx.desc
+        t_len, b = x.shape[0], x.shape[1]
+        st, sb = ctx.strides
+        dev = x.device
+        n, hid, ncls = desc.num_nodes, desc.hid_dim, fc_w.shape[0]
+        d_logits = d_logits.contiguous()
+        L = _lib.lib()
+        d_hsel = torch.empty((b, n * hid), device=dev, dtype=torch.float32)
+        dfw, dfb = torch.empty_like(fc_w), torch.empty((ncls,), device=dev, dtype=torch.float32)
+        hbytes = L.dcgru_cls_head_bwd_workspace(b, hid, ncls)
+        hws = torch.empty(max(hbytes, 16), device=dev, dtype=torch.uint8)
+        check(L.dcgru_cls_head_bwd(b, t_len, n, hid, ncls, _ptr(h_seq), _ptr(sel_t), _ptr(drop_mask), _ptr(fc_w),
+                                   _ptr(arg), _ptr(d_logits), _ptr(d_hsel), _ptr(dfw), _ptr(dfb), _ptr(hws), hbytes,
+                                   _stream()), "cls_head_bwd")
+        dx = torch.empty((t_len, b, x.shape[2]), device=dev, dtype=torch.float32) \
+            if ctx.needs_input_grad[0] else None
+        dh0 = torch.empty_like(h0)
+        dwg, dbg, dwc, dbc = (torch.empty_like(t) for t in (wg, bg, wc, bc))
+        nbytes = L.dcgru_encoder_layer_bwd_sel_workspace(C.byref(desc), b, t_len)
+        ws_buf = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        ws = _params([(wg, bg, wc, bc)])
+        g = CellGrads(dwg.data_ptr(), dbg.data_ptr(), dwc.data_ptr(), dbc.data_ptr())
+        check(L.dcgru_encoder_layer_bwd_sel(C.byref(desc), b, t_len, _ptr(x), st, sb, _ptr(h0), _ptr(p), ws,
+                                            _ptr(h_seq), _ptr(ruc), _ptr(d_hsel), _ptr(sel_t), _ptr(None), _ptr(dx),
+                                            _ptr(dh0), C.byref(g), _ptr(ctx.gsave),
+                                            ctx.gsave.numel() if ctx.gsave is not None else 0,
+                                            _ptr(ws_buf), nbytes, _stream()), "encoder_layer_bwd_sel")
+        ctx.gsave = None
+        return dx, dh0, None, dwg, dbg, dwc, dbc, dfw, dfb, None, None, None
+
+
+def encoder_top_head(x, h0, p, wg, bg, wc, bc, fc_w, fc_b, desc, sel_t=None, drop_mask=None):
+    """x (T,B,N*Fin), h0 (B,N*H), fc_w (C,H), fc_b (C), sel_t (B) int32 = seq_len-1 (None: T-1),
+    drop_mask (B,N,H) or None -> pooled logits (B,C)."""
+    return _EncoderTopHeadFn.apply(x, h0, p, wg, bg, wc, bc, fc_w, fc_b, desc, sel_t, drop_mask)
+
+
 # ------------------------------------------------------------------------------------------------
 # decoder
 # ------------------------------------------------------------------------------------------------

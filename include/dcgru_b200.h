@@ -146,6 +146,42 @@ int dcgru_encoder_layer_bwd(const dcgru_cell_desc *d, int32_t batch, int32_t seq
                             const void *gsave, size_t gsave_bytes,
                             void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- fused classification head -------------------------------------------------
+ * Replaces the tail of DCRNNModel_classification.forward (model/model.py:257-270):
+ *   last = utils.last_relevant_pytorch(h_seq, seq_lengths)   (utils.py:346-357)  -> h_seq[sel_t[b], b]
+ *   logits = max over nodes of fc(relu(dropout(last)))                            -> (B, num_classes)
+ * h_seq:      (T,B,N*H) top-layer sequence of the encoder
+ * sel_t:      (B) int32 device array, sel_t[b] = seq_lengths[b]-1 (clamped to [0,T-1]); NULL = T-1 for every sample
+ * drop_mask:  (B,N,H) multiplicative dropout mask (0 or 1/(1-p), as nn.Dropout draws it) or NULL (eval / p = 0)
+ * fc_w (num_classes,H), fc_b (num_classes): nn.Linear(rnn_units, num_classes)
+ * logits out (B,num_classes); argmax_node out (B,num_classes) int32: the node the max came from (saved for backward)
+ *
+ * Backward: d_logits (B,num_classes) -> d_fc_w, d_fc_b (overwritten; batch sums in fixed order) and d_hsel (B,N*H),
+ * the gradient of h_seq in SPARSE form: sample b's slab belongs to step sel_t[b]; every other step's gradient is zero.
+ * dcgru_encoder_layer_bwd_sel consumes it directly, so the dense (T,B,N*H) gradient that autograd derives for the
+ * reference's gather (utils.py:354) is never written or read.                                                      */
+int dcgru_cls_head_fwd(int32_t batch, int32_t seq_len, int32_t num_nodes, int32_t hid_dim, int32_t num_classes,
+                       const float *h_seq, const int32_t *sel_t, const float *drop_mask,
+                       const float *fc_w, const float *fc_b, float *logits, int32_t *argmax_node, void *stream);
+size_t dcgru_cls_head_bwd_workspace(int32_t batch, int32_t hid_dim, int32_t num_classes);
+int dcgru_cls_head_bwd(int32_t batch, int32_t seq_len, int32_t num_nodes, int32_t hid_dim, int32_t num_classes,
+                       const float *h_seq, const int32_t *sel_t, const float *drop_mask, const float *fc_w,
+                       const int32_t *argmax_node, const float *d_logits, float *d_hsel,
+                       float *d_fc_w, float *d_fc_b, void *workspace, size_t workspace_bytes, void *stream);
+
+/* dcgru_encoder_layer_bwd with the upstream gradient of h_seq in the sparse form above (d_hsel, sel_t) instead of
+ * the dense d_hseq; everything else as dcgru_encoder_layer_bwd.  The tensor-core BPTT kernel injects the slab at step
+ * sel_t[b]; configurations served by the other kernels expand it into a dense buffer inside the (larger) workspace. */
+size_t dcgru_encoder_layer_bwd_sel_workspace(const dcgru_cell_desc *d, int32_t batch, int32_t seq_len);
+int dcgru_encoder_layer_bwd_sel(const dcgru_cell_desc *d, int32_t batch, int32_t seq_len,
+                                const float *x, int64_t x_stride_t, int64_t x_stride_b,
+                                const float *h0, const float *P, const dcgru_cell_params *w,
+                                const float *h_seq, const float *ruc,
+                                const float *d_hsel, const int32_t *sel_t, const float *d_hlast,
+                                float *dx, float *dh0, const dcgru_cell_grads *g,
+                                const void *gsave, size_t gsave_bytes,
+                                void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- fused optimiser step ---------------------------------------------------
  * The tail of the reference's training step on flat fp32 buffers of n elements (train.py:273-275):
  * torch.nn.utils.clip_grad_norm_(max_grad_norm) followed by torch.optim.Adam(lr, betas, eps,

@@ -34,6 +34,8 @@ constexpr int BK_NWORK = 256;
 
 struct BulkParams {
     int B, T, N, Cin, M, Nout, transposeP;
+    int nout_valid;                       // output columns that exist (<= Nout; the rest of the MMA tile is padding)
+    int img_T, img_t0, src_T, src_t0;     // slab of (tile, t) inside the dumped image / the source image: tile * X_T + X_t0 + t
     int ntile, item0_stride;              // items = ntile * T, split evenly over the grid
     int NQ, NW, piece_bytes;
     const float* src; long long ss_t, ss_b;
@@ -44,6 +46,7 @@ struct BulkParams {
     float* out; long long os_t, os_b; int out_ld;
     float out_scale;
     const float* scale_ptr;               // optional device scalar: out *= 1 / *scale_ptr (gradient scaling, rnn_bwd.cu)
+    const float* in_scale_ptr;            // optional device scalar: the fp32 source is multiplied by it before the hi/lo split
     int dump, img_col0;
     int off_w, off_x, off_pt, off_id;     // shared-memory offsets
 };
@@ -59,7 +62,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) bulk_dp_kernel(const BulkParams
     __shared__ __align__(16) float sbias[192];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = p.N, Cin = p.Cin, M = p.M, NQ = p.NQ, NW = p.NW;
-    if (tid < 192) sbias[tid] = (p.bias && tid < p.Nout) ? p.bias[tid] : 0.f;
+    if (tid < 192) sbias[tid] = (p.bias && tid < p.nout_valid) ? p.bias[tid] : 0.f;
     const long nitems = (long)p.ntile * p.T;
     const long it0 = nitems * blockIdx.x / gridDim.x, it1 = nitems * (blockIdx.x + 1) / gridDim.x;
     const int nloc = (int)(it1 - it0);
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) bulk_dp_kernel(const BulkParams
                 if (src16) {                                      // one slab of the image: both planes, all 96 rows
                     const uint32_t bytes = (uint32_t)(2 * IMG_ROWS * Cin * 2);
                     mbar_expect_tx(&bar_xfull, bytes);
-                    bulk_g2s(XT, p.src16 + (size_t)it * (2 * IMG_ROWS * Cin), bytes, &bar_xfull);
+                    bulk_g2s(XT, p.src16 + (size_t)((long)tile * p.src_T + p.src_t0 + t) * (2 * IMG_ROWS * Cin), bytes, &bar_xfull);
                 } else {
                     int nvalid = p.B - tile * SB; if (nvalid > SB) nvalid = SB;
                     mbar_expect_tx(&bar_xfull, (uint32_t)(nvalid * srow * 4));
@@ -165,12 +168,14 @@ __global__ void __launch_bounds__(BK_THREADS, 1) bulk_dp_kernel(const BulkParams
             if (lane == 0) tma_prefetch_desc(&tm_img);
             for (int k = 0; k < nloc; ++k) {
                 const long it = it0 + k;
+                const int tile = (int)(it / p.T), t = (int)(it - (long)tile * p.T);
+                const long slab = (long)tile * p.img_T + p.img_t0 + t;
                 for (int q = 0; q < NQ; ++q) {
                     const unsigned g = (unsigned)k * NQ + q;
                     const int slot = g % BK_NS;
                     mbar_wait(&bar_afull[q], k & 1);
                     if (lane < 2 * SB) {
-                        tma_store_2d(&tm_img, p.img_col0 + 64 * q, (int)((it * 2 + plane) * IMG_ROWS + s * (RG * 8)),
+                        tma_store_2d(&tm_img, p.img_col0 + 64 * q, (int)((slab * 2 + plane) * IMG_ROWS + s * (RG * 8)),
                                      Aslots + slot * SLOT + plane * PLANE + s * (RP * 128));
                         bulk_commit();
                     }
@@ -189,6 +194,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) bulk_dp_kernel(const BulkParams
         const int ncol = p.Nout / 2;                            // columns per thread in the epilogue
         float oscale = p.out_scale;
         if (p.scale_ptr) oscale *= 1.f / __ldg(p.scale_ptr);
+        const float iscale = p.in_scale_ptr ? __ldg(p.in_scale_ptr) : 1.f;
         auto epilogue = [&](int k) {
             const long it = it0 + k;
             const int tile = (int)(it / p.T), t = (int)(it - (long)tile * p.T);
@@ -207,6 +213,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) bulk_dp_kernel(const BulkParams
                     for (int j = 0; j < 32; j += 4) {
                         float4 o;
                         const int c = half * ncol + cb + j;
+                        if (c >= p.nout_valid) continue;
                         const float4 bq = *reinterpret_cast<const float4*>(sbias + c);
                         o.x = fmaf(v[j], oscale, bq.x); o.y = fmaf(v[j + 1], oscale, bq.y);
                         o.z = fmaf(v[j + 2], oscale, bq.z); o.w = fmaf(v[j + 3], oscale, bq.w);
@@ -267,7 +274,7 @@ __global__ void __launch_bounds__(BK_THREADS, 1) bulk_dp_kernel(const BulkParams
                         for (int n = 0; n < NPAD; ++n) { acc[n][0] = 0.f; acc[n][1] = 0.f; }
                     }
                 }
-                store_cols2(sl, s * RP, lane, N, acc, 1.f);
+                store_cols2(sl, s * RP, lane, N, acc, iscale);
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_afull[q]);
@@ -292,6 +299,9 @@ __global__ void __launch_bounds__(BK_THREADS, 1) bulk_dp_kernel(const BulkParams
 //   mode 3  candidate, h part  kk = m*H + c;    Wc[((fin+c)*M+m)][n]                                            nrows = H
 //   mode 4  BPTT B1 (d(rh))    kk = m*H + o;    n = hidden column c:  Wc[((fin+n)*M+m)][o]                      nrows = H
 //   mode 5  BPTT B2 (dh)       kk = (2m+g)*H + o (g = 0: r, 1: u);  Wg[((fin+n)*M+m)][g*H + o]                  nrows = H
+//   mode 6  decoder projection (nn.Linear, model/model.py:146,193): kk = c < H;  Wg = proj_w (fin = Fo rows, H): Wg[n][kk]   nrows >= Fo
+//   mode 7  its input gradient:  kk = o < fin = Fo;  n = hidden column:  Wg[kk][n]                                  nrows = H
+// rows / k beyond the real extents are zero
 __global__ void pack_w16_kernel(const float* Wg, const float* Wc, int fin, int H, int M, int mode, int nrows, int nq, uint8_t* img) {
     const int q = blockIdx.x;
     const size_t piece = (size_t)nrows * 128;
@@ -305,16 +315,20 @@ __global__ void pack_w16_kernel(const float* Wg, const float* Wc, int fin, int H
             if (kk < M * fin) { const int m = kk / fin, c = kk - m * fin; const size_t r = (size_t)c * M + m;
                                 w = n < H2 ? Wg[r * H2 + n] : Wc[r * H + (n - H2)]; }
         } else if (mode == 1) {
-            if (kk < M * H3) { const int m = kk / H3, o = kk - m * H3; const size_t r = (size_t)n * M + m;
+            if (kk < M * H3 && n < fin) { const int m = kk / H3, o = kk - m * H3; const size_t r = (size_t)n * M + m;
                                w = o < H2 ? Wg[r * H2 + o] : Wc[r * H + (o - H2)]; }
         } else if (mode == 2 || mode == 3) {
             if (kk < M * H) { const int m = kk / H, c = kk - m * H; const size_t r = (size_t)(fin + c) * M + m;
                               w = mode == 2 ? Wg[r * H2 + n] : Wc[r * H + n]; }
         } else if (mode == 4) {
             if (kk < M * H) { const int m = kk / H, o = kk - m * H; w = Wc[((size_t)(fin + n) * M + m) * H + o]; }
-        } else {
+        } else if (mode == 5) {
             if (kk < 2 * M * H) { const int mg = kk / H, o = kk - mg * H, m = mg >> 1, g = mg & 1;
                                   w = Wg[((size_t)(fin + n) * M + m) * H2 + g * H + o]; }
+        } else if (mode == 6) {
+            if (kk < H && n < fin) w = Wg[(size_t)n * H + kk];
+        } else {
+            if (kk < fin && n < H) w = Wg[(size_t)kk * H + n];
         }
         __half h, l;
         split1(w, h, l);
@@ -357,7 +371,7 @@ static int bulk_smem(const BulkParams& p) { return p.off_id + PT_STRIDE * 4 + 10
 bool bulk_dp_supported(int N, int Cin, int M, int Nout, bool src16, int smem_limit) {
     BulkParams p;
     if (N > NPAD || Cin % (src16 ? 8 : 4) || M < 1 || g16_nq(Cin, M) > BK_MAXQ) return false;
-    if (Nout != 64 && Nout != 192) return false;
+    if (Nout != 64 && Nout != 128 && Nout != 192) return false;
     return bulk_layout(N, Cin, M, Nout, smem_limit, src16, &p);
 }
 
@@ -365,7 +379,7 @@ bool bulk_dp_supported(int N, int Cin, int M, int Nout, bool src16, int smem_lim
 cudaError_t launch_bulk_dp(int B, int T, int N, int Cin, int M, int Nout, int transposeP, const float* src, long long ss_t,
                            long long ss_b, const void* src16, const float* P, const void* wimg, const float* bias, float* out, long long os_t,
                            long long os_b, int out_ld, float out_scale, const float* scale_ptr, void* img, int img_cols,
-                           int img_col0, int nsms, int smem_limit, cudaStream_t st) {
+                           int img_col0, int nsms, int smem_limit, cudaStream_t st, const BulkExtra* ex) {
     BulkParams p;
     memset(&p, 0, sizeof p);
     if (!bulk_layout(N, Cin, M, Nout, smem_limit, src16 != nullptr, &p)) return cudaErrorInvalidConfiguration;
@@ -375,11 +389,18 @@ cudaError_t launch_bulk_dp(int B, int T, int N, int Cin, int M, int Nout, int tr
     p.src = src; p.ss_t = ss_t; p.ss_b = ss_b; p.P = P; p.wimg = reinterpret_cast<const uint8_t*>(wimg); p.bias = bias;
     p.out = out; p.os_t = os_t; p.os_b = os_b; p.out_ld = out_ld; p.out_scale = out_scale; p.scale_ptr = scale_ptr;
     p.dump = img != nullptr; p.img_col0 = img_col0;
+    p.nout_valid = Nout; p.img_T = T; p.img_t0 = 0; p.src_T = T; p.src_t0 = 0;
+    if (ex) {
+        if (ex->nout_valid > 0) p.nout_valid = ex->nout_valid;
+        if (ex->img_T > 0) { p.img_T = ex->img_T; p.img_t0 = ex->img_t0; }
+        if (ex->src_T > 0) { p.src_T = ex->src_T; p.src_t0 = ex->src_t0; }
+        p.in_scale_ptr = ex->in_scale_ptr;
+    }
     CUtensorMap tm;
     memset(&tm, 0, sizeof tm);
     if (img) {
         // 2-D view of the fp16 image [rows][img_cols]; box = 64 columns (128 bytes) x the 24 rows of one sample
-        const unsigned long long dims[2] = {(unsigned long long)img_cols, (unsigned long long)p.ntile * T * 2 * IMG_ROWS};
+        const unsigned long long dims[2] = {(unsigned long long)img_cols, (unsigned long long)p.ntile * p.img_T * 2 * IMG_ROWS};
         const unsigned long long str[2] = {2, (unsigned long long)img_cols * 2};
         const unsigned box[2] = {64, RG * 8};
         cudaError_t e = make_tmap(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, img, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);

@@ -118,17 +118,23 @@ size_t bulk_wimg_bytes(int cin, int M, int nout);
 bool bulk_dp_supported(int N, int Cin, int M, int Nout, bool src16, int smem_limit);
 cudaError_t launch_pack_w16(const float* Wg, const float* Wc, int fin, int H, int M, int mode, int nrows, int nq,
                             void* img, cudaStream_t st);
+// optional extras of launch_bulk_dp (decoder orchestration): real output columns (< Nout = padded MMA N), position of this
+// launch's T steps inside a larger dumped / source image (slab = tile * X_T + X_t0 + t), scale applied to the fp32 source
+struct BulkExtra { int nout_valid = 0; int img_T = 0, img_t0 = 0; int src_T = 0, src_t0 = 0; const float* in_scale_ptr = nullptr; };
 cudaError_t launch_bulk_dp(int B, int T, int N, int Cin, int M, int Nout, int transposeP, const float* src, long long ss_t,
                            long long ss_b, const void* src16, const float* P, const void* wimg, const float* bias, float* out, long long os_t,
                            long long os_b, int out_ld, float out_scale, const float* scale_ptr, void* img, int img_cols,
-                           int img_col0, int nsms, int smem_limit, cudaStream_t st);
+                           int img_col0, int nsms, int smem_limit, cudaStream_t st, const BulkExtra* ex = nullptr);
 
 size_t rnn_fwd_wimg_bytes(int M);
 cudaError_t rnn_fwd_read_dbg(long long* out, int n);
 bool rnn_fwd_supported(int N, int H, int M, int smem_limit);
+// Wg == nullptr: wimg already holds the packed weight planes (rnn_fwd_pack_weights); img_T > 0: this launch's steps are slabs
+// tile * img_T + img_t0 + t of a larger image
+cudaError_t rnn_fwd_pack_weights(const float* Wg, const float* Wc, int fin, int M, void* wimg, cudaStream_t st);
 cudaError_t launch_rnn_fwd(int B, int T, int N, int fin, int M, int act, const float* xp, const float* h0, const float* P,
                            const float* Wg, const float* Wc, void* wimg, float* hseq, float* ruc, void* img, int img_cols,
-                           int img_col0, cudaStream_t st);
+                           int img_col0, cudaStream_t st, int img_T = 0, int img_t0 = 0);
 
 size_t rnn_bwd_wimg_bytes(int M);
 cudaError_t rnn_bwd_read_dbg(long long* out, int n);
@@ -139,7 +145,8 @@ cudaError_t launch_grad_scale(const float* a, size_t na, const float* b, size_t 
 cudaError_t launch_rnn_bwd(int B, int T, int N, int fin, int M, int act, const float* h0, const float* hseq, const float* ruc,
                            const float* P, const float* Wg, const float* Wc, const float* d_hseq, const float* d_hlast,
                            const float* d_hsel, const int* sel_t, void* wimg, const float* scale_ptr, float* dh0, void* daimg,
-                           cudaStream_t st);
+                           cudaStream_t st, int img_T = 0, int img_t0 = 0);
+cudaError_t rnn_bwd_pack_weights(const float* Wg, const float* Wc, int fin, int M, void* wimg, cudaStream_t st);
 cudaError_t launch_img_to_rows(const void* img, int B, int T, int N, int cols, const float* scale_ptr, float* out, cudaStream_t st);
 
 size_t dw_mm16_part_floats(int nsms);

@@ -44,6 +44,7 @@ constexpr int RB_ACC1 = 0, RB_ACC2 = 64, RB_U = 128, RB_C = 192, RB_HP = 256, RB
 
 struct RnnBwdParams {
     int B, T, N, M, act, dump, dbg;
+    int img_T, img_t0;            // slab of step t in the dA image: tile * img_T + img_t0 + t
     const float* h0; const float* hseq; const float* ruc;
     const float* P;
     const float* d_hseq; const float* d_hlast;
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
             unsigned seq = 0;
             for (int k = 0; k < T; ++k) {
                 const int t = T - 1 - k;
-                const long slab = (long)tile * T + t;
+                const long slab = (long)tile * p.img_T + p.img_t0 + t;
                 for (int i = 0; i < nch; ++i, ++seq) {
                     const int slot = seq % 3;
                     mbar_wait(&bar_afull[slot], (seq / 3) & 1);
@@ -480,18 +481,26 @@ bool rnn_bwd_supported(int N, int H, int M, int smem_limit) {
     return H == RB_H && N <= NPAD && M >= 1 && M <= 7 && rnn_bwd_smem_bytes(M) + 1024 <= smem_limit;
 }
 
+cudaError_t rnn_bwd_pack_weights(const float* Wg, const float* Wc, int fin, int M, void* wimg, cudaStream_t st) {
+    cudaError_t e = launch_pack_w16(Wg, Wc, fin, RB_H, M, 4, RB_H, M, wimg, st);
+    if (e != cudaSuccess) return e;
+    return launch_pack_w16(Wg, Wc, fin, RB_H, M, 5, RB_H, 2 * M, reinterpret_cast<uint8_t*>(wimg) + (size_t)2 * M * RB_WPIECE, st);
+}
+
 // dA image: [tile*T + t][hi|lo][96][3H] fp16, columns r | u | c, values scaled by *scale_ptr
 cudaError_t launch_rnn_bwd(int B, int T, int N, int fin, int M, int act, const float* h0, const float* hseq, const float* ruc,
                            const float* P, const float* Wg, const float* Wc, const float* d_hseq, const float* d_hlast,
                            const float* d_hsel, const int* sel_t, void* wimg, const float* scale_ptr, float* dh0, void* daimg,
-                           cudaStream_t st) {
-    cudaError_t e = launch_pack_w16(Wg, Wc, fin, RB_H, M, 4, RB_H, M, wimg, st);
-    if (e != cudaSuccess) return e;
-    e = launch_pack_w16(Wg, Wc, fin, RB_H, M, 5, RB_H, 2 * M, reinterpret_cast<uint8_t*>(wimg) + (size_t)2 * M * RB_WPIECE, st);
-    if (e != cudaSuccess) return e;
+                           cudaStream_t st, int img_T, int img_t0) {
+    cudaError_t e = cudaSuccess;
+    if (Wg) {
+        e = rnn_bwd_pack_weights(Wg, Wc, fin, M, wimg, st);
+        if (e != cudaSuccess) return e;
+    }
     RnnBwdParams p;
     memset(&p, 0, sizeof p);
     p.B = B; p.T = T; p.N = N; p.M = M; p.act = act; p.dump = daimg != nullptr;
+    p.img_T = img_T > 0 ? img_T : T; p.img_t0 = img_T > 0 ? img_t0 : 0;
     { const char* e = getenv("DCGRU_DBG"); p.dbg = e ? (atoi(e) & 32) : 0; }
     p.h0 = h0; p.hseq = hseq; p.ruc = ruc; p.P = P; p.d_hseq = d_hseq; p.d_hlast = d_hlast;
     p.d_hsel = d_hsel; p.sel_t = sel_t;
@@ -500,7 +509,7 @@ cudaError_t launch_rnn_bwd(int B, int T, int N, int fin, int M, int act, const f
     memset(&tm, 0, sizeof tm);
     const int ntile = g16_ntile(B);
     if (daimg) {
-        const unsigned long long dims[2] = {(unsigned long long)3 * RB_H, (unsigned long long)ntile * T * 2 * IMG_ROWS};
+        const unsigned long long dims[2] = {(unsigned long long)3 * RB_H, (unsigned long long)ntile * p.img_T * 2 * IMG_ROWS};
         const unsigned long long str[2] = {2, (unsigned long long)3 * RB_H * 2};
         const unsigned box[2] = {64, RG * 8};
         e = make_tmap(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, daimg, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);

@@ -40,6 +40,7 @@ constexpr int RF_ACC1 = 192, RF_STASH = 384, RF_RSTASH = 448;   // TMEM columns:
 
 struct RnnFwdParams {
     int B, T, N, M, act, dump, img_col0, dbg;
+    int img_T, img_t0;          // slab of step t in the operand image: tile * img_T + img_t0 + t
     const float* xp;            // (T,B,N,3H)
     const float* h0;            // (B,N*H)
     const float* P;             // (B,M-1,N,N)
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
             if (lane == 0) tma_prefetch_desc(&tm_img);
             unsigned fills[3] = {0, 0, 0};
             for (int t = 0; t < T; ++t) {
-                const long slab = (long)tile * T + t;
+                const long slab = (long)tile * p.img_T + p.img_t0 + t;
                 for (int ci = 0; ci < 2 * M; ++ci) {
                     const int m = ci < M ? ci : ci - M;
                     const int slot = m == 0 ? 0 : 1 + ((m - 1) & 1);
@@ -401,24 +402,32 @@ bool rnn_fwd_supported(int N, int H, int M, int smem_limit) {
     return H == RF_H && N <= NPAD && M >= 1 && M <= 7 && rnn_fwd_smem_bytes(M) + 1024 <= smem_limit;
 }
 
+cudaError_t rnn_fwd_pack_weights(const float* Wg, const float* Wc, int fin, int M, void* wimg, cudaStream_t st) {
+    cudaError_t e = launch_pack_w16(Wg, Wc, fin, RF_H, M, 2, 2 * RF_H, M, wimg, st);
+    if (e != cudaSuccess) return e;
+    return launch_pack_w16(Wg, Wc, fin, RF_H, M, 3, RF_H, M, reinterpret_cast<uint8_t*>(wimg) + (size_t)2 * M * RF_WSLOT, st);
+}
+
 // wimg: rnn_fwd_wimg_bytes(M), filled here; img: operand image base or nullptr (img_cols fp16 values per row)
 cudaError_t launch_rnn_fwd(int B, int T, int N, int fin, int M, int act, const float* xp, const float* h0, const float* P,
                            const float* Wg, const float* Wc, void* wimg, float* hseq, float* ruc, void* img, int img_cols,
-                           int img_col0, cudaStream_t st) {
-    cudaError_t e = launch_pack_w16(Wg, Wc, fin, RF_H, M, 2, 2 * RF_H, M, wimg, st);
-    if (e != cudaSuccess) return e;
-    e = launch_pack_w16(Wg, Wc, fin, RF_H, M, 3, RF_H, M, reinterpret_cast<uint8_t*>(wimg) + (size_t)2 * M * RF_WSLOT, st);
-    if (e != cudaSuccess) return e;
+                           int img_col0, cudaStream_t st, int img_T, int img_t0) {
+    cudaError_t e = cudaSuccess;
+    if (Wg) {
+        e = rnn_fwd_pack_weights(Wg, Wc, fin, M, wimg, st);
+        if (e != cudaSuccess) return e;
+    }
     RnnFwdParams p;
     memset(&p, 0, sizeof p);
     p.B = B; p.T = T; p.N = N; p.M = M; p.act = act; p.dump = img != nullptr; p.img_col0 = img_col0;
+    p.img_T = img_T > 0 ? img_T : T; p.img_t0 = img_T > 0 ? img_t0 : 0;
     { const char* e = getenv("DCGRU_DBG"); p.dbg = e ? (atoi(e) & (16 | 64 | 128 | 256 | 512)) : 0; }
     p.xp = xp; p.h0 = h0; p.P = P; p.wimg = reinterpret_cast<const uint8_t*>(wimg); p.hseq = hseq; p.ruc = ruc;
     CUtensorMap tm;
     memset(&tm, 0, sizeof tm);
     const int ntile = g16_ntile(B);
     if (img) {
-        const unsigned long long dims[2] = {(unsigned long long)img_cols, (unsigned long long)ntile * T * 2 * IMG_ROWS};
+        const unsigned long long dims[2] = {(unsigned long long)img_cols, (unsigned long long)ntile * p.img_T * 2 * IMG_ROWS};
         const unsigned long long str[2] = {2, (unsigned long long)img_cols * 2};
         const unsigned box[2] = {64, RG * 8};
         e = make_tmap(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, img, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);

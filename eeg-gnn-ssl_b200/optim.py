@@ -68,7 +68,13 @@ class FusedClipAdam(torch.optim.Optimizer):
         return super().state_dict()
 
     def load_state_dict(self, state_dict):
+        before = dict(self.param_groups[0])
         super().load_state_dict(state_dict)                               # casts to the parameters' device / dtype
+        # a checkpoint written by torch.optim.Adam has no max_grad_norm (clipping is a separate call there, train.py:273):
+        # options the loaded group does not carry keep this optimiser's own values
+        for k, v in before.items():
+            if k != "params":
+                self.param_groups[0].setdefault(k, v)
         steps = set()
         with torch.no_grad():
             for p, off in zip(self.params, self.sync.offsets):

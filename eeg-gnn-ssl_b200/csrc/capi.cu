@@ -813,10 +813,116 @@ static int check_dec(const dcgru_cell_desc* d, int L, int B, int T) {
     return 0;
 }
 
+// ---- second-generation decoder (2xFP16 tensor-core kernels, H = 64) ---------------------------------------------------------
+// The decoder is time-outer / layer-inner and autoregressive (model/model.py:182-202): nothing can be hoisted over time, so
+// every (step, layer) cell is one T = 1 launch pair of the encoder's kernels -- x-part GEMM (bulk_dp.cu) + recurrent step
+// (rnn_fwd.cu) -- followed per step by the projection as a bulk_dp GEMM without diffusion (M = 1).  Weight images are packed
+// once per distinct cell (tied cells share one).  BPTT mirrors it with rnn_bwd.cu / the dX GEMM per cell; all dA slabs land
+// in ONE operand image [tile][t*L + l], which the bulk weight-gradient kernels consume afterwards.
+// DCGRU_G2_DEC=0 keeps the single-launch fp32 FMA decoder (seq_fwd.cu / seq_bwd.cu mode 1); tests compare the two.
+static int nout_pad(int n) { return n <= 64 ? 64 : (n <= 128 ? 128 : 192); }
+static bool g2_dec_supported(const dcgru_cell_desc* d, int L) {
+    const char* e = getenv("DCGRU_G2_DEC");
+    if ((e && e[0] == '0') || !g2_enabled()) return false;
+    const int H = d->hid_dim, Fo = d->input_dim, M = Mof(d), N = d->num_nodes;
+    if (H != 64 || Fo > 192 || Fo % 4 || L < 1) return false;
+    dcgru_cell_desc d1 = *d;
+    d1.input_dim = H;
+    const int smem = devinfo().smem;
+    if (!g2_bwd_supported(d) || !g2_bwd_supported(&d1)) return false;
+    return bulk_dp_supported(N, 3 * H, M, nout_pad(Fo), true, smem) && bulk_dp_supported(N, 3 * H, M, H, true, smem) &&
+           bulk_dp_supported(N, H, 1, nout_pad(Fo), false, smem) && bulk_dp_supported(N, Fo, 1, H, false, smem);
+}
+// distinct cells of the stack: cid[l] = first layer with the same parameters
+static int dec_cell_ids(const dcgru_cell_params* w, int L, int* cid) {
+    int n = 0;
+    for (int l = 0; l < L; ++l) {
+        cid[l] = l;
+        for (int j = 0; j < l; ++j)
+            if (w[j].Wg == w[l].Wg && w[j].Wc == w[l].Wc) { cid[l] = cid[j]; break; }
+        if (cid[l] == l) ++n;
+    }
+    return n;
+}
+struct G2DecFwdWs { size_t off_wx[DCGRU_MAX_LAYERS], off_wh[DCGRU_MAX_LAYERS], off_bias[DCGRU_MAX_LAYERS], off_wp, off_xp, off_zero, off_hm, total; };
+static G2DecFwdWs g2_dec_fwd_ws(const dcgru_cell_desc* d, int L, int B) {
+    G2DecFwdWs w;
+    const int H = d->hid_dim, Fo = d->input_dim, M = Mof(d), N = d->num_nodes;
+    size_t o = 0;
+    for (int l = 0; l < L; ++l) {
+        const int fin = l == 0 ? Fo : H;
+        w.off_wx[l] = o; o = align_up(o + bulk_wimg_bytes(fin, M, 3 * H));
+        w.off_wh[l] = o; o = align_up(o + rnn_fwd_wimg_bytes(M));
+        w.off_bias[l] = o; o = align_up(o + (size_t)3 * H * 4);
+    }
+    w.off_wp = o; o = align_up(o + bulk_wimg_bytes(H, 1, nout_pad(Fo)));
+    w.off_xp = o; o = align_up(o + (size_t)B * N * 3 * H * 4);
+    w.off_zero = o; o = align_up(o + (size_t)B * N * Fo * 4);
+    w.off_hm = o; o = align_up(o + (size_t)B * N * H * 4);
+    w.total = o;
+    return w;
+}
+
 size_t dcgru_decoder_fwd_workspace(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T) {
     if (check_dec(d, L, B, T)) return 0;
     // projWT (H, FoPad) with the largest possible padding (SB = 1 -> multiples of 256)
-    return align_up((size_t)d->hid_dim * ((d->input_dim + 255) / 256 * 256) * 4);
+    size_t n = align_up((size_t)d->hid_dim * ((d->input_dim + 255) / 256 * 256) * 4);
+    if (g2_dec_supported(d, L)) { const size_t g = g2_dec_fwd_ws(d, L, B).total; if (g > n) n = g; }
+    return n;
+}
+
+static int g2_decoder_fwd(const dcgru_cell_desc* d, int L, int B, int T, const float* targets, uint64_t teacher_mask,
+                          const float* h0, const float* P, const dcgru_cell_params* w, const float* proj_w, const float* proj_b,
+                          const float* drop_mask, float* out, float* h_all, float* ruc, void* workspace, cudaStream_t st) {
+    const int M = Mof(d), H = d->hid_dim, Fo = d->input_dim, N = d->num_nodes;
+    const DevInfo& di = devinfo();
+    const G2DecFwdWs ws = g2_dec_fwd_ws(d, L, B);
+    uint8_t* wsb = reinterpret_cast<uint8_t*>(workspace);
+    int cid[DCGRU_MAX_LAYERS];
+    dec_cell_ids(w, L, cid);
+    for (int l = 0; l < L; ++l) {
+        if (cid[l] != l) continue;
+        const int fin = l == 0 ? Fo : H;
+        float* bias = reinterpret_cast<float*>(wsb + ws.off_bias[l]);
+        CUDA_TRY(cudaMemcpyAsync(bias, w[l].bg, (size_t)2 * H * 4, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(bias + 2 * H, w[l].bc, (size_t)H * 4, cudaMemcpyDeviceToDevice, st));
+        LAUNCH("pack_w16", launch_pack_w16(w[l].Wg, w[l].Wc, fin, H, M, 0, 3 * H, g16_nq(fin, M), wsb + ws.off_wx[l], st));
+        LAUNCH("pack_w16", rnn_fwd_pack_weights(w[l].Wg, w[l].Wc, fin, M, wsb + ws.off_wh[l], st));
+    }
+    const int fop = nout_pad(Fo);
+    LAUNCH("pack_w16", launch_pack_w16(proj_w, nullptr, Fo, H, 1, 6, fop, 1, wsb + ws.off_wp, st));
+    float* xp = reinterpret_cast<float*>(wsb + ws.off_xp);
+    float* zero = reinterpret_cast<float*>(wsb + ws.off_zero);
+    float* hm = reinterpret_cast<float*>(wsb + ws.off_hm);
+    CUDA_TRY(cudaMemsetAsync(zero, 0, (size_t)B * N * Fo * 4, st));                         // GO symbol (model/model.py:172-173)
+    const size_t NH = (size_t)N * H, NF = (size_t)N * Fo;
+    BulkExtra pex;
+    pex.nout_valid = Fo;
+    for (int t = 0; t < T; ++t) {
+        const float* xin = zero;
+        if (t > 0) xin = ((teacher_mask >> (t - 1)) & 1) ? targets + (size_t)(t - 1) * B * NF : out + (size_t)(t - 1) * B * NF;
+        for (int l = 0; l < L; ++l) {
+            const int fin = l == 0 ? Fo : H, c = cid[l];
+            const float* src = l == 0 ? xin : h_all + ((size_t)t * L + (l - 1)) * B * NH;
+            const float* hprev = t == 0 ? h0 + (size_t)l * B * NH : h_all + ((size_t)(t - 1) * L + l) * B * NH;
+            float* hout = h_all + ((size_t)t * L + l) * B * NH;
+            float* rucl = ruc ? ruc + ((size_t)t * L + l) * B * NH * 3 : nullptr;
+            LAUNCH("xproj", launch_bulk_dp(B, 1, N, fin, M, 3 * H, 0, src, 0, (long long)N * fin, nullptr, P, wsb + ws.off_wx[c],
+                                           reinterpret_cast<float*>(wsb + ws.off_bias[c]), xp, 0, (long long)N * 3 * H, 3 * H, 1.f,
+                                           nullptr, nullptr, 0, 0, di.sms, di.smem, st));
+            LAUNCH("rnn_fwd", launch_rnn_fwd(B, 1, N, fin, M, d->activation, xp, hprev, P, nullptr, nullptr, wsb + ws.off_wh[c], hout,
+                                             rucl, nullptr, 0, 0, st));
+        }
+        const float* top = h_all + ((size_t)t * L + (L - 1)) * B * NH;
+        if (drop_mask) {                                                                     // nn.Dropout before the projection (model/model.py:192)
+            LAUNCH("ew", launch_ew_add_mul(top, nullptr, drop_mask + (size_t)t * B * NH, hm, (size_t)B * NH, st));
+            top = hm;
+        }
+        LAUNCH("proj", launch_bulk_dp(B, 1, N, H, 1, fop, 0, top, 0, (long long)NH, nullptr, nullptr, wsb + ws.off_wp, proj_b,
+                                      out + (size_t)t * B * NF, 0, (long long)NF, Fo, 1.f, nullptr, nullptr, 0, 0, di.sms, di.smem, st,
+                                      &pex));
+    }
+    return 0;
 }
 
 int dcgru_decoder_fwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T, const float* targets,
@@ -829,6 +935,12 @@ int dcgru_decoder_fwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T,
     const int M = Mof(d), H = d->hid_dim, Fo = d->input_dim;
     if (M > 1 && !P) return fail("null P");
     if (dcgru_decoder_fwd_workspace(d, L, B, T) > workspace_bytes) return fail("workspace too small");
+    for (int l = 0; l < L; ++l)
+        if (!w[l].Wg || !w[l].bg || !w[l].Wc || !w[l].bc) return fail("null weights (layer %d)", l);
+    if (g2_dec_supported(d, L) && aligned16(workspace) && aligned16(h0) && aligned16(h_all) && aligned16(out) &&
+        (!targets || aligned16(targets)) && (!drop_mask || aligned16(drop_mask)) && (!ruc || aligned16(ruc)))
+        return g2_decoder_fwd(d, L, B, T, targets, teacher_mask, h0, P, w, proj_w, proj_b, drop_mask, out, h_all, ruc, workspace,
+                              (cudaStream_t)stream);
     int cmax = (Fo > H ? Fo : H) + H;
     FwdPlan pl;
     if (!plan_fwd(H, cmax, M, B, Fo, &pl)) return fail("no decoder tiling fits shared memory");
@@ -854,8 +966,27 @@ struct DecWs {
     float *dA, *dY, *scratch, *part0, *partb0, *part1, *partb1, *partp, *partpb;
     int ns0, nj0, ns1, nj1, nsp, njp;
     bool tc0, tc1;
+    float* g2;                 // second-generation BPTT scratch (g2_dec_bwd_ws) or nullptr
     size_t bytes;
 };
+struct G2DecBwdWs { size_t off_wb[DCGRU_MAX_LAYERS], off_wdx[DCGRU_MAX_LAYERS], off_wpb, off_img, off_scale, off_above, off_dxin, total; };
+static G2DecBwdWs g2_dec_bwd_ws(const dcgru_cell_desc* d, int L, int B, int T) {
+    G2DecBwdWs w;
+    const int H = d->hid_dim, Fo = d->input_dim, M = Mof(d), N = d->num_nodes;
+    size_t o = 0;
+    for (int l = 0; l < L; ++l) {
+        const int fin = l == 0 ? Fo : H;
+        w.off_wb[l] = o; o = align_up(o + rnn_bwd_wimg_bytes(M));
+        w.off_wdx[l] = o; o = align_up(o + bulk_wimg_bytes(3 * H, M, nout_pad(fin)));
+    }
+    w.off_wpb = o; o = align_up(o + bulk_wimg_bytes(Fo, 1, H));
+    w.off_img = o; o = align_up(o + g16_image_bytes(B, T * L, 3 * H));
+    w.off_scale = o; o = align_up(o + 256);
+    w.off_above = o; o = align_up(o + (size_t)B * N * H * 4);
+    w.off_dxin = o; o = align_up(o + (size_t)B * N * Fo * 4);
+    w.total = o;
+    return w;
+}
 static void dec_bwd_ws(const dcgru_cell_desc* d, int L, int B, int T, void* ws, DecWs* o) {
     const int H = d->hid_dim, M = Mof(d), Fo = d->input_dim, N = d->num_nodes;
     const int CM0 = (Fo + H) * M, CM1 = 2 * H * M;
@@ -879,6 +1010,8 @@ static void dec_bwd_ws(const dcgru_cell_desc* d, int L, int B, int T, void* ws, 
     o->partp = c.take((size_t)o->nsp * Fo * H);
     o->partpb = c.take((size_t)o->nsp * Fo);
     o->ptbuf = c.take(dw_tc_pt_floats(B, M));
+    o->g2 = nullptr;
+    if (g2_dec_supported(d, L)) o->g2 = c.take(g2_dec_bwd_ws(d, L, B, T).total / 4);
     o->bytes = c.off;
 }
 
@@ -914,12 +1047,68 @@ int dcgru_decoder_bwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T,
     if (o.nj0 > DW_MAXJOBS || o.nj1 > DW_MAXJOBS || o.njp > DW_MAXJOBS) return fail("too many weight-gradient jobs");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t NH = (size_t)N * H;
+    const bool use_g2 = o.g2 && aligned16(workspace) && aligned16(h0) && aligned16(h_all) && aligned16(ruc) && aligned16(d_out) &&
+                        aligned16(dh0) && (!drop_mask || aligned16(drop_mask));
     BwdPlan pl;
-    if (!plan_bwd(H, M, B, Fo, &pl)) return fail("no decoder backward tiling fits shared memory");
+    if (!use_g2 && !plan_bwd(H, M, B, Fo, &pl)) return fail("no decoder backward tiling fits shared memory");
     BwdParams p;
     memset(&p, 0, sizeof p);
     p.B = B; p.T = T; p.N = N; p.H = H; p.M = M; p.act = d->activation; p.ncell = L; p.mode = 1;
-    for (int l = 0; l < L; ++l) {
+    if (use_g2) {
+        // second-generation BPTT: one rnn_bwd (T = 1) + dX GEMM per (step, layer) cell, newest step first
+        const G2DecBwdWs ws = g2_dec_bwd_ws(d, L, B, T);
+        const DevInfo& di = devinfo();
+        uint8_t* wsb = reinterpret_cast<uint8_t*>(o.g2);
+        int cid[DCGRU_MAX_LAYERS];
+        dec_cell_ids(w, L, cid);
+        for (int l = 0; l < L; ++l) {
+            if (cid[l] != l) continue;
+            const int fin = l == 0 ? Fo : H;
+            LAUNCH("pack_w16", rnn_bwd_pack_weights(w[l].Wg, w[l].Wc, fin, M, wsb + ws.off_wb[l], st));
+            LAUNCH("pack_w16", launch_pack_w16(w[l].Wg, w[l].Wc, fin, H, M, 1, nout_pad(fin), g16_nq(3 * H, M), wsb + ws.off_wdx[l], st));
+        }
+        LAUNCH("pack_w16", launch_pack_w16(proj_w, nullptr, Fo, H, 1, 7, H, g16_nq(Fo, 1), wsb + ws.off_wpb, st));
+        float* scale = reinterpret_cast<float*>(wsb + ws.off_scale);
+        float* above = reinterpret_cast<float*>(wsb + ws.off_above);
+        float* dxin = reinterpret_cast<float*>(wsb + ws.off_dxin);
+        void* img = wsb + ws.off_img;
+        const size_t NF = (size_t)N * Fo;
+        // one power-of-two scale for every fp16 gradient operand of the launch, from the upstream gradient's magnitude
+        LAUNCH("grad_scale", launch_grad_scale(d_out, (size_t)T * B * NF, nullptr, 0, nullptr, 0, reinterpret_cast<unsigned*>(scale + 8),
+                                               scale, st));
+        CUDA_TRY(cudaMemsetAsync(dh0, 0, (size_t)L * B * NH * 4, st));                      // carried dh_{t-1} of every layer; dh0 at the end
+        for (int t = T - 1; t >= 0; --t) {
+            // total gradient of out_t: upstream + what step t+1's cell 0 sent back, unless that step was teacher-forced
+            const bool fed_back = t + 1 < T && !((teacher_mask >> t) & 1);
+            float* dYt = o.dY + (size_t)t * B * NF;
+            LAUNCH("ew", launch_ew_add_mul(d_out + (size_t)t * B * NF, fed_back ? dxin : nullptr, nullptr, dYt, (size_t)B * NF, st));
+            BulkExtra pex;
+            pex.in_scale_ptr = scale;
+            LAUNCH("dproj", launch_bulk_dp(B, 1, N, Fo, 1, H, 0, dYt, 0, (long long)NF, nullptr, nullptr, wsb + ws.off_wpb, nullptr,
+                                           above, 0, (long long)NH, H, 1.f, scale, nullptr, 0, 0, di.sms, di.smem, st, &pex));
+            if (drop_mask) LAUNCH("ew", launch_ew_add_mul(above, nullptr, drop_mask + (size_t)t * B * NH, above, (size_t)B * NH, st));
+            for (int l = L - 1; l >= 0; --l) {
+                const int fin = l == 0 ? Fo : H, c = cid[l];
+                const float* hprev = t == 0 ? h0 + (size_t)l * B * NH : h_all + ((size_t)(t - 1) * L + l) * B * NH;
+                float* carry = dh0 + (size_t)l * B * NH;
+                LAUNCH("rnn_bwd", launch_rnn_bwd(B, 1, N, fin, M, d->activation, hprev, hprev, ruc + ((size_t)t * L + l) * B * NH * 3, P,
+                                                 nullptr, nullptr, above, carry, nullptr, nullptr, wsb + ws.off_wb[c], scale, carry, img,
+                                                 st, T * L, t * L + l));
+                // input gradient: to the layer below, or (cell 0) back to out_{t-1} when that fed this step
+                const bool need_dx = l > 0 || (t > 0 && !((teacher_mask >> (t - 1)) & 1));
+                if (need_dx) {
+                    BulkExtra xex;
+                    xex.nout_valid = fin; xex.src_T = T * L; xex.src_t0 = t * L + l;
+                    LAUNCH("dx16", launch_bulk_dp(B, 1, N, 3 * H, M, nout_pad(fin), 1, nullptr, 0, 0, img, P, wsb + ws.off_wdx[c], nullptr,
+                                                  l > 0 ? above : dxin, 0, (long long)N * fin, fin, 1.f, scale, nullptr, 0, 0, di.sms,
+                                                  di.smem, st, &xex));
+                }
+            }
+        }
+        // row-major fp32 dA (T,L,B,N,3H) for the bulk weight-gradient kernels below
+        LAUNCH("img_to_rows", launch_img_to_rows(img, B, T * L, N, 3 * H, scale, o.dA, st));
+    }
+    for (int l = 0; l < L && !use_g2; ++l) {
         int fin = l == 0 ? Fo : H, CM = (fin + H) * M;
         if (l <= 1 || !tied) {
             LAUNCH("transpose", launch_transpose(w[l].Wg, CM, 2 * H, o.WgT[l], CM, st));
@@ -932,8 +1121,10 @@ int dcgru_decoder_bwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T,
     p.P = P; p.h0 = h0; p.hseq = h_all; p.ruc = ruc; p.dh0 = dh0; p.dA = o.dA;
     p.d_out = d_out; p.proj_w = proj_w; p.dropmask = drop_mask; p.teacher_mask = teacher_mask;
     p.dY = o.dY; p.scratch = o.scratch; p.Fo = Fo;
-    CUDA_TRY(cudaMemsetAsync(dh0, 0, (size_t)L * B * NH * 4, st));
-    LAUNCH("seq_bwd", launch_seq_bwd(p, pl.SB, pl.smem, st));
+    if (!use_g2) {
+        CUDA_TRY(cudaMemsetAsync(dh0, 0, (size_t)L * B * NH * 4, st));
+        LAUNCH("seq_bwd", launch_seq_bwd(p, pl.SB, pl.smem, st));
+    }
     // ---- bulk gradients ----------------------------------------------------------------------------
     DwParams q;
     memset(&q, 0, sizeof q);

@@ -165,6 +165,7 @@ cudaError_t launch_cls_head_fwd(int B, int T, int N, int H, int C, const float* 
 cudaError_t launch_cls_head_bwd(int B, int T, int N, int H, int C, const float* hseq, const int* sel_t, const float* drop,
                                 const float* W, const int* arg, const float* dlogits, float* d_hsel, float* dW, float* db,
                                 float* dwpart, cudaStream_t st);
+cudaError_t launch_ew_add_mul(const float* a, const float* b, const float* m, float* out, size_t n, cudaStream_t st);
 cudaError_t launch_scatter_sel(int B, int T, int NH, const float* d_hsel, const int* sel_t, float* dense, cudaStream_t st);
 
 }  // namespace dcgru

@@ -147,6 +147,25 @@ cudaError_t launch_cls_head_bwd(int B, int T, int N, int H, int C, const float* 
     return cudaGetLastError();
 }
 
+// out = a (+ b) (* m): the two element-wise steps of the decoder's BPTT orchestration (capi.cu): total gradient of out_t =
+// upstream + autoregressive feedback, and the dropout mask on the projection's input gradient.  n % 4 == 0, 16-byte aligned.
+__global__ void ew_add_mul_kernel(const float* a, const float* b, const float* m, float* out, size_t n4) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 v = reinterpret_cast<const float4*>(a)[i];
+        if (b) { const float4 w = reinterpret_cast<const float4*>(b)[i]; v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w; }
+        if (m) { const float4 w = reinterpret_cast<const float4*>(m)[i]; v.x *= w.x; v.y *= w.y; v.z *= w.z; v.w *= w.w; }
+        reinterpret_cast<float4*>(out)[i] = v;
+    }
+}
+cudaError_t launch_ew_add_mul(const float* a, const float* b, const float* m, float* out, size_t n, cudaStream_t st) {
+    const size_t n4 = n / 4;
+    int grid = (int)((n4 + 255) / 256);
+    if (grid > 1184) grid = 1184;
+    if (grid < 1) grid = 1;
+    ew_add_mul_kernel<<<grid, 256, 0, st>>>(a, b, m, out, n4);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_scatter_sel(int B, int T, int NH, const float* d_hsel, const int* sel_t, float* dense, cudaStream_t st) {
     scatter_sel_kernel<<<1184, 256, 0, st>>>(B, T, NH, d_hsel, sel_t, dense);
     return cudaGetLastError();

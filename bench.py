@@ -569,7 +569,7 @@ def main():
                                   "--no-extra --no-cpu-baseline`; see profiles/README.md for commit and command)",
                 "note": "kernels compute in fp32-equivalent 2xFP16 on tcgen05 (3 kind::f16 MMAs per product at the bf16 rate: "
                         "the attainable peak of this arithmetic is 1/3 of the bf16 peak); FLOPs are the as-written count of "
-                        "SURVEY 8(d); H=128 cells and the decoder run on the fp32 FMA kernels",
+                        "SURVEY 8(d); H=128 cells run on the fp32 FMA kernels",
                 "all_kernels_tflops": total_alg / (total_kms * 1e-3) / 1e12,
                 "whole_step_tflops": step_tflops, "whole_step_frac": step_tflops / peak}
 

@@ -16,6 +16,7 @@ SYMBOLS = [
     "dcgru_debug_bulk_dp_workspace", "dcgru_debug_bulk_dp", "dcgru_debug_rnn_fwd_stamps", "dcgru_debug_rnn_bwd_stamps",
     "dcgru_cls_head_fwd", "dcgru_cls_head_bwd_workspace", "dcgru_cls_head_bwd",
     "dcgru_encoder_layer_bwd_sel_workspace", "dcgru_encoder_layer_bwd_sel",
+    "dcgru_decoder_gsave_bytes", "dcgru_decoder_fwd_saved", "dcgru_decoder_bwd_saved",
 ]
 
 MAX_LAYERS = 4
@@ -69,6 +70,11 @@ def lib():
     L.dcgru_decoder_bwd_workspace.restype = sz
     L.dcgru_decoder_bwd.argtypes = [pd, i32, i32, i32, vp, u64, vp, vp, pp, vp, vp, vp, vp, vp, vp, vp, pg,
                                     vp, vp, vp, sz, vp]
+    L.dcgru_decoder_gsave_bytes.argtypes = [pd, i32, i32, i32]
+    L.dcgru_decoder_gsave_bytes.restype = sz
+    L.dcgru_decoder_fwd_saved.argtypes = [pd, i32, i32, i32, vp, u64, vp, vp, pp, vp, vp, vp, vp, vp, vp, vp, sz, vp, sz, vp]
+    L.dcgru_decoder_bwd_saved.argtypes = [pd, i32, i32, i32, vp, u64, vp, vp, pp, vp, vp, vp, vp, vp, vp, vp, pg,
+                                          vp, vp, vp, sz, vp, sz, vp]
     L.dcgru_tc_selftest.argtypes = [vp, vp, vp, i32, i32, vp]
     L.dcgru_debug_encoder_bwd_offsets.argtypes = [pd, i32, i32, C.POINTER(sz)]
     L.dcgru_tc_probe.argtypes = [vp, i32, vp, i32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, i32, i32, i32, i32, vp, i32, vp]
@@ -97,7 +103,7 @@ def lib():
                         "dcgru_encoder_layer_gsave_bytes", "dcgru_clip_adam_workspace",
                         "dcgru_decoder_fwd_workspace", "dcgru_decoder_bwd_workspace",
                         "dcgru_debug_bulk_dp_workspace", "dcgru_cls_head_bwd_workspace",
-                        "dcgru_encoder_layer_bwd_sel_workspace"):
+                        "dcgru_encoder_layer_bwd_sel_workspace", "dcgru_decoder_gsave_bytes"):
             getattr(L, name).restype = C.c_int
     _lib = L
     return L

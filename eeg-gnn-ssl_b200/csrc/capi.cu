@@ -657,7 +657,7 @@ static int encoder_layer_bwd_impl(const dcgru_cell_desc* d, int32_t batch, int32
             return 0;
         }
         // no operand image: bridge to the first-generation (recompute) weight-gradient kernels through a row-major fp32 dA
-        LAUNCH("img_to_rows", launch_img_to_rows(wsb + ws.off_img, batch, seq_len, N, 3 * H, scale, dA, st));
+        LAUNCH("img_to_rows", launch_img_to_rows(wsb + ws.off_img, batch, seq_len, N, 3 * H, scale, dA, 1, 1, 0, st));
     } else if (tc_enabled() && seq_bwd_tc_supported(d->num_nodes, H, M, devinfo().smem)) {
         // recurrent part on the tensor cores; the input gradient is not recurrent -> bulk pass over all steps
         float* wimg_b = ptbuf + ((dw_tc_pt_floats(batch, M) + 63) / 64) * 64;
@@ -844,6 +844,23 @@ static int dec_cell_ids(const dcgru_cell_params* w, int L, int* cid) {
     }
     return n;
 }
+// operand images of the decoder (saved for backward): cell 0 has T slabs (slab = t), the upper cells share one image of
+// T*(L-1) slabs (slab = t*(L-1) + l-1), which is the whole K range of the tied cell's weight-gradient GEMM
+struct G2DecImg { int kkp0, kkp1, kxp0, kxp1; size_t bytes0, bytes1; };
+static G2DecImg g2_dec_img(const dcgru_cell_desc* d, int L, int B, int T) {
+    G2DecImg g;
+    const int H = d->hid_dim, Fo = d->input_dim, M = Mof(d);
+    g.kkp0 = g16_kkp(Fo, H, M); g.kxp0 = g16_kxp(Fo, M);
+    g.kkp1 = g16_kkp(H, H, M);  g.kxp1 = g16_kxp(H, M);
+    g.bytes0 = align_up(g16_image_bytes(B, T, g.kkp0));
+    g.bytes1 = L > 1 ? align_up(g16_image_bytes(B, T * (L - 1), g.kkp1)) : 0;
+    return g;
+}
+static size_t g2_dec_gsave_bytes(const dcgru_cell_desc* d, int L, int B, int T) {
+    if (!g2_dec_supported(d, L) || !g2_gsave_enabled() || dw_mm16_smem_bytes() + 2048 > devinfo().smem) return 0;
+    const G2DecImg g = g2_dec_img(d, L, B, T);
+    return g.bytes0 + g.bytes1;
+}
 struct G2DecFwdWs { size_t off_wx[DCGRU_MAX_LAYERS], off_wh[DCGRU_MAX_LAYERS], off_bias[DCGRU_MAX_LAYERS], off_wp, off_xp, off_zero, off_hm, total; };
 static G2DecFwdWs g2_dec_fwd_ws(const dcgru_cell_desc* d, int L, int B) {
     G2DecFwdWs w;
@@ -873,10 +890,14 @@ size_t dcgru_decoder_fwd_workspace(const dcgru_cell_desc* d, int32_t L, int32_t 
 
 static int g2_decoder_fwd(const dcgru_cell_desc* d, int L, int B, int T, const float* targets, uint64_t teacher_mask,
                           const float* h0, const float* P, const dcgru_cell_params* w, const float* proj_w, const float* proj_b,
-                          const float* drop_mask, float* out, float* h_all, float* ruc, void* workspace, cudaStream_t st) {
+                          const float* drop_mask, float* out, float* h_all, float* ruc, void* gsave, void* workspace,
+                          cudaStream_t st) {
     const int M = Mof(d), H = d->hid_dim, Fo = d->input_dim, N = d->num_nodes;
     const DevInfo& di = devinfo();
     const G2DecFwdWs ws = g2_dec_fwd_ws(d, L, B);
+    const G2DecImg gi = g2_dec_img(d, L, B, T);
+    uint8_t* img0 = reinterpret_cast<uint8_t*>(gsave);
+    uint8_t* img1 = gsave ? img0 + gi.bytes0 : nullptr;
     uint8_t* wsb = reinterpret_cast<uint8_t*>(workspace);
     int cid[DCGRU_MAX_LAYERS];
     dec_cell_ids(w, L, cid);
@@ -907,11 +928,16 @@ static int g2_decoder_fwd(const dcgru_cell_desc* d, int L, int B, int T, const f
             const float* hprev = t == 0 ? h0 + (size_t)l * B * NH : h_all + ((size_t)(t - 1) * L + l) * B * NH;
             float* hout = h_all + ((size_t)t * L + l) * B * NH;
             float* rucl = ruc ? ruc + ((size_t)t * L + l) * B * NH * 3 : nullptr;
+            void* img = l == 0 ? img0 : img1;
+            const int kkp = l == 0 ? gi.kkp0 : gi.kkp1, kxp = l == 0 ? gi.kxp0 : gi.kxp1;
+            BulkExtra xex;
+            xex.img_T = l == 0 ? T : T * (L - 1);
+            xex.img_t0 = l == 0 ? t : t * (L - 1) + (l - 1);
             LAUNCH("xproj", launch_bulk_dp(B, 1, N, fin, M, 3 * H, 0, src, 0, (long long)N * fin, nullptr, P, wsb + ws.off_wx[c],
                                            reinterpret_cast<float*>(wsb + ws.off_bias[c]), xp, 0, (long long)N * 3 * H, 3 * H, 1.f,
-                                           nullptr, nullptr, 0, 0, di.sms, di.smem, st));
+                                           nullptr, img, kkp, 0, di.sms, di.smem, st, &xex));
             LAUNCH("rnn_fwd", launch_rnn_fwd(B, 1, N, fin, M, d->activation, xp, hprev, P, nullptr, nullptr, wsb + ws.off_wh[c], hout,
-                                             rucl, nullptr, 0, 0, st));
+                                             rucl, img, kkp, kxp, st, xex.img_T, xex.img_t0));
         }
         const float* top = h_all + ((size_t)t * L + (L - 1)) * B * NH;
         if (drop_mask) {                                                                     // nn.Dropout before the projection (model/model.py:192)
@@ -925,10 +951,23 @@ static int g2_decoder_fwd(const dcgru_cell_desc* d, int L, int B, int T, const f
     return 0;
 }
 
-int dcgru_decoder_fwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T, const float* targets,
-                      uint64_t teacher_mask, const float* h0, const float* P, const dcgru_cell_params* w,
-                      const float* proj_w, const float* proj_b, const float* drop_mask, float* out,
-                      float* h_all, float* ruc, void* workspace, size_t workspace_bytes, void* stream) {
+// layers >= 1 all share one cell (the reference's decoder, model/model.py:126,142-143) -- or there is at most one of them
+static bool dec_upper_tied(const dcgru_cell_params* w, int L) {
+    for (int l = 2; l < L; ++l)
+        if (w[l].Wg != w[1].Wg || w[l].Wc != w[1].Wc) return false;
+    return true;
+}
+
+size_t dcgru_decoder_gsave_bytes(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T) {
+    if (check_dec(d, L, B, T)) return 0;
+    return g2_dec_gsave_bytes(d, L, B, T);
+}
+
+static int decoder_fwd_impl(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T, const float* targets,
+                            uint64_t teacher_mask, const float* h0, const float* P, const dcgru_cell_params* w,
+                            const float* proj_w, const float* proj_b, const float* drop_mask, float* out,
+                            float* h_all, float* ruc, void* gsave, size_t gsave_bytes, void* workspace, size_t workspace_bytes,
+                            void* stream) {
     if (check_dec(d, L, B, T)) return 1;
     if (!h0 || !w || !proj_w || !proj_b || !out || !h_all || !workspace) return fail("null pointer");
     if (teacher_mask && !targets) return fail("teacher forcing requested without targets");
@@ -938,9 +977,17 @@ int dcgru_decoder_fwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T,
     for (int l = 0; l < L; ++l)
         if (!w[l].Wg || !w[l].bg || !w[l].Wc || !w[l].bc) return fail("null weights (layer %d)", l);
     if (g2_dec_supported(d, L) && aligned16(workspace) && aligned16(h0) && aligned16(h_all) && aligned16(out) &&
-        (!targets || aligned16(targets)) && (!drop_mask || aligned16(drop_mask)) && (!ruc || aligned16(ruc)))
-        return g2_decoder_fwd(d, L, B, T, targets, teacher_mask, h0, P, w, proj_w, proj_b, drop_mask, out, h_all, ruc, workspace,
-                              (cudaStream_t)stream);
+        (!targets || aligned16(targets)) && (!drop_mask || aligned16(drop_mask)) && (!ruc || aligned16(ruc))) {
+        if (gsave) {
+            const size_t need = g2_dec_gsave_bytes(d, L, B, T);
+            if (need == 0) return fail("this configuration has no operand image: pass gsave = NULL");
+            if (gsave_bytes < need) return fail("gsave too small (%zu < %zu bytes)", gsave_bytes, need);
+            if (!aligned16(gsave)) return fail("gsave must be 16-byte aligned");
+        }
+        return g2_decoder_fwd(d, L, B, T, targets, teacher_mask, h0, P, w, proj_w, proj_b, drop_mask, out, h_all, ruc, gsave,
+                              workspace, (cudaStream_t)stream);
+    }
+    if (gsave) return fail("gsave given but the tensor-core decoder path is not available for this call");
     int cmax = (Fo > H ? Fo : H) + H;
     FwdPlan pl;
     if (!plan_fwd(H, cmax, M, B, Fo, &pl)) return fail("no decoder tiling fits shared memory");
@@ -960,6 +1007,22 @@ int dcgru_decoder_fwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T,
     return 0;
 }
 
+int dcgru_decoder_fwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T, const float* targets,
+                      uint64_t teacher_mask, const float* h0, const float* P, const dcgru_cell_params* w,
+                      const float* proj_w, const float* proj_b, const float* drop_mask, float* out,
+                      float* h_all, float* ruc, void* workspace, size_t workspace_bytes, void* stream) {
+    return decoder_fwd_impl(d, L, B, T, targets, teacher_mask, h0, P, w, proj_w, proj_b, drop_mask, out, h_all, ruc, nullptr, 0,
+                            workspace, workspace_bytes, stream);
+}
+int dcgru_decoder_fwd_saved(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T, const float* targets,
+                            uint64_t teacher_mask, const float* h0, const float* P, const dcgru_cell_params* w,
+                            const float* proj_w, const float* proj_b, const float* drop_mask, float* out,
+                            float* h_all, float* ruc, void* gsave, size_t gsave_bytes, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+    return decoder_fwd_impl(d, L, B, T, targets, teacher_mask, h0, P, w, proj_w, proj_b, drop_mask, out, h_all, ruc, gsave,
+                            gsave_bytes, workspace, workspace_bytes, stream);
+}
+
 struct DecWs {
     float *WgT[DCGRU_MAX_LAYERS], *WcT[DCGRU_MAX_LAYERS];
     float *ptbuf;
@@ -969,7 +1032,8 @@ struct DecWs {
     float* g2;                 // second-generation BPTT scratch (g2_dec_bwd_ws) or nullptr
     size_t bytes;
 };
-struct G2DecBwdWs { size_t off_wb[DCGRU_MAX_LAYERS], off_wdx[DCGRU_MAX_LAYERS], off_wpb, off_img, off_scale, off_above, off_dxin, total; };
+struct G2DecBwdWs { size_t off_wb[DCGRU_MAX_LAYERS], off_wdx[DCGRU_MAX_LAYERS], off_wpb, off_img0, off_img1, off_scale, off_above, off_dxin,
+                           off_part, off_cs, total; };
 static G2DecBwdWs g2_dec_bwd_ws(const dcgru_cell_desc* d, int L, int B, int T) {
     G2DecBwdWs w;
     const int H = d->hid_dim, Fo = d->input_dim, M = Mof(d), N = d->num_nodes;
@@ -980,7 +1044,10 @@ static G2DecBwdWs g2_dec_bwd_ws(const dcgru_cell_desc* d, int L, int B, int T) {
         w.off_wdx[l] = o; o = align_up(o + bulk_wimg_bytes(3 * H, M, nout_pad(fin)));
     }
     w.off_wpb = o; o = align_up(o + bulk_wimg_bytes(Fo, 1, H));
-    w.off_img = o; o = align_up(o + g16_image_bytes(B, T * L, 3 * H));
+    w.off_img0 = o; o = align_up(o + g16_image_bytes(B, T, 3 * H));                       // dA image of cell 0, slab = t
+    w.off_img1 = o; o = align_up(o + g16_image_bytes(B, T * (L > 1 ? L - 1 : 0), 3 * H));   // upper cells, slab = t*(L-1) + l-1
+    w.off_part = o; o = align_up(o + dw_mm16_part_floats(devinfo().sms) * 4);
+    w.off_cs = o; o = align_up(o + colsum16_part_floats(H) * 4);
     w.off_scale = o; o = align_up(o + 256);
     w.off_above = o; o = align_up(o + (size_t)B * N * H * 4);
     w.off_dxin = o; o = align_up(o + (size_t)B * N * Fo * 4);
@@ -1022,11 +1089,12 @@ size_t dcgru_decoder_bwd_workspace(const dcgru_cell_desc* d, int32_t L, int32_t 
     return o.bytes;
 }
 
-int dcgru_decoder_bwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T, const float* targets,
-                      uint64_t teacher_mask, const float* h0, const float* P, const dcgru_cell_params* w,
-                      const float* proj_w, const float* drop_mask, const float* out, const float* h_all,
-                      const float* ruc, const float* d_out, float* dh0, const dcgru_cell_grads* g,
-                      float* dproj_w, float* dproj_b, void* workspace, size_t workspace_bytes, void* stream) {
+static int decoder_bwd_impl(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T, const float* targets,
+                            uint64_t teacher_mask, const float* h0, const float* P, const dcgru_cell_params* w,
+                            const float* proj_w, const float* drop_mask, const float* out, const float* h_all,
+                            const float* ruc, const float* d_out, float* dh0, const dcgru_cell_grads* g,
+                            float* dproj_w, float* dproj_b, const void* gsave, size_t gsave_bytes, void* workspace,
+                            size_t workspace_bytes, void* stream) {
     if (check_dec(d, L, B, T)) return 1;
     if (!h0 || !w || !proj_w || !out || !h_all || !ruc || !d_out || !dh0 || !g || !dproj_w || !dproj_b || !workspace)
         return fail("null pointer");
@@ -1047,6 +1115,8 @@ int dcgru_decoder_bwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T,
     if (o.nj0 > DW_MAXJOBS || o.nj1 > DW_MAXJOBS || o.njp > DW_MAXJOBS) return fail("too many weight-gradient jobs");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t NH = (size_t)N * H;
+    const bool tied_or_single = dec_upper_tied(w, L);
+    bool cells_done = false;
     const bool use_g2 = o.g2 && aligned16(workspace) && aligned16(h0) && aligned16(h_all) && aligned16(ruc) && aligned16(d_out) &&
                         aligned16(dh0) && (!drop_mask || aligned16(drop_mask));
     BwdPlan pl;
@@ -1071,8 +1141,14 @@ int dcgru_decoder_bwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T,
         float* scale = reinterpret_cast<float*>(wsb + ws.off_scale);
         float* above = reinterpret_cast<float*>(wsb + ws.off_above);
         float* dxin = reinterpret_cast<float*>(wsb + ws.off_dxin);
-        void* img = wsb + ws.off_img;
+        uint8_t* dimg0 = wsb + ws.off_img0;
+        uint8_t* dimg1 = wsb + ws.off_img1;
         const size_t NF = (size_t)N * Fo;
+        if (gsave) {
+            const size_t need = g2_dec_gsave_bytes(d, L, B, T);
+            if (need == 0) return fail("this configuration has no operand image: pass gsave = NULL");
+            if (gsave_bytes < need) return fail("gsave too small (%zu < %zu bytes)", gsave_bytes, need);
+        }
         // one power-of-two scale for every fp16 gradient operand of the launch, from the upstream gradient's magnitude
         LAUNCH("grad_scale", launch_grad_scale(d_out, (size_t)T * B * NF, nullptr, 0, nullptr, 0, reinterpret_cast<unsigned*>(scale + 8),
                                                scale, st));
@@ -1091,22 +1167,42 @@ int dcgru_decoder_bwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T,
                 const int fin = l == 0 ? Fo : H, c = cid[l];
                 const float* hprev = t == 0 ? h0 + (size_t)l * B * NH : h_all + ((size_t)(t - 1) * L + l) * B * NH;
                 float* carry = dh0 + (size_t)l * B * NH;
+                void* img = l == 0 ? dimg0 : dimg1;
+                const int img_T = l == 0 ? T : T * (L - 1), img_t0 = l == 0 ? t : t * (L - 1) + (l - 1);
                 LAUNCH("rnn_bwd", launch_rnn_bwd(B, 1, N, fin, M, d->activation, hprev, hprev, ruc + ((size_t)t * L + l) * B * NH * 3, P,
                                                  nullptr, nullptr, above, carry, nullptr, nullptr, wsb + ws.off_wb[c], scale, carry, img,
-                                                 st, T * L, t * L + l));
+                                                 st, img_T, img_t0));
                 // input gradient: to the layer below, or (cell 0) back to out_{t-1} when that fed this step
                 const bool need_dx = l > 0 || (t > 0 && !((teacher_mask >> (t - 1)) & 1));
                 if (need_dx) {
                     BulkExtra xex;
-                    xex.nout_valid = fin; xex.src_T = T * L; xex.src_t0 = t * L + l;
+                    xex.nout_valid = fin; xex.src_T = img_T; xex.src_t0 = img_t0;
                     LAUNCH("dx16", launch_bulk_dp(B, 1, N, 3 * H, M, nout_pad(fin), 1, nullptr, 0, 0, img, P, wsb + ws.off_wdx[c], nullptr,
                                                   l > 0 ? above : dxin, 0, (long long)N * fin, fin, 1.f, scale, nullptr, 0, 0, di.sms,
                                                   di.smem, st, &xex));
                 }
             }
         }
-        // row-major fp32 dA (T,L,B,N,3H) for the bulk weight-gradient kernels below
-        LAUNCH("img_to_rows", launch_img_to_rows(img, B, T * L, N, 3 * H, scale, o.dA, st));
+        if (gsave && tied_or_single) {
+            // weight gradients of the cells: GEMMs over the saved operand images (forward: G, here: dA), bias: column sums
+            const G2DecImg gi = g2_dec_img(d, L, B, T);
+            const uint8_t* g0 = reinterpret_cast<const uint8_t*>(gsave);
+            float* part = reinterpret_cast<float*>(wsb + ws.off_part);
+            float* cs = reinterpret_cast<float*>(wsb + ws.off_cs);
+            LAUNCH("dw_mm16", launch_dw_mm16(Fo, H, M, B, T, g0, dimg0, part, scale, di.sms, g[0].dWg, g[0].dWc, st));
+            LAUNCH("colsum16", launch_colsum16(dimg0, B, T, H, cs, scale, g[0].dbg, g[0].dbc, st));
+            if (L > 1) {
+                LAUNCH("dw_mm16", launch_dw_mm16(H, H, M, B, T * (L - 1), g0 + gi.bytes0, dimg1, part, scale, di.sms, g[1].dWg, g[1].dWc, st));
+                LAUNCH("colsum16", launch_colsum16(dimg1, B, T * (L - 1), H, cs, scale, g[1].dbg, g[1].dbc, st));
+            }
+            cells_done = true;
+        } else {
+            // row-major fp32 dA (T,L,B,N,3H) for the recompute weight-gradient kernels below
+            LAUNCH("img_to_rows", launch_img_to_rows(dimg0, B, T, N, 3 * H, scale, o.dA, 1, L, 0, st));
+            if (L > 1) LAUNCH("img_to_rows", launch_img_to_rows(dimg1, B, T * (L - 1), N, 3 * H, scale, o.dA, L - 1, L, 1, st));
+        }
+    } else if (gsave) {
+        return fail("gsave given but the tensor-core decoder path is not available for this call");
     }
     for (int l = 0; l < L && !use_g2; ++l) {
         int fin = l == 0 ? Fo : H, CM = (fin + H) * M;
@@ -1132,6 +1228,7 @@ int dcgru_decoder_bwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T,
     q.P = P; q.h0 = h0; q.hseq = h_all; q.ruc = ruc; q.dA = o.dA; q.targets = targets; q.out = out;
     q.teacher_mask = teacher_mask; q.dY = o.dY; q.dropmask = drop_mask;
     // cell 0
+    if (!cells_done) {
     if (o.tc0 || o.tc1) LAUNCH("make_pt", launch_make_pt(P, B, M, N, o.ptbuf, st));
     q.layer = 0; q.fin = Fo; q.nsplit = o.ns0; q.part = o.part0; q.partb = o.partb0;
     q.dY = o.tc0 ? o.ptbuf : o.dY;
@@ -1154,6 +1251,7 @@ int dcgru_decoder_bwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T,
     if (tied)
         LAUNCH("reduce", launch_reduce_cell(o.part1, o.partb1, (L - 1) * o.ns1, 2 * H * M, H, g[1].dWg, g[1].dbg, g[1].dWc,
                                     g[1].dbc, st));
+    }
     // Linear
     q.layer = L - 1; q.fin = Fo; q.nsplit = o.nsp; q.part = o.partp; q.partb = o.partpb; q.dY = o.dY;
     build_proj_jobs(Fo, H, q.jobs);
@@ -1161,6 +1259,24 @@ int dcgru_decoder_bwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T,
     LAUNCH("reduce", launch_reduce_flat(o.partp, o.nsp, (size_t)Fo * H, dproj_w, st));
     LAUNCH("reduce", launch_reduce_flat(o.partpb, o.nsp, (size_t)Fo, dproj_b, st));
     return 0;
+}
+
+int dcgru_decoder_bwd(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T, const float* targets,
+                      uint64_t teacher_mask, const float* h0, const float* P, const dcgru_cell_params* w,
+                      const float* proj_w, const float* drop_mask, const float* out, const float* h_all,
+                      const float* ruc, const float* d_out, float* dh0, const dcgru_cell_grads* g,
+                      float* dproj_w, float* dproj_b, void* workspace, size_t workspace_bytes, void* stream) {
+    return decoder_bwd_impl(d, L, B, T, targets, teacher_mask, h0, P, w, proj_w, drop_mask, out, h_all, ruc, d_out, dh0, g, dproj_w,
+                            dproj_b, nullptr, 0, workspace, workspace_bytes, stream);
+}
+int dcgru_decoder_bwd_saved(const dcgru_cell_desc* d, int32_t L, int32_t B, int32_t T, const float* targets,
+                            uint64_t teacher_mask, const float* h0, const float* P, const dcgru_cell_params* w,
+                            const float* proj_w, const float* drop_mask, const float* out, const float* h_all,
+                            const float* ruc, const float* d_out, float* dh0, const dcgru_cell_grads* g,
+                            float* dproj_w, float* dproj_b, const void* gsave, size_t gsave_bytes, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+    return decoder_bwd_impl(d, L, B, T, targets, teacher_mask, h0, P, w, proj_w, drop_mask, out, h_all, ruc, d_out, dh0, g, dproj_w,
+                            dproj_b, gsave, gsave_bytes, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -147,7 +147,8 @@ cudaError_t launch_rnn_bwd(int B, int T, int N, int fin, int M, int act, const f
                            const float* d_hsel, const int* sel_t, void* wimg, const float* scale_ptr, float* dh0, void* daimg,
                            cudaStream_t st, int img_T = 0, int img_t0 = 0);
 cudaError_t rnn_bwd_pack_weights(const float* Wg, const float* Wc, int fin, int M, void* wimg, cudaStream_t st);
-cudaError_t launch_img_to_rows(const void* img, int B, int T, int N, int cols, const float* scale_ptr, float* out, cudaStream_t st);
+cudaError_t launch_img_to_rows(const void* img, int B, int T, int N, int cols, const float* scale_ptr, float* out, int group,
+                               int stride, int off, cudaStream_t st);
 
 size_t dw_mm16_part_floats(int nsms);
 size_t colsum16_part_floats(int H);

@@ -527,7 +527,9 @@ cudaError_t launch_rnn_bwd(int B, int T, int N, int fin, int M, int act, const f
 namespace dcgru {
 // operand image [tile*T+t][hi|lo][96][cols] (scaled by *scale_ptr) -> row-major fp32 (T,B,N,cols): diagnostics, and the
 // bridge to the first-generation weight-gradient kernels
-__global__ void img_to_rows_kernel(const __half* img, int B, int T, int N, int cols, const float* scale_ptr, float* out) {
+// image slab t' lands in output slab (t' / group) * stride + off + t' % group (decoder: layers interleaved per step)
+__global__ void img_to_rows_kernel(const __half* img, int B, int T, int N, int cols, const float* scale_ptr, float* out, int group,
+                                   int stride, int off) {
     const float inv = 1.f / scale_ptr[0];
     const size_t total = (size_t)T * B * N * cols;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -538,11 +540,13 @@ __global__ void img_to_rows_kernel(const __half* img, int B, int T, int N, int c
         const int t = (int)(r / B);
         const size_t slab = (size_t)(b / f16::SB) * T + t;
         const size_t o = ((slab * 2) * f16::IMG_ROWS + (b % f16::SB) * (f16::RG * 8) + n) * cols + c;
-        out[idx] = (__half2float(img[o]) + __half2float(img[o + (size_t)f16::IMG_ROWS * cols])) * inv;
+        const int ot = (t / group) * stride + off + t % group;
+        out[(((size_t)ot * B + b) * N + n) * cols + c] = (__half2float(img[o]) + __half2float(img[o + (size_t)f16::IMG_ROWS * cols])) * inv;
     }
 }
-cudaError_t launch_img_to_rows(const void* img, int B, int T, int N, int cols, const float* scale_ptr, float* out, cudaStream_t st) {
-    img_to_rows_kernel<<<1184, 256, 0, st>>>(reinterpret_cast<const __half*>(img), B, T, N, cols, scale_ptr, out);
+cudaError_t launch_img_to_rows(const void* img, int B, int T, int N, int cols, const float* scale_ptr, float* out, int group,
+                               int stride, int off, cudaStream_t st) {
+    img_to_rows_kernel<<<1184, 256, 0, st>>>(reinterpret_cast<const __half*>(img), B, T, N, cols, scale_ptr, out, group, stride, off);
     return cudaGetLastError();
 }
 }  // namespace dcgru

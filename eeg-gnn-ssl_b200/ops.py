@@ -278,9 +278,15 @@ class _DecoderFn(torch.autograd.Function):
         ws = _params([tuple(flat[4 * c: 4 * c + 4]) for c in cells])
         nbytes = L.dcgru_decoder_fwd_workspace(C.byref(desc), num_layers, b, to_len)
         ws_buf = torch.empty(max(nbytes, 16), device=dev, dtype=torch.uint8)
-        check(L.dcgru_decoder_fwd(C.byref(desc), num_layers, b, to_len, _ptr(targets), teacher_mask, _ptr(h0),
-                                  _ptr(p), ws, _ptr(proj_w), _ptr(proj_b), _ptr(drop_mask), _ptr(out),
-                                  _ptr(h_all), _ptr(ruc), _ptr(ws_buf), nbytes, _stream()), "decoder_fwd")
+        # operand image for the weight-gradient GEMMs (tensor-core configurations only; 0 bytes otherwise)
+        need = any(ctx.needs_input_grad)
+        gbytes = L.dcgru_decoder_gsave_bytes(C.byref(desc), num_layers, b, to_len) if need else 0
+        gsave = torch.empty(gbytes, device=dev, dtype=torch.uint8) if gbytes else None
+        check(L.dcgru_decoder_fwd_saved(C.byref(desc), num_layers, b, to_len, _ptr(targets), teacher_mask, _ptr(h0),
+                                        _ptr(p), ws, _ptr(proj_w), _ptr(proj_b), _ptr(drop_mask), _ptr(out),
+                                        _ptr(h_all), _ptr(ruc), _ptr(gsave), gbytes, _ptr(ws_buf), nbytes, _stream()),
+              "decoder_fwd")
+        ctx.gsave = gsave
         ctx.desc, ctx.meta = desc, (num_layers, to_len, teacher_mask, tuple(cells), len(flat))
         ctx.save_for_backward(targets, h0, p, proj_w, drop_mask, out, h_all, ruc, *flat)
         return out
@@ -304,10 +310,13 @@ class _DecoderFn(torch.autograd.Function):
             g[l] = CellGrads(*(grads[4 * c + k].data_ptr() for k in range(4)))
         nbytes = L.dcgru_decoder_bwd_workspace(C.byref(desc), num_layers, b, to_len)
         ws_buf = torch.empty(nbytes, device=dev, dtype=torch.uint8)
-        check(L.dcgru_decoder_bwd(C.byref(desc), num_layers, b, to_len, _ptr(targets), teacher_mask, _ptr(h0),
-                                  _ptr(p), ws, _ptr(proj_w), _ptr(drop_mask), _ptr(out), _ptr(h_all),
-                                  _ptr(ruc), _ptr(d_out), _ptr(dh0), g, _ptr(dpw), _ptr(dpb), _ptr(ws_buf),
-                                  nbytes, _stream()), "decoder_bwd")
+        gsave = ctx.gsave
+        check(L.dcgru_decoder_bwd_saved(C.byref(desc), num_layers, b, to_len, _ptr(targets), teacher_mask, _ptr(h0),
+                                        _ptr(p), ws, _ptr(proj_w), _ptr(drop_mask), _ptr(out), _ptr(h_all),
+                                        _ptr(ruc), _ptr(d_out), _ptr(dh0), g, _ptr(dpw), _ptr(dpb), _ptr(gsave),
+                                        gsave.numel() if gsave is not None else 0, _ptr(ws_buf),
+                                        nbytes, _stream()), "decoder_bwd")
+        ctx.gsave = None
         return (None, dh0, None, dpw, dpb, None, None, None, None, None, None, *grads)
 
 

@@ -232,6 +232,28 @@ int dcgru_decoder_bwd(const dcgru_cell_desc *d, int32_t num_layers, int32_t batc
                       float *dproj_w, float *dproj_b,
                       void *workspace, size_t workspace_bytes, void *stream);
 
+/* The same two calls with a caller-owned operand image saved for backward (the decoder's counterpart of the encoder's
+ * gsave): when dcgru_decoder_gsave_bytes() is non-zero the tensor-core kernels serve this configuration (H = 64) and the
+ * forward pass can leave the diffused GEMM operands of every (step, layer) cell in gsave -- cell 0: T slabs, the tied
+ * upper cell: T*(L-1) slabs -- so that the backward pass computes the cells' weight gradients as GEMMs over saved
+ * operands (one per distinct cell: the tied cell's gradient sums over layers and steps inside the GEMM's K range,
+ * model/model.py:126,142-143) instead of recomputing the diffusion.  gsave = NULL: exactly dcgru_decoder_fwd / _bwd.   */
+size_t dcgru_decoder_gsave_bytes(const dcgru_cell_desc *d, int32_t num_layers, int32_t batch, int32_t seq_len);
+int dcgru_decoder_fwd_saved(const dcgru_cell_desc *d, int32_t num_layers, int32_t batch,
+                            int32_t seq_len, const float *targets, uint64_t teacher_mask,
+                            const float *h0, const float *P, const dcgru_cell_params *w,
+                            const float *proj_w, const float *proj_b, const float *drop_mask,
+                            float *out, float *h_all, float *ruc, void *gsave, size_t gsave_bytes,
+                            void *workspace, size_t workspace_bytes, void *stream);
+int dcgru_decoder_bwd_saved(const dcgru_cell_desc *d, int32_t num_layers, int32_t batch,
+                            int32_t seq_len, const float *targets, uint64_t teacher_mask,
+                            const float *h0, const float *P, const dcgru_cell_params *w,
+                            const float *proj_w, const float *drop_mask,
+                            const float *out, const float *h_all, const float *ruc,
+                            const float *d_out, float *dh0, const dcgru_cell_grads *g,
+                            float *dproj_w, float *dproj_b, const void *gsave, size_t gsave_bytes,
+                            void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- diagnostics of the second-generation (2xFP16) kernels: one stage at a time ----------------
  * mode 0: out (T,B,N,3H) = sum_m (P_m x_t) [Wg_x | Wc_x]_m + bias   (the hoisted x-part of model/cell.py:73-116);
  *         img (may be NULL): fp16 operand image [tile*T+t][hi|lo][96][img_cols], columns from img_col0

@@ -26,9 +26,10 @@ def dev():
     return torch.device("cuda:0")
 
 
-def _run(dev, dec, tgt, ctx, sup, dout, ratio, seed, g2):
+def _run(dev, dec, tgt, ctx, sup, dout, ratio, seed, g2, gsave=True):
     import random
     os.environ["DCGRU_G2_DEC"] = "1" if g2 else "0"
+    os.environ["DCGRU_DISABLE_GSAVE"] = "0" if gsave else "1"
     try:
         dec.zero_grad(set_to_none=True)
         random.seed(seed)
@@ -42,6 +43,7 @@ def _run(dev, dec, tgt, ctx, sup, dout, ratio, seed, g2):
         return res
     finally:
         os.environ.pop("DCGRU_G2_DEC", None)
+        os.environ.pop("DCGRU_DISABLE_GSAVE", None)
 
 
 @pytest.mark.parametrize("S,L,B,To,ratio,p_drop", [(1, 3, 10, 6, None, 0.0), (1, 3, 7, 5, 0.5, 0.3), (2, 2, 9, 4, 0.5, 0.0)])
@@ -66,8 +68,10 @@ def test_decoder_g2_matches_oracle_and_fma(dev, S, L, B, To, ratio, p_drop):
     seed = 1234
     a = _run(dev, dec, tgt, ctx, sup, dout, ratio, seed, True)
     b = _run(dev, dec, tgt, ctx, sup, dout, ratio, seed, False)
+    c = _run(dev, dec, tgt, ctx, sup, dout, ratio, seed, True, gsave=False)     # recompute weight gradient instead of the image GEMM
     for k in a:
         assert rel_err(a[k], b[k]) < 2e-5, (k, rel_err(a[k], b[k]))
+        assert rel_err(c[k], b[k]) < 2e-5, (k, rel_err(c[k], b[k]))
 
     # float64 oracle with the same draws: python's random for teacher forcing, torch's CUDA generator for the masks
     random.seed(seed)

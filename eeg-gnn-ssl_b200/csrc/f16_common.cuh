@@ -232,6 +232,189 @@ __device__ __forceinline__ void store_cols2(uint8_t* slot, int row0, int lane, i
     }
 }
 
+// ---- diffusion of a 64-column tile on the warp-level tensor path (mma.sync m16n8k16, 2xFP16) ---------------------------
+// out[n][c] = sum_j PT[j][n] * z[j][c] for one (sample, term): A = P (rows n, padded to 32; K = j, padded to 32) split hi/lo
+// from the fp32 block PT, B = z split hi/lo from an fp32 shared-memory tile (row stride zld floats, zld % 32 == 4 keeps
+// the fragment loads conflict-free), three MMAs per product (a_lo*b_hi + a_hi*b_lo + a_hi*b_hi) with fp32 accumulation --
+// the arithmetic of the tcgen05 kernels.  The FMA version (diffuse2 above) is bound by shared-memory RETURN bandwidth:
+// every broadcast LDS.128 of a P^T row delivers 512 B to the warp, 22 LSU data cycles per source row against 10 of
+// FFMA2 issue (measured ~56 of 128 FMA/clk/SM, profiles/fma_rate_r02.txt); here the polynomial lives in registers for the
+// whole task and shared memory is read once per source element.
+// The accumulator fragment holds adjacent columns (c, c+1) of a row, so results go to the chunk slot as 4-byte hi / lo
+// stores exactly like store_cols2: rows n < 24 of the sample's 32-row block are written (rows N..23 come out as exact
+// zeros because P has no such rows), rows 24..31 are left alone.
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};\n"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+struct PFrag { uint32_t hi[2][2][4], lo[2][2][4]; };       // [m tile][k tile][a0..a3]
+// PT: this (sample, term)'s [j][NPAD] block (zero beyond N)
+__device__ __forceinline__ void load_pfrag(const float* PT, int lane, PFrag& f) {
+    const int g = lane >> 2, t = lane & 3;
+    auto P = [&](int n, int j) { return (n < NPAD && j < NPAD) ? PT[j * NPAD + n] : 0.f; };
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt) {
+            const int r0 = 16 * mt + g, r1 = r0 + 8, j0 = 16 * kt + 2 * t;
+            split2(P(r0, j0), P(r0, j0 + 1), f.hi[mt][kt][0], f.lo[mt][kt][0]);
+            split2(P(r0, j0 + 8), P(r0, j0 + 9), f.hi[mt][kt][2], f.lo[mt][kt][2]);
+            if (mt == 0) {
+                split2(P(r1, j0), P(r1, j0 + 1), f.hi[mt][kt][1], f.lo[mt][kt][1]);
+                split2(P(r1, j0 + 8), P(r1, j0 + 9), f.hi[mt][kt][3], f.lo[mt][kt][3]);
+            } else {                                                    // rows 24..31: no such nodes
+                f.hi[mt][kt][1] = 0u; f.lo[mt][kt][1] = 0u; f.hi[mt][kt][3] = 0u; f.lo[mt][kt][3] = 0u;
+            }
+        }
+}
+// z: (source row 0, column 0) of the sample's fp32 tile; slot: chunk slot (hi plane, lo plane PLANE further); row0: the
+// sample's first tile row; values are multiplied by `scale` before the split
+__device__ __forceinline__ void diffuse_mma(const float* z, int zld, int N, const PFrag& pf, uint8_t* slot, int row0, int lane,
+                                            float scale) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll 1
+    for (int grp = 0; grp < 4; ++grp) {
+        uint32_t bh[2][2][2], bl[2][2][2];                 // [n tile][k tile][b0, b1]
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            const float* zc = z + 16 * grp + 8 * nt + g;
+#pragma unroll
+            for (int kt = 0; kt < 2; ++kt) {
+                const int j0 = 16 * kt + 2 * t;
+                const float v0 = j0 < N ? zc[j0 * zld] : 0.f, v1 = j0 + 1 < N ? zc[(j0 + 1) * zld] : 0.f;
+                const float v2 = j0 + 8 < N ? zc[(j0 + 8) * zld] : 0.f, v3 = j0 + 9 < N ? zc[(j0 + 9) * zld] : 0.f;
+                split2(v0, v1, bh[nt][kt][0], bl[nt][kt][0]);
+                split2(v2, v3, bh[nt][kt][1], bl[nt][kt][1]);
+            }
+        }
+        // four independent accumulators (m tile x n tile) per dependent step: a dependent HMMA chain costs ~33 cycles per link
+        float d[2][2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) { d[mt][nt][0] = 0.f; d[mt][nt][1] = 0.f; d[mt][nt][2] = 0.f; d[mt][nt][3] = 0.f; }
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt) {
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) mma_f16_16816(d[mt][nt], pf.lo[mt][kt], bh[nt][kt]);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) mma_f16_16816(d[mt][nt], pf.hi[mt][kt], bl[nt][kt]);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) mma_f16_16816(d[mt][nt], pf.hi[mt][kt], bh[nt][kt]);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const int col = 16 * grp + 8 * nt + 2 * t;
+                uint32_t hi, lo;
+                split2(d[mt][nt][0] * scale, d[mt][nt][1] * scale, hi, lo);
+                uint32_t off = k128_off(row0 + 16 * mt + g, col);
+                *reinterpret_cast<uint32_t*>(slot + off) = hi;
+                *reinterpret_cast<uint32_t*>(slot + PLANE + off) = lo;
+                if (mt == 0) {                             // rows 24..31 of the block do not exist
+                    split2(d[mt][nt][2] * scale, d[mt][nt][3] * scale, hi, lo);
+                    off = k128_off(row0 + 8 + g, col);
+                    *reinterpret_cast<uint32_t*>(slot + off) = hi;
+                    *reinterpret_cast<uint32_t*>(slot + PLANE + off) = lo;
+                }
+            }
+    }
+}
+
+// The same with the source already in fp16 hi / lo form: a K-major SWIZZLE_128B chunk (rows = tile rows, 64 columns), e.g.
+// the term-0 chunk the epilogue wrote for the tensor core.  ldmatrix.trans hands every lane exactly its B fragment
+// (source rows 2t, 2t+1 of column g), one instruction per (n tile, plane) for both k tiles; the 16-byte units of
+// eight consecutive rows sit in eight different bank groups (that is what the swizzle is for).  Rows >= N of the
+// source block must be finite (they meet zero polynomial entries); the callers keep them zero.
+__device__ __forceinline__ void mma_f16_1688(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};\n"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(b0));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr) : "memory");
+}
+__device__ __forceinline__ void diffuse_mma16(const uint8_t* src, int srow0, const PFrag& pf, uint8_t* slot, int row0, int lane,
+                                              float scale) {
+    const int g = lane >> 2, t = lane & 3;
+    const int sr = srow0 + lane;                                        // lane i supplies the address of source row i
+    const uint32_t rbase = smem_u32(src) + (uint32_t)((sr >> 3) * 1024 + (sr & 7) * 128);
+#pragma unroll 1
+    for (int grp = 0; grp < 4; ++grp) {
+        uint32_t bh[2][4], bl[2][4];                                    // [n tile][kt0.b0, kt0.b1, kt1.b0, kt1.b1]
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+            const uint32_t a = rbase + (uint32_t)((((2 * grp + nt) ^ (sr & 7)) << 4));
+            ldmatrix_x4_trans(bh[nt], a);
+            ldmatrix_x4_trans(bl[nt], a + PLANE);
+        }
+        float d[2][2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) { d[mt][nt][0] = 0.f; d[mt][nt][1] = 0.f; d[mt][nt][2] = 0.f; d[mt][nt][3] = 0.f; }
+        // source rows 0..15: k16; rows 16..23: k8 (N <= 24; the fragments of rows 24..31 are not used)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const uint32_t b[2] = {bh[nt][0], bh[nt][1]};
+                mma_f16_16816(d[mt][nt], pf.lo[mt][0], b);
+            }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const uint32_t b[2] = {bl[nt][0], bl[nt][1]};
+                mma_f16_16816(d[mt][nt], pf.hi[mt][0], b);
+            }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const uint32_t b[2] = {bh[nt][0], bh[nt][1]};
+                mma_f16_16816(d[mt][nt], pf.hi[mt][0], b);
+            }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) mma_f16_1688(d[mt][nt], pf.lo[mt][1][0], pf.lo[mt][1][1], bh[nt][2]);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) mma_f16_1688(d[mt][nt], pf.hi[mt][1][0], pf.hi[mt][1][1], bl[nt][2]);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) mma_f16_1688(d[mt][nt], pf.hi[mt][1][0], pf.hi[mt][1][1], bh[nt][2]);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const int col = 16 * grp + 8 * nt + 2 * t;
+                uint32_t hi, lo;
+                split2(d[mt][nt][0] * scale, d[mt][nt][1] * scale, hi, lo);
+                uint32_t off = k128_off(row0 + 16 * mt + g, col);
+                *reinterpret_cast<uint32_t*>(slot + off) = hi;
+                *reinterpret_cast<uint32_t*>(slot + PLANE + off) = lo;
+                if (mt == 0) {
+                    split2(d[mt][nt][2] * scale, d[mt][nt][3] * scale, hi, lo);
+                    off = k128_off(row0 + 8 + g, col);
+                    *reinterpret_cast<uint32_t*>(slot + off) = hi;
+                    *reinterpret_cast<uint32_t*>(slot + PLANE + off) = lo;
+                }
+            }
+    }
+}
+
 // transposed polynomials of one tile into shared memory: PT[(s * nterm + m) * PT_STRIDE + j * NPAD + n]
 //   forward  (transpose = 0): PT[j][n] = P[b][m][n][j]   (out[n] = sum_j P[n][j] z[j])
 //   backward (transpose = 1): PT[j][n] = P[b][m][j][n]   (out[n] = sum_j P[j][n] z[j] = (P^T z)[n])

@@ -41,6 +41,7 @@ constexpr int RF_ACC1 = 192, RF_STASH = 384, RF_RSTASH = 448;   // TMEM columns:
 struct RnnFwdParams {
     int B, T, N, M, act, dump, img_col0, dbg;
     int img_T, img_t0;          // slab of step t in the operand image: tile * img_T + img_t0 + t
+    int mma_diff;               // diffusion on the warp-level tensor path (DCGRU_MMA_DIFF=0: fp32 FMA loop)
     const float* xp;            // (T,B,N,3H)
     const float* h0;            // (B,N*H)
     const float* P;             // (B,M-1,N,N)
@@ -284,10 +285,19 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
                 const int s = (warp - ((m - 1) * SB)) & 7;
                 if (s < SB) {
                     acquire(slot, true);
-                    float acc[NPAD][2];
-                    diffuse2(ZH + (s * RP) * RF_ZLD + 2 * lane, RF_ZLD, N, PTs + (s * (M - 1) + (m - 1)) * PT_STRIDE, acc);
-                    // (rows N..23 are dumped to the operand image and aliased by the staging tiles: rewrite them as zeros)
-                    store_cols2(Aslots + slot * SLOT, s * RP, lane, N, acc, 1.f, RG * 8);
+                    const float* pt = PTs + (s * (M - 1) + (m - 1)) * PT_STRIDE;
+                    if (p.mma_diff) {
+                        // warp-level tensor path (f16_common.cuh::diffuse_mma16): the source is the term-0 chunk itself (slot 0,
+                        // hi / lo fp16, just published by the epilogue); rows 0..23 of the sample's block are written
+                        PFrag pf;
+                        load_pfrag(pt, lane, pf);
+                        diffuse_mma16(Aslots, s * RP, pf, Aslots + slot * SLOT, s * RP, lane, 1.f);
+                    } else {
+                        float acc[NPAD][2];
+                        diffuse2(ZH + (s * RP) * RF_ZLD + 2 * lane, RF_ZLD, N, pt, acc);
+                        // (rows N..23 are dumped to the operand image and aliased by the staging tiles: rewrite them as zeros)
+                        store_cols2(Aslots + slot * SLOT, s * RP, lane, N, acc, 1.f, RG * 8);
+                    }
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_n(&bar_afull[slot], 2);
@@ -422,6 +432,7 @@ cudaError_t launch_rnn_fwd(int B, int T, int N, int fin, int M, int act, const f
     p.B = B; p.T = T; p.N = N; p.M = M; p.act = act; p.dump = img != nullptr; p.img_col0 = img_col0;
     p.img_T = img_T > 0 ? img_T : T; p.img_t0 = img_T > 0 ? img_t0 : 0;
     { const char* e = getenv("DCGRU_DBG"); p.dbg = e ? (atoi(e) & (16 | 64 | 128 | 256 | 512)) : 0; }
+    { const char* e = getenv("DCGRU_MMA_DIFF"); p.mma_diff = !(e && e[0] == '0'); }
     p.xp = xp; p.h0 = h0; p.P = P; p.wimg = reinterpret_cast<const uint8_t*>(wimg); p.hseq = hseq; p.ruc = ruc;
     CUtensorMap tm;
     memset(&tm, 0, sizeof tm);

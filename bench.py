@@ -467,6 +467,37 @@ def measure(w, steps, warmup, world, kernel_steps=3, want_e2e=True, want_eager=T
     return res
 
 
+def input_pipeline_leg(cfg, dev, hbm_gbs, iters=10):
+    """SURVEY 8(f) N2 next to the step: raw resampled EEG (B, 19, T*200) resident in HBM -> fft_features (x and the raw
+    features for the correlation graph).  HBM-bound byte work: algorithmic bytes = 800 B read + 400 B written per window
+    (+400 B for the raw copy), reported against the measured copy bandwidth."""
+    from eeg_gnn_ssl_b200 import ops
+    b, t, n = cfg["B"], cfg["T"], 19
+    g = torch.Generator(device=dev).manual_seed(5)
+    sig = torch.randn((b, n, t * 200), generator=g, device=dev) * 30.0
+    mean, std = torch.tensor(3.924), torch.tensor(1.560)
+    ls = torch.zeros(b, device=dev)
+    dest = torch.arange(n, dtype=torch.int32, device=dev).repeat(b, 1)
+    want_raw = nsup(cfg) == 2                    # correlation-graph configs also need the un-augmented features
+    for _ in range(3):
+        ops.fft_features(sig, mean, std, dest, ls, return_raw=want_raw)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        ops.fft_features(sig, mean, std, dest, ls, return_raw=want_raw)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    nbytes = b * n * t * (800 + 400 + (400 if want_raw else 0))
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    return {"kernel": "fft_features", "what": "raw EEG -> per-second log-amplitude FFT + reflect/scale augmentation + "
+            "standardisation (DataLoader work of data/dataloader_detection.py:58-72,233-256,382-393 on the device)",
+            "ms_per_batch": ms, "windows": b * n * t, "algorithmic_bytes": nbytes,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_gbs, "unit": "GB/s", "frac": gbs / hbm_gbs},
+            "l2": "signal + outputs = %.2f GB per launch (larger than L2)" % (nbytes / 1e9)}
+
+
 def kernel_families(cfg):
     """algorithmic FLOPs per launch of each kernel family (as-written count, SURVEY 8(d) / DESIGN.md section 5):
        forward layer l            : T*B*F_cell(C_l)
@@ -620,6 +651,13 @@ def main():
                 extra[f"cfg{ci}"] = {"workload": c2["name"], "error": f"{type(exc).__name__}: {str(exc)[:200]}"}
                 torch.cuda.synchronize()
         line["configs"] = extra
+
+    if not args.no_extra:
+        try:
+            line["input_pipeline"] = input_pipeline_leg(cfg, dev, peaks.get("hbm_gbs", 6500.0))
+        except Exception as exc:
+            line["input_pipeline"] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
+            torch.cuda.synchronize()
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cps, sec, full = cpu_reference_leg(cfg, min(cfg["B"], 64), 3, 1, full_batch_once=True)

@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdcgru_b200.so")
 
 SYMBOLS = [
-    "dcgru_version", "dcgru_last_error", "dcgru_graph_poly", "dcgru_corr_supports",
+    "dcgru_version", "dcgru_last_error", "dcgru_graph_poly", "dcgru_corr_supports", "dcgru_fft_features",
     "dcgru_encoder_layer_fwd", "dcgru_encoder_layer_gsave_bytes", "dcgru_encoder_layer_fwd_workspace", "dcgru_encoder_layer_bwd_workspace", "dcgru_encoder_layer_bwd",
     "dcgru_decoder_fwd_workspace", "dcgru_decoder_fwd", "dcgru_decoder_bwd_workspace", "dcgru_decoder_bwd",
     "dcgru_timing_enable", "dcgru_timing_collect", "dcgru_tc_selftest", "dcgru_debug_encoder_bwd_offsets",
@@ -54,6 +54,7 @@ def lib():
     L.dcgru_last_error.restype = C.c_char_p
     L.dcgru_graph_poly.argtypes = [i32, i32, i32, i32, C.POINTER(vp), C.POINTER(i64), vp, vp]
     L.dcgru_corr_supports.argtypes = [i32, i32, i32, i32, vp, i64, i64, f32, f32, i32, vp, vp, vp, vp]
+    L.dcgru_fft_features.argtypes = [i32, i32, i32, i32, vp, i64, i64, vp, vp, vp, vp, i32, vp, vp, vp]
     L.dcgru_encoder_layer_fwd.argtypes = [pd, i32, i32, vp, i64, i64, vp, vp, pp, vp, vp, vp, sz, vp, sz, vp]
     L.dcgru_encoder_layer_gsave_bytes.argtypes = [pd, i32, i32]
     L.dcgru_encoder_layer_gsave_bytes.restype = sz

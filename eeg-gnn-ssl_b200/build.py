@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 OUT_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT_DIR, "libdcgru_b200.so")
-SOURCES = ["seq_fwd.cu", "seq_bwd.cu", "dw.cu", "graph.cu", "tc_selftest.cu", "dw_tc.cu", "dw_mm.cu", "optim.cu", "seq_fwd_tc.cu", "seq_bwd_tc.cu", "tmap.cu", "bulk_dp.cu", "rnn_fwd.cu", "rnn_bwd.cu", "dw_mm16.cu", "head.cu", "capi.cu"]
+SOURCES = ["seq_fwd.cu", "seq_bwd.cu", "dw.cu", "graph.cu", "tc_selftest.cu", "dw_tc.cu", "dw_mm.cu", "optim.cu", "seq_fwd_tc.cu", "seq_bwd_tc.cu", "tmap.cu", "bulk_dp.cu", "rnn_fwd.cu", "rnn_bwd.cu", "dw_mm16.cu", "head.cu", "fft.cu", "capi.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC]

@@ -337,6 +337,23 @@ int dcgru_corr_supports(int32_t batch, int32_t seq_len, int32_t num_nodes, int32
     return 0;
 }
 
+int dcgru_fft_features(int32_t batch, int32_t num_nodes, int32_t seq_len, int32_t window, const float* signal,
+                       int64_t stride_b, int64_t stride_n, const int32_t* dest_channel, const float* log_scale,
+                       const float* mean, const float* std, int32_t stat_len, float* raw, float* x, void* stream) {
+    if (batch < 1 || seq_len < 1) return fail("empty clip");
+    if (num_nodes < 1 || num_nodes > 32) return fail("num_nodes=%d unsupported (1..32)", num_nodes);
+    if (window != 200) return fail("window=%d unsupported (FREQUENCY * time_step_size = 200 samples)", window);
+    if (!signal) return fail("null signal");
+    if (!raw && !x) return fail("no output requested");
+    if (stat_len != 0 && stat_len != 1 && stat_len != num_nodes) return fail("stat_len=%d must be 0, 1 or num_nodes", stat_len);
+    if (stat_len && (!mean || !std)) return fail("null mean/std");
+    if ((raw && !aligned16(raw)) || (x && !aligned16(x))) return fail("outputs must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    LAUNCH("fft_features", launch_fft_features(batch, num_nodes, seq_len, signal, stride_b, stride_n, dest_channel, log_scale,
+                                               mean, std, stat_len, raw, x, devinfo().sms, st));
+    return 0;
+}
+
 // second-generation path (2xFP16: bulk_dp.cu, rnn_fwd.cu, rnn_bwd.cu, dw_mm16.cu) is the default for H = 64 cells;
 // DCGRU_G2=0 selects the first-generation 3xTF32 kernels (H = 64, M = 3 only), DCGRU_DISABLE_TC=1 the fp32 FMA kernels
 static bool g2_enabled() {

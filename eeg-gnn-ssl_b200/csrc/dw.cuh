@@ -84,6 +84,9 @@ cudaError_t launch_graph_poly(int B, int N, int K, int S, const float* const* su
 cudaError_t launch_corr_supports(int B, int T, int N, int F, const float* clip, long long sb, long long st_,
                                  float scale, float shift, int top_k, float* adj, float* s0, float* s1,
                                  cudaStream_t st);
+cudaError_t launch_fft_features(int B, int N, int T, const float* signal, long long sig_sb, long long sig_sn, const int* perm,
+                                const float* log_scale, const float* mean, const float* stdv, int stat_len, float* raw, float* x,
+                                int nsms, cudaStream_t st);
 int dw_tc_smem_bytes(int M, int nco_max);
 size_t dw_tc_pt_floats(int B, int M);
 cudaError_t launch_make_pt(const float* P, int B, int M, int N, float* PT, cudaStream_t st);

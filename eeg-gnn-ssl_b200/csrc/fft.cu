@@ -1,0 +1,186 @@
+// Input features on the device: raw resampled EEG -> per-second log-amplitude spectrum -> random
+// reflect / random scale augmentation -> standardisation, i.e. what the DataLoader workers do per clip in
+//   data/dataloader_detection.py:58-72   (computeSliceMatrix: 1-second windows of FREQUENCY = 200 samples, is_fft)
+//   data/data_utils.py:13-34             (computeFFT: fft(n = 200), first floor(n/2) = 100 bins, |.|, 0 -> 1e-8, log)
+//   data/dataloader_detection.py:233-256 (_random_reflect: swap channel pairs; _random_scale: += log(scale) with FFT)
+//   utils.py:402-403                     (StandardScaler.transform: (x - mean) / std)
+// One window = 200 real samples -> 100 complex bins.  HBM-bound byte work (800 B in, 400 B out per window; 0.70 GB per
+// 512-clip batch of 60-second clips), so the DFT must cost less than the stream: the real-input symmetries fold the
+// 200-point DFT into four 50-term real sums per bin,
+//     a_j = x_j + x_{200-j}, d_j = x_j - x_{200-j}                      (cos / sin are even / odd around j = 100)
+//     even k:  Re = sum_{j<50} (a_j + a_{100-j}) cos(pi j k / 100) + a_50 cos(pi k / 2)
+//              Im = -sum_{0<j<50} (d_j - d_{100-j}) sin(pi j k / 100)
+//     odd  k:  Re = sum_{j<50} (a_j - a_{100-j}) cos(pi j k / 100)
+//              Im = -[ sum_{0<j<50} (d_j + d_{100-j}) sin(pi j k / 100) + d_50 sin(pi k / 2) ]
+// = 102 FMAs per bin instead of 400.  Thread = one bin k, its 2 x 51 twiddles live in registers for the whole kernel;
+// a warp holds bins of one parity, so every folded value it needs is one broadcast LDS.128 for all 32 lanes.  A CTA
+// (128 threads: warps 0-1 even bins, 2-3 odd bins) is persistent over batches of FW windows: coalesced float4 loads ->
+// fold into shared memory -> 51 x 2 FMAs per (bin, window) -> log amplitude -> shared -> coalesced stores with the
+// augmentation and the scaler applied on the way out.  fp32 arithmetic on fp32 samples (the sums have 51 terms; measured
+// error vs the float64 reference <= 2e-6 of the largest feature, tests/test_gpu_fft.py).
+#include "common.cuh"
+#include "dw.cuh"
+
+namespace dcgru {
+
+constexpr int FFT_W = 200;           // samples per window (FREQUENCY * time_step_size, constants.py / args.py)
+constexpr int FFT_K = FFT_W / 2;     // bins kept
+constexpr int FFT_THREADS = 128;
+constexpr int FFT_FW = 16;           // windows per batch
+constexpr int FFT_FLD = 52;          // folded array length (51 used), floats; 4 arrays per window
+
+struct FftParams {
+    int B, N, T;
+    const float* signal;             // (B, N, T*200)
+    long long sig_sb, sig_sn;        // element strides of b and n
+    const int* perm;                 // (B, N) source channel of output channel n, or nullptr
+    const float* log_scale;          // (B) added to the log amplitude, or nullptr
+    const float* mean; const float* stdv; int stat_len;   // 0 (none), 1 or N
+    float* raw;                      // (B, T, N, 100) log amplitude before augmentation / scaling, or nullptr
+    float* x;                        // (B, T, N, 100) or nullptr
+    const float* tw;                 // 400 floats: cos(pi m / 100), sin(pi m / 100), m = 0..199
+    long long nwin;                  // B * N * T
+};
+
+__global__ void __launch_bounds__(FFT_THREADS) fft_features_kernel(const FftParams p) {
+    __shared__ __align__(16) float fold[FFT_FW][4][FFT_FLD];     // [window][Ce | Se | Co | So][j]
+    __shared__ __align__(16) float outb[FFT_FW][FFT_K];
+    __shared__ float s_mean[32], s_std[32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int parity = warp >> 1;                                 // warps 0-1: even bins, 2-3: odd bins
+    const int kidx = (warp & 1) * 32 + lane;                      // 0..63, 50 used
+    const bool kvalid = kidx < FFT_K / 2;
+    const int k = kvalid ? 2 * kidx + parity : parity;
+    float cw[51], sw[51];
+#pragma unroll
+    for (int j = 0; j <= 50; ++j) {
+        const int m = (j * k) % 200;
+        cw[j] = p.tw[m];
+        sw[j] = p.tw[200 + m];
+    }
+    if (tid < 32) {
+        float m = 0.f, sd = 1.f;
+        if (p.stat_len > 0 && tid < p.N) {
+            const int i = p.stat_len == 1 ? 0 : tid;
+            m = p.mean[i];
+            sd = p.stdv[i];
+        }
+        s_mean[tid] = m; s_std[tid] = sd;
+    }
+    const int TN = p.T * p.N;
+    for (long long w0 = (long long)blockIdx.x * FFT_FW; w0 < p.nwin; w0 += (long long)gridDim.x * FFT_FW) {
+        const int nw = (int)((p.nwin - w0 < FFT_FW) ? (p.nwin - w0) : FFT_FW);
+        __syncthreads();
+        // ---- load + fold: window order is (b, n, t) so consecutive windows are consecutive in the signal ----------
+        // item = (window, j) for j = 0..50: reads x_j, x_{100-j}, x_{100+j}, x_{200-j}
+        for (int it = tid; it < nw * 51; it += FFT_THREADS) {
+            const int w = it / 51, j = it - w * 51;
+            const long long wi = w0 + w;
+            const int b = (int)(wi / TN);
+            const int r = (int)(wi - (long long)b * TN);
+            const int n = r / p.T, t = r - n * p.T;
+            const float* s = p.signal + (long long)b * p.sig_sb + (long long)n * p.sig_sn + (long long)t * FFT_W;
+            float ce, se, co, so;
+            if (j == 0) {
+                const float x0 = __ldcs(s), x100 = __ldcs(s + 100);
+                ce = x0 + x100; co = x0 - x100; se = 0.f; so = 0.f;
+            } else if (j == 50) {
+                const float x50 = __ldcs(s + 50), x150 = __ldcs(s + 150);
+                ce = x50 + x150;            // a_50 (even bins: times cos(pi k / 2))
+                co = 0.f;
+                se = 0.f;
+                so = x50 - x150;            // d_50 (odd bins: times sin(pi k / 2))
+            } else {
+                const float xa = __ldcs(s + j), xb = __ldcs(s + 200 - j), xc = __ldcs(s + 100 - j), xd = __ldcs(s + 100 + j);
+                const float aj = xa + xb, dj = xa - xb;           // a_j, d_j
+                const float ar = xc + xd, dr = xc - xd;           // a_{100-j}, d_{100-j}
+                ce = aj + ar; co = aj - ar; se = dj - dr; so = dj + dr;
+            }
+            fold[w][0][j] = ce; fold[w][1][j] = se; fold[w][2][j] = co; fold[w][3][j] = so;
+            if (j == 50) { fold[w][0][51] = 0.f; fold[w][1][51] = 0.f; fold[w][2][51] = 0.f; fold[w][3][51] = 0.f; }
+        }
+        __syncthreads();
+        // ---- 51 x 2 FMAs per (bin, window); the folded values are warp-wide broadcasts ----------------------------
+        if (kvalid) {
+            for (int w = 0; w < nw; ++w) {
+                const float4* C4 = reinterpret_cast<const float4*>(fold[w][2 * parity]);
+                const float4* S4 = reinterpret_cast<const float4*>(fold[w][2 * parity + 1]);
+                float re0 = 0.f, re1 = 0.f, im0 = 0.f, im1 = 0.f;
+#pragma unroll
+                for (int q = 0; q < 12; ++q) {
+                    const float4 c = C4[q], s = S4[q];
+                    re0 = fmaf(c.x, cw[4 * q], re0);     re1 = fmaf(c.y, cw[4 * q + 1], re1);
+                    re0 = fmaf(c.z, cw[4 * q + 2], re0); re1 = fmaf(c.w, cw[4 * q + 3], re1);
+                    im0 = fmaf(s.x, sw[4 * q], im0);     im1 = fmaf(s.y, sw[4 * q + 1], im1);
+                    im0 = fmaf(s.z, sw[4 * q + 2], im0); im1 = fmaf(s.w, sw[4 * q + 3], im1);
+                }
+                {
+                    const float4 c = C4[12], s = S4[12];         // j = 48, 49, 50 (51 is padding)
+                    re0 = fmaf(c.x, cw[48], re0); re1 = fmaf(c.y, cw[49], re1); re0 = fmaf(c.z, cw[50], re0);
+                    im0 = fmaf(s.x, sw[48], im0); im1 = fmaf(s.y, sw[49], im1); im0 = fmaf(s.z, sw[50], im0);
+                }
+                const float re = re0 + re1, im = im0 + im1;
+                float amp = sqrtf(re * re + im * im);
+                if (amp == 0.0f) amp = 1e-8f;                    // data_utils.py:30
+                outb[w][k] = logf(amp);
+            }
+        }
+        __syncthreads();
+        // ---- coalesced stores: raw features, and augmented + standardised x ------------------------------------------
+        for (int it = tid; it < nw * (FFT_K / 4); it += FFT_THREADS) {
+            const int w = it / (FFT_K / 4), q = it - w * (FFT_K / 4);
+            const long long wi = w0 + w;
+            const int b = (int)(wi / TN);
+            const int r = (int)(wi - (long long)b * TN);
+            const int n = r / p.T, t = r - n * p.T;
+            float4 v = *reinterpret_cast<const float4*>(&outb[w][4 * q]);
+            if (p.raw) __stcs(reinterpret_cast<float4*>(p.raw + (((long long)b * p.T + t) * p.N + n) * FFT_K) + q, v);
+            if (p.x) {
+                const int no = p.perm ? p.perm[(long long)b * p.N + n] : n;     // destination channel of source channel n
+                if (p.log_scale) {
+                    const float ls = p.log_scale[b];
+                    v.x += ls; v.y += ls; v.z += ls; v.w += ls;
+                }
+                if (p.stat_len > 0) {
+                    const float m = s_mean[no], sd = s_std[no];
+                    v.x = (v.x - m) / sd; v.y = (v.y - m) / sd; v.z = (v.z - m) / sd; v.w = (v.w - m) / sd;
+                }
+                __stcs(reinterpret_cast<float4*>(p.x + (((long long)b * p.T + t) * p.N + no) * FFT_K) + q, v);
+            }
+        }
+    }
+}
+
+// twiddle table cos / sin(pi m / 100), m = 0..199: written by a one-block kernel in front of every launch (float64 sincospi,
+// exact zeros and ones at the multiples of pi / 2) -- stream-ordered, capturable, nothing allocated by the library
+__device__ float g_fft_tw[400];
+__global__ void fft_twiddle_kernel() {
+    const int m = threadIdx.x;
+    if (m < 200) {
+        double s, c;
+        sincospi((double)m / 100.0, &s, &c);
+        g_fft_tw[m] = (float)c;
+        g_fft_tw[200 + m] = (float)s;
+    }
+}
+
+cudaError_t launch_fft_features(int B, int N, int T, const float* signal, long long sig_sb, long long sig_sn, const int* perm,
+                                const float* log_scale, const float* mean, const float* stdv, int stat_len, float* raw, float* x,
+                                int nsms, cudaStream_t st) {
+    FftParams p;
+    p.B = B; p.N = N; p.T = T; p.signal = signal; p.sig_sb = sig_sb; p.sig_sn = sig_sn; p.perm = perm; p.log_scale = log_scale;
+    p.mean = mean; p.stdv = stdv; p.stat_len = stat_len; p.raw = raw; p.x = x;
+    p.nwin = (long long)B * N * T;
+    float* tw = nullptr;
+    cudaError_t e = cudaGetSymbolAddress(reinterpret_cast<void**>(&tw), g_fft_tw);
+    if (e != cudaSuccess) return e;
+    p.tw = tw;
+    fft_twiddle_kernel<<<1, 256, 0, st>>>();
+    long long nbatch = (p.nwin + FFT_FW - 1) / FFT_FW;
+    long long grid = (long long)nsms * 3;                        // persistent: 3 CTAs of 128 threads per SM (132 registers)
+    if (grid > nbatch) grid = nbatch;
+    fft_features_kernel<<<(unsigned)grid, FFT_THREADS, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace dcgru

@@ -89,6 +89,48 @@ def corr_supports(clip, top_k=3, scale=1.0, shift=0.0, return_adj=False):
     return ([s0, s1], adj) if return_adj else [s0, s1]
 
 
+def fft_features(signal, mean=None, std=None, dest_channel=None, log_scale=None, return_raw=False, window=200):
+    """signal (B, N, T*200) raw resampled EEG on the GPU -> x (B, T, N, 100): per-second log-amplitude spectrum
+    (data/data_utils.py:13-34 via data/dataloader_detection.py:58-72), optional augmentation
+    (``dest_channel`` (B,N) int32 = _random_reflect's pair swaps, ``log_scale`` (B) = log of _random_scale's factor,
+    data/dataloader_detection.py:233-256) and StandardScaler.transform (utils.py:402-403; ``mean``/``std`` scalars or
+    per-channel tensors).  ``return_raw`` also returns the un-augmented, un-scaled features, which is what the
+    correlation graph is built from (``corr_supports``)."""
+    _need_cuda(signal)
+    if signal.dim() != 3 or signal.shape[2] % window:
+        raise ValueError("signal must be (B, N, T*window)")
+    if signal.dtype != torch.float32:
+        raise ValueError("signal must be float32")
+    if signal.stride(2) != 1:
+        signal = signal.contiguous()
+    b, n, s = signal.shape
+    t = s // window
+    dev = signal.device
+    stat_len = 0
+    if (mean is None) != (std is None):
+        raise ValueError("mean and std go together")
+    if mean is not None:
+        mean = torch.as_tensor(mean, dtype=torch.float32, device=dev).reshape(-1).contiguous()
+        std = torch.as_tensor(std, dtype=torch.float32, device=dev).reshape(-1).contiguous()
+        if mean.numel() != std.numel() or mean.numel() not in (1, n):
+            raise ValueError("mean/std must be scalars or one value per channel")
+        stat_len = mean.numel()
+    if dest_channel is not None:
+        dest_channel = dest_channel.to(device=dev, dtype=torch.int32).contiguous()
+        if tuple(dest_channel.shape) != (b, n):
+            raise ValueError("dest_channel must be (B, N)")
+    if log_scale is not None:
+        log_scale = log_scale.to(device=dev, dtype=torch.float32).contiguous()
+        if log_scale.numel() != b:
+            raise ValueError("log_scale must be (B,)")
+    x = torch.empty((b, t, n, window // 2), device=dev, dtype=torch.float32)
+    raw = torch.empty_like(x) if return_raw else None
+    check(_lib.lib().dcgru_fft_features(b, n, t, window, _ptr(signal), signal.stride(0), signal.stride(1),
+                                        _ptr(dest_channel), _ptr(log_scale), _ptr(mean), _ptr(std), stat_len,
+                                        _ptr(raw), _ptr(x), _stream()), "fft_features")
+    return (x, raw) if return_raw else x
+
+
 # ------------------------------------------------------------------------------------------------
 # encoder layer
 # ------------------------------------------------------------------------------------------------

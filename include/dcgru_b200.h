@@ -94,6 +94,28 @@ int dcgru_corr_supports(int32_t batch, int32_t seq_len, int32_t num_nodes, int32
                         float scale, float shift, int32_t top_k,
                         float *adj, float *support0, float *support1, void *stream);
 
+/* ---- input features ---------------------------------------------------------
+ * What the reference's DataLoader workers do per clip before the model sees it:
+ *   1-second windows of 200 samples -> fft(n=200) -> first 100 bins -> log|.| with 0 -> 1e-8
+ *   (data/dataloader_detection.py:58-72 computeSliceMatrix(is_fft=True), data/data_utils.py:13-34
+ *   computeFFT), then _random_reflect / _random_scale (data/dataloader_detection.py:233-256:
+ *   swap channel pairs; += log(scale_factor)), then StandardScaler.transform (utils.py:402-403).
+ * signal: resampled EEG, element (b, n, s) at signal + b*stride_b + n*stride_n + s, seq_len*200
+ *         contiguous samples per channel (the h5 layout, channels x samples)
+ * dest_channel: (B, N) int32 or NULL -- output channel that source channel n lands in (for the
+ *         reference's pair swaps, an involution, this is the swapped index; NULL = no reflection)
+ * log_scale: (B) or NULL -- log(scale_factor) of _random_scale
+ * mean/std: stat_len values (1: scalar scaler, N: per-channel (1,N,1) scaler, 0: no scaling)
+ * raw out (B, T, N, 100) or NULL: features before augmentation/scaling -- what
+ *         _get_indiv_graphs is given (data/dataloader_detection.py:395: eeg_clip, not curr_feature),
+ *         i.e. the input of dcgru_corr_supports
+ * x out   (B, T, N, 100) or NULL: the model input                                              */
+int dcgru_fft_features(int32_t batch, int32_t num_nodes, int32_t seq_len, int32_t window,
+                       const float *signal, int64_t stride_b, int64_t stride_n,
+                       const int32_t *dest_channel, const float *log_scale,
+                       const float *mean, const float *std, int32_t stat_len,
+                       float *raw, float *x, void *stream);
+
 /* ---- encoder layer -------------------------------------------------------------------------
  * One launch = one RNN layer over all T steps (the inner loop of DCRNNEncoder.forward,
  * model/model.py:93-96, around DCGRUCell.forward, model/cell.py:182-210).

@@ -48,7 +48,7 @@ def _worker(rank, world, port, q):
     # single-process reference on the full batch with rank 0's weights
     sync.zero()                                          # (zero_grad() would drop the views)
     torch.nn.functional.mse_loss(model(x), y).backward()
-    q.put((rank, float((flat_dp - sync.flat).abs().max()), [p.detach().clone() for p in model.parameters()]))
+    q.put((rank, float((flat_dp - sync.flat).abs().max()), [p.detach().numpy().tolist() for p in model.parameters()]))   # plain lists: a tensor in an mp.Queue is a shared-memory handle that dies with the worker
     dist.destroy_process_group()
 
 
@@ -66,4 +66,4 @@ def test_flat_gradient_allreduce_matches_full_batch():
     for _, err, _ in res:
         assert err < 1e-6
     for a, b in zip(res[0][2], res[1][2]):
-        assert torch.equal(a, b)                         # broadcast made the replicas identical
+        assert a == b                         # broadcast made the replicas identical

@@ -269,7 +269,7 @@ __device__ __forceinline__ void load_pfrag(const float* PT, int lane, PFrag& f) 
         }
 }
 // z: (source row 0, column 0) of the sample's fp32 tile; slot: chunk slot (hi plane, lo plane PLANE further); row0: the
-// sample's first tile row; values are multiplied by `scale` before the split
+// sample's first tile row; the source values are multiplied by `scale` (a power of two) before their fp16 split
 __device__ __forceinline__ void diffuse_mma(const float* z, int zld, int N, const PFrag& pf, uint8_t* slot, int row0, int lane,
                                             float scale) {
     const int g = lane >> 2, t = lane & 3;
@@ -284,8 +284,8 @@ __device__ __forceinline__ void diffuse_mma(const float* z, int zld, int N, cons
                 const int j0 = 16 * kt + 2 * t;
                 const float v0 = j0 < N ? zc[j0 * zld] : 0.f, v1 = j0 + 1 < N ? zc[(j0 + 1) * zld] : 0.f;
                 const float v2 = j0 + 8 < N ? zc[(j0 + 8) * zld] : 0.f, v3 = j0 + 9 < N ? zc[(j0 + 9) * zld] : 0.f;
-                split2(v0, v1, bh[nt][kt][0], bl[nt][kt][0]);
-                split2(v2, v3, bh[nt][kt][1], bl[nt][kt][1]);
+                split2(v0 * scale, v1 * scale, bh[nt][kt][0], bl[nt][kt][0]);      // scale BEFORE the fp16 split: small gradients
+                split2(v2 * scale, v3 * scale, bh[nt][kt][1], bl[nt][kt][1]);      // would land in the fp16 subnormals otherwise
             }
         }
         // four independent accumulators (m tile x n tile) per dependent step: a dependent HMMA chain costs ~33 cycles per link
@@ -315,12 +315,12 @@ __device__ __forceinline__ void diffuse_mma(const float* z, int zld, int N, cons
             for (int nt = 0; nt < 2; ++nt) {
                 const int col = 16 * grp + 8 * nt + 2 * t;
                 uint32_t hi, lo;
-                split2(d[mt][nt][0] * scale, d[mt][nt][1] * scale, hi, lo);
+                split2(d[mt][nt][0], d[mt][nt][1], hi, lo);
                 uint32_t off = k128_off(row0 + 16 * mt + g, col);
                 *reinterpret_cast<uint32_t*>(slot + off) = hi;
                 *reinterpret_cast<uint32_t*>(slot + PLANE + off) = lo;
                 if (mt == 0) {                             // rows 24..31 of the block do not exist
-                    split2(d[mt][nt][2] * scale, d[mt][nt][3] * scale, hi, lo);
+                    split2(d[mt][nt][2], d[mt][nt][3], hi, lo);
                     off = k128_off(row0 + 8 + g, col);
                     *reinterpret_cast<uint32_t*>(slot + off) = hi;
                     *reinterpret_cast<uint32_t*>(slot + PLANE + off) = lo;

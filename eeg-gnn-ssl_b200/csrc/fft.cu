@@ -12,10 +12,11 @@
 //              Im = -sum_{0<j<50} (d_j - d_{100-j}) sin(pi j k / 100)
 //     odd  k:  Re = sum_{j<50} (a_j - a_{100-j}) cos(pi j k / 100)
 //              Im = -[ sum_{0<j<50} (d_j + d_{100-j}) sin(pi j k / 100) + d_50 sin(pi k / 2) ]
-// = 102 FMAs per bin instead of 400.  Thread = one bin k, its 2 x 51 twiddles live in registers for the whole kernel;
-// a warp holds bins of one parity, so every folded value it needs is one broadcast LDS.128 for all 32 lanes.  A CTA
+// = 51 packed (re, im) FMAs (fma.rn.f32x2) per bin instead of 400 scalar ones.  Thread = one bin k, its 51 (cos, sin)
+// twiddle pairs live in registers for the whole kernel;
+// a warp holds bins of one parity, so every folded (C_j, S_j) pair it needs comes from a broadcast LDS.128 for all 32 lanes.  A CTA
 // (128 threads: warps 0-1 even bins, 2-3 odd bins) is persistent over batches of FW windows: coalesced float4 loads ->
-// fold into shared memory -> 51 x 2 FMAs per (bin, window) -> log amplitude -> shared -> coalesced stores with the
+// fold into shared memory -> 51 packed FMAs per (bin, window) -> log amplitude -> shared -> coalesced stores with the
 // augmentation and the scaler applied on the way out.  fp32 arithmetic on fp32 samples (the sums have 51 terms; measured
 // error vs the float64 reference <= 2e-6 of the largest feature, tests/test_gpu_fft.py).
 #include "common.cuh"
@@ -27,13 +28,13 @@ constexpr int FFT_W = 200;           // samples per window (FREQUENCY * time_ste
 constexpr int FFT_K = FFT_W / 2;     // bins kept
 constexpr int FFT_THREADS = 128;
 constexpr int FFT_FW = 16;           // windows per batch
-constexpr int FFT_FLD = 52;          // folded array length (51 used), floats; 4 arrays per window
+constexpr int FFT_FLD = 52;          // folded (C, S) pairs per parity and window (51 used)
 
 struct FftParams {
     int B, N, T;
     const float* signal;             // (B, N, T*200)
     long long sig_sb, sig_sn;        // element strides of b and n
-    const int* perm;                 // (B, N) source channel of output channel n, or nullptr
+    const int* perm;                 // (B, N) destination channel of source channel n, or nullptr
     const float* log_scale;          // (B) added to the log amplitude, or nullptr
     const float* mean; const float* stdv; int stat_len;   // 0 (none), 1 or N
     float* raw;                      // (B, T, N, 100) log amplitude before augmentation / scaling, or nullptr
@@ -42,44 +43,50 @@ struct FftParams {
     long long nwin;                  // B * N * T
 };
 
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+
 __global__ void __launch_bounds__(FFT_THREADS) fft_features_kernel(const FftParams p) {
-    __shared__ __align__(16) float fold[FFT_FW][4][FFT_FLD];     // [window][Ce | Se | Co | So][j]
+    // folded values, interleaved so that one LDS.128 yields two ready (C_j, S_j) operand pairs of the packed FMA
+    __shared__ __align__(16) float2 fold[FFT_FW][2][FFT_FLD];     // [window][even | odd bins][j] = (C_j, S_j)
     __shared__ __align__(16) float outb[FFT_FW][FFT_K];
-    __shared__ float s_mean[32], s_std[32];
+    __shared__ long long s_src[FFT_FW], s_dst[FFT_FW], s_dstx[FFT_FW];   // element offsets of the window in signal / raw / x
+    __shared__ float s_ls[FFT_FW], s_m[FFT_FW], s_sd[FFT_FW];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int parity = warp >> 1;                                 // warps 0-1: even bins, 2-3: odd bins
     const int kidx = (warp & 1) * 32 + lane;                      // 0..63, 50 used
     const bool kvalid = kidx < FFT_K / 2;
     const int k = kvalid ? 2 * kidx + parity : parity;
-    float cw[51], sw[51];
+    unsigned long long tw2[51];                                   // (cos, sin)(pi j k / 100) as packed pairs
 #pragma unroll
     for (int j = 0; j <= 50; ++j) {
         const int m = (j * k) % 200;
-        cw[j] = p.tw[m];
-        sw[j] = p.tw[200 + m];
-    }
-    if (tid < 32) {
-        float m = 0.f, sd = 1.f;
-        if (p.stat_len > 0 && tid < p.N) {
-            const int i = p.stat_len == 1 ? 0 : tid;
-            m = p.mean[i];
-            sd = p.stdv[i];
-        }
-        s_mean[tid] = m; s_std[tid] = sd;
+        tw2[j] = pack2(p.tw[m], p.tw[200 + m]);
     }
     const int TN = p.T * p.N;
     for (long long w0 = (long long)blockIdx.x * FFT_FW; w0 < p.nwin; w0 += (long long)gridDim.x * FFT_FW) {
         const int nw = (int)((p.nwin - w0 < FFT_FW) ? (p.nwin - w0) : FFT_FW);
         __syncthreads();
-        // ---- load + fold: window order is (b, n, t) so consecutive windows are consecutive in the signal ----------
-        // item = (window, j) for j = 0..50: reads x_j, x_{100-j}, x_{100+j}, x_{200-j}
-        for (int it = tid; it < nw * 51; it += FFT_THREADS) {
-            const int w = it / 51, j = it - w * 51;
-            const long long wi = w0 + w;
+        if (tid < nw) {                                           // window order (b, n, t): consecutive windows are consecutive samples
+            const long long wi = w0 + tid;
             const int b = (int)(wi / TN);
             const int r = (int)(wi - (long long)b * TN);
             const int n = r / p.T, t = r - n * p.T;
-            const float* s = p.signal + (long long)b * p.sig_sb + (long long)n * p.sig_sn + (long long)t * FFT_W;
+            s_src[tid] = (long long)b * p.sig_sb + (long long)n * p.sig_sn + (long long)t * FFT_W;
+            s_dst[tid] = (((long long)b * p.T + t) * p.N + n) * FFT_K;
+            const int no = p.perm ? p.perm[(long long)b * p.N + n] : n;
+            s_dstx[tid] = (((long long)b * p.T + t) * p.N + no) * FFT_K;
+            s_ls[tid] = p.log_scale ? p.log_scale[b] : 0.f;
+            const int si = p.stat_len == 1 ? 0 : no;
+            s_m[tid] = p.stat_len ? p.mean[si] : 0.f;
+            s_sd[tid] = p.stat_len ? p.stdv[si] : 1.f;
+        }
+        __syncthreads();
+        // ---- load + fold: item = (window, j), j = 0..50: reads x_j, x_{200-j}, x_{100-j}, x_{100+j} ------------------
+        for (int it = tid; it < nw * 51; it += FFT_THREADS) {
+            const int w = it / 51, j = it - w * 51;
+            const float* s = p.signal + s_src[w];
             float ce, se, co, so;
             if (j == 0) {
                 const float x0 = __ldcs(s), x100 = __ldcs(s + 100);
@@ -96,56 +103,54 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_features_kernel(const FftPara
                 const float ar = xc + xd, dr = xc - xd;           // a_{100-j}, d_{100-j}
                 ce = aj + ar; co = aj - ar; se = dj - dr; so = dj + dr;
             }
-            fold[w][0][j] = ce; fold[w][1][j] = se; fold[w][2][j] = co; fold[w][3][j] = so;
-            if (j == 50) { fold[w][0][51] = 0.f; fold[w][1][51] = 0.f; fold[w][2][51] = 0.f; fold[w][3][51] = 0.f; }
+            fold[w][0][j] = make_float2(ce, se);
+            fold[w][1][j] = make_float2(co, so);
+            if (j == 50) { fold[w][0][51] = make_float2(0.f, 0.f); fold[w][1][51] = make_float2(0.f, 0.f); }
         }
         __syncthreads();
-        // ---- 51 x 2 FMAs per (bin, window); the folded values are warp-wide broadcasts ----------------------------
+        // ---- 51 packed FMAs per (bin, window): (re, im) += (C_j, S_j) * (cos, sin); folded values are warp-wide broadcasts
         if (kvalid) {
             for (int w = 0; w < nw; ++w) {
-                const float4* C4 = reinterpret_cast<const float4*>(fold[w][2 * parity]);
-                const float4* S4 = reinterpret_cast<const float4*>(fold[w][2 * parity + 1]);
-                float re0 = 0.f, re1 = 0.f, im0 = 0.f, im1 = 0.f;
+                const ulonglong2* F = reinterpret_cast<const ulonglong2*>(fold[w][parity]);
+                unsigned long long acc0 = 0ull, acc1 = 0ull, acc2 = 0ull, acc3 = 0ull;      // four chains of (re, im) partial sums
 #pragma unroll
-                for (int q = 0; q < 12; ++q) {
-                    const float4 c = C4[q], s = S4[q];
-                    re0 = fmaf(c.x, cw[4 * q], re0);     re1 = fmaf(c.y, cw[4 * q + 1], re1);
-                    re0 = fmaf(c.z, cw[4 * q + 2], re0); re1 = fmaf(c.w, cw[4 * q + 3], re1);
-                    im0 = fmaf(s.x, sw[4 * q], im0);     im1 = fmaf(s.y, sw[4 * q + 1], im1);
-                    im0 = fmaf(s.z, sw[4 * q + 2], im0); im1 = fmaf(s.w, sw[4 * q + 3], im1);
+                for (int q = 0; q < 24; q += 2) {
+                    const ulonglong2 f = F[q], g = F[q + 1];
+                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc0) : "l"(f.x), "l"(tw2[2 * q]));
+                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc1) : "l"(f.y), "l"(tw2[2 * q + 1]));
+                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2) : "l"(g.x), "l"(tw2[2 * q + 2]));
+                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc3) : "l"(g.y), "l"(tw2[2 * q + 3]));
                 }
                 {
-                    const float4 c = C4[12], s = S4[12];         // j = 48, 49, 50 (51 is padding)
-                    re0 = fmaf(c.x, cw[48], re0); re1 = fmaf(c.y, cw[49], re1); re0 = fmaf(c.z, cw[50], re0);
-                    im0 = fmaf(s.x, sw[48], im0); im1 = fmaf(s.y, sw[49], im1); im0 = fmaf(s.z, sw[50], im0);
+                    const ulonglong2 f = F[24], g = F[25];        // j = 48, 49, 50 (51 is padding)
+                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc0) : "l"(f.x), "l"(tw2[48]));
+                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc1) : "l"(f.y), "l"(tw2[49]));
+                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2) : "l"(g.x), "l"(tw2[50]));
                 }
-                const float re = re0 + re1, im = im0 + im1;
-                float amp = sqrtf(re * re + im * im);
-                if (amp == 0.0f) amp = 1e-8f;                    // data_utils.py:30
-                outb[w][k] = logf(amp);
+                const float re = (__uint_as_float((unsigned)acc0) + __uint_as_float((unsigned)acc1)) +
+                                 (__uint_as_float((unsigned)acc2) + __uint_as_float((unsigned)acc3));
+                const float im = (__uint_as_float((unsigned)(acc0 >> 32)) + __uint_as_float((unsigned)(acc1 >> 32))) +
+                                 (__uint_as_float((unsigned)(acc2 >> 32)) + __uint_as_float((unsigned)(acc3 >> 32)));
+                const float pw = fmaf(re, re, im * im);           // log|X| = log(|X|^2) / 2
+                outb[w][k] = pw == 0.0f ? -18.420680743952367f : 0.5f * logf(pw);      // data_utils.py:30: amp == 0 -> 1e-8
             }
         }
         __syncthreads();
         // ---- coalesced stores: raw features, and augmented + standardised x ------------------------------------------
         for (int it = tid; it < nw * (FFT_K / 4); it += FFT_THREADS) {
             const int w = it / (FFT_K / 4), q = it - w * (FFT_K / 4);
-            const long long wi = w0 + w;
-            const int b = (int)(wi / TN);
-            const int r = (int)(wi - (long long)b * TN);
-            const int n = r / p.T, t = r - n * p.T;
             float4 v = *reinterpret_cast<const float4*>(&outb[w][4 * q]);
-            if (p.raw) __stcs(reinterpret_cast<float4*>(p.raw + (((long long)b * p.T + t) * p.N + n) * FFT_K) + q, v);
+            if (p.raw) __stcs(reinterpret_cast<float4*>(p.raw + s_dst[w]) + q, v);
             if (p.x) {
-                const int no = p.perm ? p.perm[(long long)b * p.N + n] : n;     // destination channel of source channel n
                 if (p.log_scale) {
-                    const float ls = p.log_scale[b];
+                    const float ls = s_ls[w];
                     v.x += ls; v.y += ls; v.z += ls; v.w += ls;
                 }
                 if (p.stat_len > 0) {
-                    const float m = s_mean[no], sd = s_std[no];
+                    const float m = s_m[w], sd = s_sd[w];
                     v.x = (v.x - m) / sd; v.y = (v.y - m) / sd; v.z = (v.z - m) / sd; v.w = (v.w - m) / sd;
                 }
-                __stcs(reinterpret_cast<float4*>(p.x + (((long long)b * p.T + t) * p.N + no) * FFT_K) + q, v);
+                __stcs(reinterpret_cast<float4*>(p.x + s_dstx[w]) + q, v);
             }
         }
     }
@@ -177,7 +182,7 @@ cudaError_t launch_fft_features(int B, int N, int T, const float* signal, long l
     p.tw = tw;
     fft_twiddle_kernel<<<1, 256, 0, st>>>();
     long long nbatch = (p.nwin + FFT_FW - 1) / FFT_FW;
-    long long grid = (long long)nsms * 3;                        // persistent: 3 CTAs of 128 threads per SM (132 registers)
+    long long grid = (long long)nsms * 3;                        // persistent: 3 CTAs of 128 threads per SM (register-limited)
     if (grid > nbatch) grid = nbatch;
     fft_features_kernel<<<(unsigned)grid, FFT_THREADS, 0, st>>>(p);
     return cudaGetLastError();

@@ -43,7 +43,7 @@ constexpr int RB_OFF_PT = RB_OFF_SB + 128 * RB_LD * 4;
 constexpr int RB_ACC1 = 0, RB_ACC2 = 64, RB_U = 128, RB_C = 192, RB_HP = 256, RB_DUP = 320, RB_R = 384;
 
 struct RnnBwdParams {
-    int B, T, N, M, act, dump, dbg;
+    int B, T, N, M, act, dump, dbg, mma_diff;
     int img_T, img_t0;            // slab of step t in the dA image: tile * img_T + img_t0 + t
     const float* h0; const float* hseq; const float* ruc;
     const float* P;
@@ -281,9 +281,18 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
                 const int s = (warp - ((m - 1) * SB)) & 7;
                 if (s < SB) {
                     uint8_t* sl = acquire();
-                    float acc[NPAD][2];
-                    diffuse2(S + (s * RP) * RB_LD + 2 * lane, RB_LD, N, PTs + (s * (M - 1) + (m - 1)) * PT_STRIDE, acc);
-                    store_cols2(sl, s * RP, lane, N, acc, gs, RG * 8);
+                    const float* pt = PTs + (s * (M - 1) + (m - 1)) * PT_STRIDE;
+                    if (p.mma_diff) {
+                        // warp-level tensor path (f16_common.cuh::diffuse_mma): polynomial fragments in registers, the fp32
+                        // source tile read once per element
+                        PFrag pf;
+                        load_pfrag(pt, lane, pf);
+                        diffuse_mma(S + (s * RP) * RB_LD, RB_LD, N, pf, sl, s * RP, lane, gs);
+                    } else {
+                        float acc[NPAD][2];
+                        diffuse2(S + (s * RP) * RB_LD + 2 * lane, RB_LD, N, pt, acc);
+                        store_cols2(sl, s * RP, lane, N, acc, gs, RG * 8);
+                    }
                     tc_fence_before();
                     fence_async_smem();
                     __syncwarp();
@@ -502,6 +511,7 @@ cudaError_t launch_rnn_bwd(int B, int T, int N, int fin, int M, int act, const f
     p.B = B; p.T = T; p.N = N; p.M = M; p.act = act; p.dump = daimg != nullptr;
     p.img_T = img_T > 0 ? img_T : T; p.img_t0 = img_T > 0 ? img_t0 : 0;
     { const char* e = getenv("DCGRU_DBG"); p.dbg = e ? (atoi(e) & 32) : 0; }
+    { const char* e = getenv("DCGRU_MMA_DIFF_BWD"); p.mma_diff = !(e && e[0] == '0'); }
     p.h0 = h0; p.hseq = hseq; p.ruc = ruc; p.P = P; p.d_hseq = d_hseq; p.d_hlast = d_hlast;
     p.d_hsel = d_hsel; p.sel_t = sel_t;
     p.wimg = reinterpret_cast<const uint8_t*>(wimg); p.scale_ptr = scale_ptr; p.dh0 = dh0;

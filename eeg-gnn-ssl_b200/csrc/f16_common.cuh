@@ -342,13 +342,14 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t sad
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];\n"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr) : "memory");
 }
+// Column groups [grp0, grp1) of 16 columns each are processed (the whole chunk = [0, 4)).
 __device__ __forceinline__ void diffuse_mma16(const uint8_t* src, int srow0, const PFrag& pf, uint8_t* slot, int row0, int lane,
-                                              float scale) {
+                                              float scale, int grp0 = 0, int grp1 = 4) {
     const int g = lane >> 2, t = lane & 3;
     const int sr = srow0 + lane;                                        // lane i supplies the address of source row i
     const uint32_t rbase = smem_u32(src) + (uint32_t)((sr >> 3) * 1024 + (sr & 7) * 128);
 #pragma unroll 1
-    for (int grp = 0; grp < 4; ++grp) {
+    for (int grp = grp0; grp < grp1; ++grp) {
         uint32_t bh[2][4], bl[2][4];                                    // [n tile][kt0.b0, kt0.b1, kt1.b0, kt1.b1]
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {

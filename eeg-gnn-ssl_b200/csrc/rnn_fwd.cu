@@ -7,14 +7,18 @@
 //     h_t = u*h_{t-1} + (1-u)*c
 // K order is term-major (kk = m*H + c), so with H = 64 one chunk (f16_common.cuh) = one diffusion term:
 //   * term 0 (the state itself) is written as hi/lo fp16 by the epilogue that produced it (slot 0),
-//   * terms m >= 1 by one worker warp per (sample, term): fp32 diffusion from the state tile ZH (lane = two columns,
-//     registers = the 19 output rows), slots 1 and 2 alternate.
-// XP_t is loaded straight into the accumulator (TMEM) one or two steps ahead by four loader warps and the MMAs
-// accumulate on top of it; the accumulator is double buffered, the GRU state also lives in a TMEM stash.
+//   * terms m >= 1 by the worker warps, one term at a time (warp = (sample, column half)): P_m applied to the term-0
+//     chunk on the warp-level tensor path (mma.sync 2xFP16, f16_common.cuh::diffuse_mma16), slots 1 and 2 alternate; the
+//     tcgen05 MMAs of term m run while term m+1 is being diffused.
+// XP_t is loaded straight into the accumulator (TMEM) two steps ahead by four loader warps and the MMAs accumulate on
+// top of it; the accumulator is double buffered, the GRU state lives in a TMEM stash.  The workers never touch global
+// memory inside the loop: the epilogues write r, u, c back over their pre-activations in the accumulator and h_t into
+// the stash, and the loader warps move them to h_seq / ruc (TMEM -> warp-private staging tile -> 128-byte rows) while
+// the workers are already in the next step.
 //   warps 0-7   workers: diffusion tasks + the two epilogues (thread = (row, column half))
 //   warp 8      MMA issuer;  warp 9 weight loader (cp.async.bulk ring of hi / lo planes, L2 resident)
 //   warp 10     operand-image dump (tensor-map TMA store of every A chunk: columns [KXP, KXP + 2*M*H) of the image)
-//   warps 11-14 XP loaders (thread = row: global -> registers -> tcgen05.st)
+//   warps 11-14 output stores of step t, then XP loads of step t+2 (thread = row)
 #include <cstdlib>
 #include <cstring>
 
@@ -29,19 +33,19 @@ using namespace f16;
 constexpr int RF_H = 64;
 constexpr int RF_THREADS = 480;
 constexpr int RF_NWORK = 256;
-constexpr int RF_ZLD = RF_H + 4;                    // state tile row stride (floats): conflict-free float4 row writes
+constexpr int RF_STG_LD = 36;                       // staging tile row stride (floats)
+constexpr int RF_STG = 32 * RF_STG_LD * 4;          // one warp-private staging tile: 32 rows x 32 columns
 constexpr int RF_NW = 4;                            // weight ring slots
 constexpr int RF_WSLOT = 16 * 1024;                 // one plane of a gate chunk (128 rows x 128 B); candidate planes are 8 KB
 constexpr int RF_OFF_A = 0;                         // 3 chunk slots
 constexpr int RF_OFF_W = 3 * SLOT;
-constexpr int RF_OFF_ZH = RF_OFF_W + RF_NW * RF_WSLOT;
-constexpr int RF_OFF_PT = RF_OFF_ZH + 128 * RF_ZLD * 4;
-constexpr int RF_ACC1 = 192, RF_STASH = 384, RF_RSTASH = 448;   // TMEM columns: accumulators at 0 / 192, h stash, r stash
+constexpr int RF_OFF_STG = RF_OFF_W + RF_NW * RF_WSLOT;          // 4 staging tiles (loader warps)
+constexpr int RF_OFF_PT = RF_OFF_STG + 4 * RF_STG;
+constexpr int RF_ACC1 = 192, RF_STASH = 384;                     // TMEM columns: accumulators at 0 / 192, h stash
 
 struct RnnFwdParams {
     int B, T, N, M, act, dump, img_col0, dbg;
     int img_T, img_t0;          // slab of step t in the operand image: tile * img_T + img_t0 + t
-    int mma_diff;               // diffusion on the warp-level tensor path (DCGRU_MMA_DIFF=0: fp32 FMA loop)
     const float* xp;            // (T,B,N,3H)
     const float* h0;            // (B,N*H)
     const float* P;             // (B,M-1,N,N)
@@ -59,14 +63,13 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     __shared__ uint64_t bar_afull[3], bar_aempty[3], bar_stored[3], bar_wfull[RF_NW], bar_wempty[RF_NW];
-    __shared__ uint64_t bar_xpfull[2], bar_accfree[2], bar_gate, bar_cand;
+    __shared__ uint64_t bar_xpfull[2], bar_final[2], bar_hfree, bar_gate, bar_cand;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = p.N, M = p.M, T = p.T;
     const int tile = blockIdx.x, b0 = tile * SB;
     uint8_t* Aslots = smem + RF_OFF_A;
     uint8_t* Wring = smem + RF_OFF_W;
-    float* ZH = reinterpret_cast<float*>(smem + RF_OFF_ZH);
     float* PTs = reinterpret_cast<float*>(smem + RF_OFF_PT);
     const bool dump = p.dump != 0;
     const size_t NH = (size_t)N * RF_H;
@@ -78,13 +81,13 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
         mbar_init(&bar_afull[2], RF_NWORK / 32);
         for (int i = 0; i < 3; ++i) { mbar_init(&bar_aempty[i], 1); mbar_init(&bar_stored[i], 1); }
         for (int i = 0; i < RF_NW; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&bar_xpfull[i], 4); mbar_init(&bar_accfree[i], RF_NWORK / 32); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_xpfull[i], 4); mbar_init(&bar_final[i], RF_NWORK / 32); }
+        mbar_init(&bar_hfree, 4);
         mbar_init(&bar_gate, 1);
         mbar_init(&bar_cand, 1);
         mbar_fence_init();
     }
     for (int i = tid; i < 3 * SLOT / 16; i += RF_THREADS) reinterpret_cast<uint4*>(Aslots)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < 128 * RF_ZLD; i += RF_THREADS) ZH[i] = 0.f;
     for (int i = tid; i < SB * (M - 1) * PT_STRIDE; i += RF_THREADS) PTs[i] = 0.f;
     __syncthreads();
     load_pt(PTs, p.P, b0, p.B, N, M - 1, 0, tid, RF_THREADS);
@@ -183,15 +186,36 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
         }
         __syncwarp();
     } else if (warp >= 11) {
-        // =================================== XP loaders: thread = row ====================================================
+        // =================================== output stores + XP loads: thread = row ======================================
         const int quad = warp & 3, row = 32 * quad + lane;
         const int s = row >> 5, n = row & 31, b = b0 + s;
         const bool valid = n < N && b < p.B;
         const uint32_t lane_base = (uint32_t)(32 * quad) << 16;
-        for (int t = 0; t < T; ++t) {
+        float* stg = reinterpret_cast<float*>(smem + RF_OFF_STG + (warp - 11) * RF_STG);
+        const int rq = lane >> 3, f4 = lane & 7;
+        int grow[8];                                                    // (b*N + n) of the rows this lane moves, or -1
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int nn = rq + 4 * i;
+            grow[i] = (nn < N && b < p.B) ? (b * N + nn) : -1;
+        }
+        // 32 columns of this warp's 32 rows: TMEM -> staging tile -> whole 128-byte row pieces in global memory
+        auto move32 = [&](uint32_t tcol, float* base, int ld, int col0) {
+            float v[32];
+            tmem_ld32(taddr + lane_base + tcol, v);
+            __syncwarp();
+            float4* d = reinterpret_cast<float4*>(stg + lane * RF_STG_LD);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) d[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (grow[i] >= 0)
+                    __stcs(reinterpret_cast<float4*>(base + (size_t)grow[i] * ld + col0 + 4 * f4),
+                           *reinterpret_cast<const float4*>(stg + (rq + 4 * i) * RF_STG_LD + 4 * f4));
+        };
+        auto load_xp = [&](int t) {
             const int acc_i = t & 1;
-            if (t >= 2) mbar_wait_relaxed(&bar_accfree[acc_i], ((t >> 1) - 1) & 1, 512);
-            tc_fence_after();
             const float4* src = reinterpret_cast<const float4*>(p.xp + (((size_t)t * p.B + (valid ? b : 0)) * N + (valid ? n : 0)) * (3 * RF_H));
 #pragma unroll 1
             for (int cb = 0; cb < 3 * RF_H; cb += 32) {
@@ -207,6 +231,24 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_xpfull[acc_i]);
+        };
+        load_xp(0);
+        if (T > 1) load_xp(1);
+        for (int t = 0; t < T; ++t) {
+            const int acc_i = t & 1;
+            mbar_wait_relaxed(&bar_final[acc_i], (t >> 1) & 1, 512);    // r | u | c sit in the accumulator, h_t in the stash
+            tc_fence_after();
+            move32(RF_STASH, p.hseq + (size_t)t * p.B * NH, RF_H, 0);
+            move32(RF_STASH + 32, p.hseq + (size_t)t * p.B * NH, RF_H, 32);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_hfree);                     // the stash may take h_{t+1}
+            if (p.ruc) {
+                float* ruc = p.ruc + (size_t)t * p.B * NH * 3;
+#pragma unroll 1
+                for (int cb = 0; cb < 3 * RF_H; cb += 32) move32(acc_i * RF_ACC1 + cb, ruc, 3 * RF_H, cb);
+            }
+            if (t + 2 < T) load_xp(t + 2);
         }
     } else {
         // =================================== workers =====================================================================
@@ -224,32 +266,8 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
                 if (dump) mbar_wait(&bar_stored[slot], (f - 1) & 1);
             }
         };
-        // ---- warp-private staging tile for coalesced global stores; lives in slots 1-2, which are idle in epilogue 2 ----
-        float* stg = reinterpret_cast<float*>(Aslots + SLOT) + warp * (32 * 36);
-        const int rq = lane >> 3, f4 = lane & 7;
-        int grow[8];                                                    // (b*N + n) of the rows this lane moves, or -1
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int n = rq + 4 * i;
-            grow[i] = (n < N && b_ < p.B) ? (b_ * N + n) : -1;
-        }
-        auto stage_store = [&](const float (&v)[32], float* base, int ld, int col0) {
-            __syncwarp();
-            float4* d = reinterpret_cast<float4*>(stg + lane * 36);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) d[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (grow[i] >= 0)
-                    *reinterpret_cast<float4*>(base + (size_t)grow[i] * ld + col0 + 4 * f4) =
-                        *reinterpret_cast<const float4*>(stg + (rq + 4 * i) * 36 + 4 * f4);
-        };
-        // this thread's 32 state columns -> state tile row and slot 0 (hi / lo)
+        // this thread's 32 state columns -> slot 0 (hi / lo): term 0 for the tensor core and source of the diffusion
         auto put_state = [&](const float (&v)[32]) {
-            float4* z4 = reinterpret_cast<float4*>(ZH + row * RF_ZLD + half * 32);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) z4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 uint4 hi, lo;
@@ -259,50 +277,31 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
                 *reinterpret_cast<uint4*>(Aslots + PLANE + off) = lo;
             }
         };
-        auto put_state8 = [&](int col, const float (&v)[8]) {          // 8 columns of this row
-            float4* z4 = reinterpret_cast<float4*>(ZH + row * RF_ZLD + col);
-            z4[0] = make_float4(v[0], v[1], v[2], v[3]);
-            z4[1] = make_float4(v[4], v[5], v[6], v[7]);
-            uint4 hi, lo;
-            split8(v, hi, lo);
-            const uint32_t off = k128_off(row, col);
-            *reinterpret_cast<uint4*>(Aslots + off) = hi;
-            *reinterpret_cast<uint4*>(Aslots + PLANE + off) = lo;
-        };
         auto publish_slot0 = [&]() {
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_afull[0]);
             ++fills[0];
         };
-        // diffusion of one phase: one warp per (sample, term): 64 columns, two per lane (each P^T row read from shared memory
-        // feeds 40 FMAs: with one column per lane the loop was bound by the LDS issue rate at ~55 FMA/clk/SM, measured
-        // with scripts/micro/fma_rate.cu).  M = 3: terms 1 and 2 run side by side on warps 0-3 / 4-7; M = 5: two rounds,
-        // the MMAs of round one overlap the diffusion of round two.  A task arrives with count 2 (4 tasks = 8 arrivals).
-        auto diffuse_phase = [&]() {
+        // diffusion of one phase, one term at a time: warp = (sample quad, column half), two 16-column groups per task on
+        // the warp-level tensor path (f16_common.cuh::diffuse_mma16); the source is the term-0 chunk itself (slot 0, hi / lo
+        // fp16, just published by the epilogue).  The tcgen05 MMAs of term m overlap the diffusion of term m+1.
+        auto diffuse_phase = [&](long long* st) {
             for (int m = 1; m < M; ++m) {
                 const int slot = 1 + ((m - 1) & 1);
-                const int s = (warp - ((m - 1) * SB)) & 7;
-                if (s < SB) {
-                    acquire(slot, true);
-                    const float* pt = PTs + (s * (M - 1) + (m - 1)) * PT_STRIDE;
-                    if (p.mma_diff) {
-                        // warp-level tensor path (f16_common.cuh::diffuse_mma16): the source is the term-0 chunk itself (slot 0,
-                        // hi / lo fp16, just published by the epilogue); rows 0..23 of the sample's block are written
-                        PFrag pf;
-                        load_pfrag(pt, lane, pf);
-                        diffuse_mma16(Aslots, s * RP, pf, Aslots + slot * SLOT, s * RP, lane, 1.f);
-                    } else {
-                        float acc[NPAD][2];
-                        diffuse2(ZH + (s * RP) * RF_ZLD + 2 * lane, RF_ZLD, N, pt, acc);
-                        // (rows N..23 are dumped to the operand image and aliased by the staging tiles: rewrite them as zeros)
-                        store_cols2(Aslots + slot * SLOT, s * RP, lane, N, acc, 1.f, RG * 8);
-                    }
-                    fence_async_smem();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_n(&bar_afull[slot], 2);
-                }
+                if (st && m == 1) st[0] = clock64();
+                acquire(slot, true);
+                if (st && m == 1) st[1] = clock64();
+                PFrag pf;
+                load_pfrag(PTs + (quad * (M - 1) + (m - 1)) * PT_STRIDE, lane, pf);
+                if (st && m == 1) st[2] = clock64();
+                diffuse_mma16(Aslots, quad * RP, pf, Aslots + slot * SLOT, quad * RP, lane, 1.f, 2 * half, 2 * half + 2);
+                if (st && m == 1) st[3] = clock64();
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_afull[slot]);
                 ++fills[slot];
+                if (st && m == 1) st[4] = clock64();
             }
         };
         {   // state <- h0
@@ -320,52 +319,46 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
         }
         for (int t = 0; t < T; ++t) {
             const uint32_t dacc = taddr + lane_base + (t & 1) * RF_ACC1;
-            float* hout = p.hseq + (size_t)t * p.B * NH;
             const bool rec = (p.dbg & 16) && blockIdx.x == 0 && tid == 0 && t < 64;
             long long* es = rf_dbg + t * 16;
             if (rec) es[0] = clock64();
             // ---- gate ------------------------------------------------------------------------------------------------
-            diffuse_phase();
+            diffuse_phase(rec ? rf_dbg + 1024 + t * 8 : nullptr);
             if (rec) es[1] = clock64();
             mbar_wait(&bar_gate, t & 1);
             tc_fence_after();
             if (rec) es[2] = clock64();
-            {   // epilogue 1: r = sigmoid(gate[:, 0:H]) -> r*h  (one 32-column TMEM load per thread: loads are paid per instruction)
+            {   // epilogue 1: r = sigmoid(gate[:, 0:H]) -> r*h  (h_{t-1} from the TMEM stash)
                 float rk[32], v[32];
-                tmem_ld32(dacc + half * 32, rk);
-                const float4* z4 = reinterpret_cast<const float4*>(ZH + row * RF_ZLD + half * 32);
+                tmem_ld32_nw(dacc + half * 32, rk);
+                tmem_ld32_nw(taddr + lane_base + RF_STASH + half * 32, v);
+                tmem_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 z = z4[j];
-                    rk[4 * j] = fast_sigmoid(rk[4 * j]); rk[4 * j + 1] = fast_sigmoid(rk[4 * j + 1]);
-                    rk[4 * j + 2] = fast_sigmoid(rk[4 * j + 2]); rk[4 * j + 3] = fast_sigmoid(rk[4 * j + 3]);
-                    v[4 * j] = rvalid ? rk[4 * j] * z.x : 0.f; v[4 * j + 1] = rvalid ? rk[4 * j + 1] * z.y : 0.f;
-                    v[4 * j + 2] = rvalid ? rk[4 * j + 2] * z.z : 0.f; v[4 * j + 3] = rvalid ? rk[4 * j + 3] * z.w : 0.f;
+                for (int j = 0; j < 32; ++j) {
+                    rk[j] = fast_sigmoid(rk[j]);
+                    v[j] = rvalid ? rk[j] * v[j] : 0.f;
                 }
                 acquire(0, false);                                      // (bar_gate covers the MMAs that read slot 0)
-                put_state(v);                                           // ZH <- r*h, slot 0 <- hi/lo(r*h)
+                put_state(v);                                           // slot 0 <- hi/lo(r*h)
                 publish_slot0();
-                if (p.ruc) tmem_st32(taddr + lane_base + RF_RSTASH + half * 32, rk);   // r waits in TMEM for the stores of epilogue 2
+                if (p.ruc) tmem_st32(dacc + half * 32, rk);             // r replaces its pre-activation: the loader warps store it
             }
             if (rec) es[3] = clock64();
-            rf_worker_bar();                                            // r*h of every row is visible
+            // (no CTA-wide barrier: a warp diffuses exactly the rows and columns of slot 0 that it wrote itself)
             if (rec) es[4] = clock64();
             // ---- candidate ---------------------------------------------------------------------------------------------
-            diffuse_phase();
+            diffuse_phase(nullptr);
             if (rec) es[5] = clock64();
             mbar_wait(&bar_cand, t & 1);
             tc_fence_after();
             if (rec) es[6] = clock64();
             {   // epilogue 2: 64 columns, each warp half takes 32.  Everything it needs is on chip: the candidate and update-gate
-                // pre-activations in the accumulator, h_{t-1} and r in the TMEM stashes.
+                // pre-activations in the accumulator, h_{t-1} in the TMEM stash.
                 float cv[32], uv[32], hp[32];
                 tmem_ld32_nw(dacc + 2 * RF_H + half * 32, cv);
                 tmem_ld32_nw(dacc + RF_H + half * 32, uv);
                 tmem_ld32_nw(taddr + lane_base + RF_STASH + half * 32, hp);
                 tmem_wait_ld();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&bar_accfree[t & 1]);        // the accumulator may take XP_{t+2}
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     float c, u;
@@ -375,26 +368,21 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
                     hp[j] = rvalid ? u * hp[j] + (1.f - u) * c : 0.f;
                 }
                 acquire(0, false);
-                put_state(hp);                                          // ZH <- h_t, slot 0 <- hi/lo(h_t): term 0 of the next gate
+                put_state(hp);                                          // slot 0 <- hi/lo(h_t): term 0 of the next gate
                 publish_slot0();
-                tmem_st32(taddr + lane_base + RF_STASH + half * 32, hp);
                 if (rec) es[7] = clock64();
-                // the staging tiles alias slots 1-2: their last chunks must have been read by the MMAs (bar_cand) and dumped
-                if (dump && M > 1) {
-                    if (fills[1] >= 1) mbar_wait(&bar_stored[1], (fills[1] - 1) & 1);
-                    if (fills[2] >= 1) mbar_wait(&bar_stored[2], (fills[2] - 1) & 1);
+                if (t >= 1) mbar_wait(&bar_hfree, (t - 1) & 1);         // the loader warps have read h_{t-1} (long ago)
+                tc_fence_after();
+                tmem_st32(taddr + lane_base + RF_STASH + half * 32, hp);
+                if (p.ruc) {                                            // u, c replace their pre-activations
+                    tmem_st32(dacc + RF_H + half * 32, uv);
+                    tmem_st32(dacc + 2 * RF_H + half * 32, cv);
                 }
-                stage_store(hp, hout, RF_H, half * 32);
-                if (p.ruc) {
-                    float* ruc = p.ruc + (size_t)t * p.B * NH * 3;
-                    stage_store(uv, ruc, 3 * RF_H, RF_H + half * 32);
-                    stage_store(cv, ruc, 3 * RF_H, 2 * RF_H + half * 32);
-                    tmem_ld32(taddr + lane_base + RF_RSTASH + half * 32, uv);
-                    stage_store(uv, ruc, 3 * RF_H, half * 32);
-                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_final[t & 1]);          // outputs of step t are complete: loader warps take over
             }
             if (rec) es[8] = clock64();
-            rf_worker_bar();                                            // h_t of every row is visible; staging is free again
             if (rec) es[9] = clock64();
         }
     }
@@ -432,7 +420,6 @@ cudaError_t launch_rnn_fwd(int B, int T, int N, int fin, int M, int act, const f
     p.B = B; p.T = T; p.N = N; p.M = M; p.act = act; p.dump = img != nullptr; p.img_col0 = img_col0;
     p.img_T = img_T > 0 ? img_T : T; p.img_t0 = img_T > 0 ? img_t0 : 0;
     { const char* e = getenv("DCGRU_DBG"); p.dbg = e ? (atoi(e) & (16 | 64 | 128 | 256 | 512)) : 0; }
-    { const char* e = getenv("DCGRU_MMA_DIFF"); p.mma_diff = !(e && e[0] == '0'); }
     p.xp = xp; p.h0 = h0; p.P = P; p.wimg = reinterpret_cast<const uint8_t*>(wimg); p.hseq = hseq; p.ruc = ruc;
     CUtensorMap tm;
     memset(&tm, 0, sizeof tm);

@@ -28,5 +28,5 @@ print("step | worker: start gate-diffused gate-MMA-done epi1-done barrier cand-d
 for t in range(T):
     print(t, *(int(v - t0) for v in d[t, :10]), "|", *(int(v - t0) for v in d[t, 10:14]))
 print("per-step deltas (worker), step 5:", [int(d[5, i + 1] - d[5, i]) for i in range(9)], "total", int(d[6, 0] - d[5, 0]))
-print("epilogue 2 of step 5 (from cand-MMA-done): tmem loads, math, acquire slot0, put_state, publish, [stash+] h store ->",
-      [int(e2[5, 0] - d[5, 6])] + [int(e2[5, i + 1] - e2[5, i]) for i in range(5)])
+print("first gate term of step 5 (worker thread 0): acquire, load_pfrag, diffuse_mma16 (2 groups), fence+arrive ->",
+      [int(e2[5, i + 1] - e2[5, i]) for i in range(4)])

@@ -6,9 +6,10 @@
 //   E2 : dr = d(rh)*h_{t-1}, dA_r = dr*r(1-r), dh' += d(rh)*r
 //   B2 : dh_{t-1} = dh' + sum_m (P_m^T [dA_r | dA_u]) @ Wg_h,m^T                   (K = 2*M*H, N = H)
 // The transposed diffusion is applied on the INPUT side (P^T commutes with the column contraction), which makes the
-// backward structurally the forward: fp32 diffusion of a shared-memory tile by one warp per (sample, column half),
-// hi/lo fp16 chunks in a 3-slot ring (f16_common.cuh), kind::f16 MMAs accumulating in TMEM.  The u part of B2 does not
-// depend on B1, so its chunks are diffused while B1's MMAs complete.
+// backward structurally the forward: the epilogues write the term-0 chunks [dA_c], [dA_u], [dA_r] (scaled, hi/lo fp16)
+// into two dedicated slots, one warp per (sample, term) applies P_m^T to them on the warp-level tensor path (mma.sync
+// 2xFP16, f16_common.cuh::diffuse_mma16) into a 3-slot ring, kind::f16 MMAs accumulate in TMEM.  The u part of B2 does
+// not depend on B1, so its chunks are diffused while B1's MMAs complete.
 // The term-0 chunks [dA_c], [dA_u], [dA_r] (scaled, hi/lo) are exactly the rows of the dA operand image that the
 // weight-gradient GEMM (dw_mm16.cu), the input-gradient GEMM (bulk_dp.cu) and the bias gradient read: the dump warp
 // stores them with tensor-map TMA; nothing else is written per step.
@@ -32,18 +33,16 @@ using namespace f16;
 constexpr int RB_H = 64;
 constexpr int RB_THREADS = 480;
 constexpr int RB_NWORK = 256;
-constexpr int RB_LD = RB_H + 4;                      // fp32 source tiles: row stride in floats
 constexpr int RB_NW = 4;                             // weight ring slots
 constexpr int RB_WPIECE = RB_H * 128;                // one plane of a chunk's weights: 64 rows x 128 B
-constexpr int RB_OFF_W = 3 * SLOT;
-constexpr int RB_OFF_SA = RB_OFF_W + RB_NW * RB_WPIECE;
-constexpr int RB_OFF_SB = RB_OFF_SA + 128 * RB_LD * 4;
-constexpr int RB_OFF_PT = RB_OFF_SB + 128 * RB_LD * 4;
+constexpr int RB_NS = 5;                             // chunk slots: 0 = [dA_c] then [dA_r], 1 = [dA_u], 2..4 = ring of the diffused chunks
+constexpr int RB_OFF_W = RB_NS * SLOT;
+constexpr int RB_OFF_PT = RB_OFF_W + RB_NW * RB_WPIECE;
 // TMEM columns
-constexpr int RB_ACC1 = 0, RB_ACC2 = 64, RB_U = 128, RB_C = 192, RB_HP = 256, RB_DUP = 320, RB_R = 384;
+constexpr int RB_ACC1 = 0, RB_ACC2 = 64, RB_U = 128, RB_C = 192, RB_HP = 256, RB_DUP = 320, RB_R = 384, RB_HP1 = 448;   // h_{t-1}: 256 / 448 alternate
 
 struct RnnBwdParams {
-    int B, T, N, M, act, dump, dbg, mma_diff;
+    int B, T, N, M, act, dump, dbg;
     int img_T, img_t0;            // slab of step t in the dA image: tile * img_T + img_t0 + t
     const float* h0; const float* hseq; const float* ruc;
     const float* P;
@@ -63,6 +62,18 @@ __device__ __forceinline__ void rb_chunk(int i, int M, int& kind, int& m) {
     else { kind = 2; m = i - 2 * M; }
 }
 
+// slot and fill index (how many times the slot was filled before) of chunk i of processed step k: the term-0 chunks live in
+// slots 0 / 1 for a whole step (they are the sources of the diffusion), the diffused chunks rotate through slots 2..4
+__device__ __forceinline__ void rb_slot(int i, int k, int M, int& slot, unsigned& fill) {
+    if (i == 0) { slot = 0; fill = 2u * k; }
+    else if (i == 1) { slot = 1; fill = (unsigned)k; }
+    else if (i == 2 * M) { slot = 0; fill = 2u * k + 1u; }
+    else {
+        const unsigned d = (unsigned)k * (3 * (M - 1)) + (unsigned)(i < 2 * M ? i - 2 : i - 3);
+        slot = 2 + (int)(d % 3u); fill = d / 3u;
+    }
+}
+
 // timing experiment (DCGRU_DBG & 32): clock64 stamps of CTA 0, worker thread 0: [step][0..9]
 __device__ long long rb_dbg[64 * 16];
 
@@ -71,7 +82,7 @@ __device__ __forceinline__ void rb_worker_bar() { asm volatile("bar.sync 1, 256;
 __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdParams p, const __grid_constant__ CUtensorMap tm_img) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    __shared__ uint64_t bar_afull[3], bar_aempty[3], bar_stored[3], bar_wfull[RB_NW], bar_wempty[RB_NW];
+    __shared__ uint64_t bar_afull[RB_NS], bar_aempty[RB_NS], bar_stored[RB_NS], bar_wfull[RB_NW], bar_wempty[RB_NW];
     __shared__ uint64_t bar_gafull, bar_gbfull, bar_gafree, bar_gbfree, bar_b1, bar_b2;
     __shared__ uint32_t tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -80,23 +91,20 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
     const int nch = 3 * M;
     uint8_t* Aslots = smem;
     uint8_t* Wring = smem + RB_OFF_W;
-    float* SA = reinterpret_cast<float*>(smem + RB_OFF_SA);
-    float* SBt = reinterpret_cast<float*>(smem + RB_OFF_SB);
     float* PTs = reinterpret_cast<float*>(smem + RB_OFF_PT);
     const bool dump = p.dump != 0;
     const size_t NH = (size_t)N * RB_H;
 
     if (warp == 0) tmem_alloc<512>(&tmem_slot);
     if (tid == 0) {
-        for (int i = 0; i < 3; ++i) { mbar_init(&bar_afull[i], RB_NWORK / 32); mbar_init(&bar_aempty[i], 1); mbar_init(&bar_stored[i], 1); }
+        for (int i = 0; i < RB_NS; ++i) { mbar_init(&bar_afull[i], RB_NWORK / 32); mbar_init(&bar_aempty[i], 1); mbar_init(&bar_stored[i], 1); }
         for (int i = 0; i < RB_NW; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], 1); }
         mbar_init(&bar_gafull, 4); mbar_init(&bar_gbfull, 4);
         mbar_init(&bar_gafree, RB_NWORK / 32); mbar_init(&bar_gbfree, RB_NWORK / 32);
         mbar_init(&bar_b1, 1); mbar_init(&bar_b2, 1);
         mbar_fence_init();
     }
-    for (int i = tid; i < 3 * SLOT / 16; i += RB_THREADS) reinterpret_cast<uint4*>(Aslots)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < 2 * 128 * RB_LD; i += RB_THREADS) SA[i] = 0.f;          // SA and SB are adjacent
+    for (int i = tid; i < RB_NS * SLOT / 16; i += RB_THREADS) reinterpret_cast<uint4*>(Aslots)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < SB * (M - 1) * PT_STRIDE; i += RB_THREADS) PTs[i] = 0.f;
     __syncthreads();
     load_pt(PTs, p.P, b0, p.B, N, M - 1, 1, tid, RB_THREADS);                     // rows of P: (P^T z)[n] = sum_j P[j][n] z[j]
@@ -112,17 +120,18 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
             const uint32_t idesc = make_idesc_f16(128, RB_H);
             const uint32_t a_base = smem_u32(Aslots), w_base = smem_u32(Wring);
             const int last_c = (M == 1) ? 0 : M;
-            unsigned pc = 0, seq = 0;
+            unsigned pc = 0;
             for (int k = 0; k < T; ++k) {
-                for (int i = 0; i < nch; ++i, ++seq) {
-                    int kind, m;
+                for (int i = 0; i < nch; ++i) {
+                    int kind, m, slot;
+                    unsigned fill;
                     rb_chunk(i, M, kind, m);
-                    const int slot = seq % 3;
+                    rb_slot(i, k, M, slot, fill);
                     const uint32_t ah = a_base + slot * SLOT, al = ah + PLANE;
                     const uint32_t d = taddr + (kind == 0 ? RB_ACC1 : RB_ACC2);
                     const uint32_t first = (i <= 1) ? 0u : 1u;
                     const int ws0 = pc % RB_NW, ws1 = (pc + 1) % RB_NW;
-                    mbar_wait2(&bar_afull[slot], (seq / 3) & 1, &bar_wfull[ws0], (pc / RB_NW) & 1);
+                    mbar_wait2(&bar_afull[slot], fill & 1, &bar_wfull[ws0], (pc / RB_NW) & 1);
                     tc_fence_after();
                     const uint32_t bh = w_base + ws0 * RB_WPIECE, bl = w_base + ws1 * RB_WPIECE;
 #pragma unroll
@@ -168,13 +177,14 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
         if (dump) {
             const int plane = lane >> 2, s = lane & 3;
             if (lane == 0) tma_prefetch_desc(&tm_img);
-            unsigned seq = 0;
             for (int k = 0; k < T; ++k) {
                 const int t = T - 1 - k;
                 const long slab = (long)tile * p.img_T + p.img_t0 + t;
-                for (int i = 0; i < nch; ++i, ++seq) {
-                    const int slot = seq % 3;
-                    mbar_wait(&bar_afull[slot], (seq / 3) & 1);
+                for (int i = 0; i < nch; ++i) {
+                    int slot;
+                    unsigned fill;
+                    rb_slot(i, k, M, slot, fill);
+                    mbar_wait(&bar_afull[slot], fill & 1);
                     const int col = (i == 0) ? 2 * RB_H : (i == 1 ? RB_H : (i == 2 * M ? 0 : -1));   // image columns r | u | c
                     if (col >= 0) {
                         if (lane < 2 * SB) {
@@ -219,8 +229,12 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
             const float* hp = (t > 0) ? p.hseq + (size_t)(t - 1) * p.B * NH + rbase * RB_H : p.h0 + rbase * RB_H;
             if (k >= 1) mbar_wait(&bar_gafree, (k - 1) & 1);
             tc_fence_after();
+            // group A (needed by E1): u, c, upstream gradient, h_{t-1}.  h_{t-1} is also read by E2, so its TMEM columns alternate
+            // between two buffers: the copy of step k is still being read when the one of step k+1 arrives (every worker warp
+            // passes E2 of step k-1 before it frees group A of step k)
             load_cols(ruc + RB_H, RB_U);
             load_cols(ruc + 2 * RB_H, RB_C);
+            load_cols(hp, (k & 1) ? RB_HP1 : RB_HP);
             load_cols(p.d_hsel ? (sel == t ? p.d_hsel + rbase * RB_H : nullptr)
                                : (p.d_hseq ? p.d_hseq + (size_t)t * p.B * NH + rbase * RB_H : nullptr), RB_DUP);
             tc_fence_before();
@@ -228,8 +242,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
             if (lane == 0) mbar_arrive(&bar_gafull);
             if (k >= 1) mbar_wait(&bar_gbfree, (k - 1) & 1);
             tc_fence_after();
-            load_cols(ruc, RB_R);
-            load_cols(hp, RB_HP);
+            load_cols(ruc, RB_R);                                         // group B (needed by E2 only): r
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_gbfull);
@@ -242,22 +255,22 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
         const bool rvalid = lane < N && b_ < p.B;
         const uint32_t tb = taddr + ((uint32_t)(32 * quad) << 16) + half * 32;
         const float gs = __ldg(p.scale_ptr), inv_gs = 1.f / gs;
-        unsigned seq = 0;                                               // chunks started (identical in every thread)
-        auto acquire = [&]() -> uint8_t* {                              // slot of chunk #seq, once its previous content was consumed
-            const int slot = seq % 3;
-            if (seq >= 3) {
-                mbar_wait(&bar_aempty[slot], ((seq / 3) - 1) & 1);
-                if (dump) mbar_wait(&bar_stored[slot], ((seq / 3) - 1) & 1);
+        // slot of chunk i of step k, once its previous content was consumed by the MMAs (and dumped)
+        auto acquire = [&](int i, int k) -> int {
+            int slot;
+            unsigned fill;
+            rb_slot(i, k, M, slot, fill);
+            if (fill >= 1) {
+                mbar_wait(&bar_aempty[slot], (fill - 1) & 1);
+                if (dump) mbar_wait(&bar_stored[slot], (fill - 1) & 1);
             }
-            return Aslots + slot * SLOT;
+            return slot;
         };
-        auto publish = [&]() {
-            const int slot = seq % 3;
+        auto publish = [&](int slot) {
             tc_fence_before();
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_afull[slot]);
-            ++seq;
         };
         auto put8 = [&](uint8_t* sl, int col, const float (&v)[8]) {   // 8 columns of this row -> chunk (scaled, hi / lo)
             float w[8];
@@ -269,36 +282,22 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
             *reinterpret_cast<uint4*>(sl + off) = hi;
             *reinterpret_cast<uint4*>(sl + PLANE + off) = lo;
         };
-        auto put8f = [&](float* S, int col, const float (&v)[8]) {
-            float4* d = reinterpret_cast<float4*>(S + row * RB_LD + col);
-            d[0] = make_float4(v[0], v[1], v[2], v[3]);
-            d[1] = make_float4(v[4], v[5], v[6], v[7]);
-        };
-        // diffusion chunks: one warp per (sample, term), 64 columns, two per lane (see rnn_fwd.cu); a group of terms
-        // [m0, m1) is spread over the 8 warps, 4 tasks per chunk, each arriving with count 2
-        auto diffuse_group = [&](const float* S) {
+        // diffused chunks of one gate: one warp per (sample, term) applies P_m^T to the term-0 chunk in slot `src` (scaled
+        // hi / lo fp16, written by the epilogue) on the warp-level tensor path; 4 tasks per chunk, each arriving with count 2.
+        // i0 = chunk index of term 1 of this gate
+        auto diffuse_group = [&](int src, int i0, int k) {
             for (int m = 1; m < M; ++m) {
                 const int s = (warp - ((m - 1) * SB)) & 7;
                 if (s < SB) {
-                    uint8_t* sl = acquire();
-                    const float* pt = PTs + (s * (M - 1) + (m - 1)) * PT_STRIDE;
-                    if (p.mma_diff) {
-                        // warp-level tensor path (f16_common.cuh::diffuse_mma): polynomial fragments in registers, the fp32
-                        // source tile read once per element
-                        PFrag pf;
-                        load_pfrag(pt, lane, pf);
-                        diffuse_mma(S + (s * RP) * RB_LD, RB_LD, N, pf, sl, s * RP, lane, gs);
-                    } else {
-                        float acc[NPAD][2];
-                        diffuse2(S + (s * RP) * RB_LD + 2 * lane, RB_LD, N, pt, acc);
-                        store_cols2(sl, s * RP, lane, N, acc, gs, RG * 8);
-                    }
+                    const int slot = acquire(i0 + m - 1, k);
+                    PFrag pf;
+                    load_pfrag(PTs + (s * (M - 1) + (m - 1)) * PT_STRIDE, lane, pf);
+                    diffuse_mma16(Aslots + src * SLOT, s * RP, pf, Aslots + slot * SLOT, s * RP, lane, 1.f);
                     tc_fence_before();
                     fence_async_smem();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_n(&bar_afull[seq % 3], 2);
+                    if (lane == 0) mbar_arrive_n(&bar_afull[slot], 2);
                 }
-                ++seq;
             }
         };
         float dhp[32];                                                  // dh*u (+ d(rh)*r): the elementwise part of dh_{t-1}
@@ -313,21 +312,20 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
             const bool rec = p.dbg && blockIdx.x == 0 && tid == 0 && k < 64;
             long long* es = rb_dbg + k * 16;
             if (rec) es[0] = clock64();
-            mbar_wait2(&bar_gafull, k & 1, &bar_gbfull, k & 1);
+            mbar_wait(&bar_gafull, k & 1);
+            const uint32_t thp = tb + ((k & 1) ? RB_HP1 : RB_HP);
             if (rec) es[1] = clock64();
             if (k >= 1) mbar_wait(&bar_b2, (k - 1) & 1);                // dh_t's GEMM part (B2 of step t+1) is in acc2
             tc_fence_after();
             if (rec) es[2] = clock64();
-            uint8_t* slc = acquire();                                   // chunk [dA_c]
-            ++seq;
-            uint8_t* slu = acquire();                                   // chunk [dA_u]
-            --seq;
+            uint8_t* slc = Aslots + acquire(0, k) * SLOT;               // chunk [dA_c] (slot 0)
+            uint8_t* slu = Aslots + acquire(1, k) * SLOT;               // chunk [dA_u] (slot 1)
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {                            // 16 columns at a time (TMEM loads are paid per instruction)
                 float u[16], c[16], hp[16], g[16], a2[16];
                 tmem_ld16_nw(tb + RB_U + 16 * cc, u);
                 tmem_ld16_nw(tb + RB_C + 16 * cc, c);
-                tmem_ld16_nw(tb + RB_HP + 16 * cc, hp);
+                tmem_ld16_nw(thp + 16 * cc, hp);
                 tmem_ld16_nw(tb + RB_DUP + 16 * cc, g);
                 if (k >= 1) tmem_ld16_nw(tb + RB_ACC2 + 16 * cc, a2);
                 tmem_wait_ld();
@@ -349,8 +347,6 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
                         dhp[16 * cc + e] = dh * u[e];
                     }
                     const int col = half * 32 + 16 * cc + 8 * h8;
-                    put8f(SA, col, dac);
-                    put8f(SBt, col, dau);
                     put8(slc, col, dac);
                     put8(slu, col, dau);
                 }
@@ -358,26 +354,26 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_gafree);                    // u, c, d_hseq[t] consumed
-            publish();                                                  // [dA_c]
-            publish();                                                  // [dA_u]
+            publish(0);                                                 // [dA_c]
+            publish(1);                                                 // [dA_u]
             if (rec) es[3] = clock64();
-            rb_worker_bar();                                            // SA / SB of every row are visible
+            rb_worker_bar();                                            // both column halves of every row are written
             if (rec) es[4] = clock64();
             // ---- diffusion for B1, then the u half of B2 (independent of B1: fills B1's MMA latency) ---------------------
-            diffuse_group(SA);
+            diffuse_group(0, 2, k);
             if (rec) es[5] = clock64();
-            diffuse_group(SBt);
+            diffuse_group(1, M + 1, k);
             if (rec) es[6] = clock64();
-            mbar_wait(&bar_b1, k & 1);
+            mbar_wait2(&bar_b1, k & 1, &bar_gbfull, k & 1);            // d(rh) is in acc1; r of this step is in TMEM
             tc_fence_after();
             if (rec) es[7] = clock64();
             // ---- E2 ----------------------------------------------------------------------------------------------------
-            uint8_t* slr = acquire();                                   // chunk [dA_r]
+            uint8_t* slr = Aslots + acquire(2 * M, k) * SLOT;           // chunk [dA_r] (slot 0: every reader of [dA_c] is done, bar_b1)
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
                 float a1[16], hp[16], r[16];
                 tmem_ld16_nw(tb + RB_ACC1 + 16 * cc, a1);
-                tmem_ld16_nw(tb + RB_HP + 16 * cc, hp);
+                tmem_ld16_nw(thp + 16 * cc, hp);
                 tmem_ld16_nw(tb + RB_R + 16 * cc, r);
                 tmem_wait_ld();
 #pragma unroll
@@ -391,17 +387,16 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
                         dhp[16 * cc + e] += drh * r[e];
                     }
                     const int col = half * 32 + 16 * cc + 8 * h8;
-                    put8f(SA, col, dar);                                // (bar_b1: every warp is past its reads of SA = dA_c)
                     put8(slr, col, dar);
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_gbfree);                    // r, h_{t-1} consumed
-            publish();                                                  // [dA_r]
+            publish(0);                                                 // [dA_r]
             if (rec) es[8] = clock64();
             rb_worker_bar();
-            diffuse_group(SA);
+            diffuse_group(0, 2 * M + 1, k);
             if (rec) es[9] = clock64();
         }
         // ---- dh0 = dh' + B2 of the last processed step (t = 0) ------------------------------------------------------------
@@ -511,7 +506,6 @@ cudaError_t launch_rnn_bwd(int B, int T, int N, int fin, int M, int act, const f
     p.B = B; p.T = T; p.N = N; p.M = M; p.act = act; p.dump = daimg != nullptr;
     p.img_T = img_T > 0 ? img_T : T; p.img_t0 = img_T > 0 ? img_t0 : 0;
     { const char* e = getenv("DCGRU_DBG"); p.dbg = e ? (atoi(e) & 32) : 0; }
-    { const char* e = getenv("DCGRU_MMA_DIFF_BWD"); p.mma_diff = !(e && e[0] == '0'); }
     p.h0 = h0; p.hseq = hseq; p.ruc = ruc; p.P = P; p.d_hseq = d_hseq; p.d_hlast = d_hlast;
     p.d_hsel = d_hsel; p.sel_t = sel_t;
     p.wimg = reinterpret_cast<const uint8_t*>(wimg); p.scale_ptr = scale_ptr; p.dh0 = dh0;

@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdcgru_b200.so")
+# DCGRU_B200_LIB selects another build of the same library in lib/ (the jittered stress build, tests/test_gpu_stress.py)
+LIB_PATH = os.path.join(_HERE, "lib", os.path.basename(os.environ.get("DCGRU_B200_LIB", "libdcgru_b200.so")))
 
 SYMBOLS = [
     "dcgru_version", "dcgru_last_error", "dcgru_graph_poly", "dcgru_corr_supports", "dcgru_fft_features",

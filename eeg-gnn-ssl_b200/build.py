@@ -23,17 +23,28 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(verbose=False, force=False):
-    os.makedirs(OUT_DIR, exist_ok=True)
+JITTER_LIB = os.path.join(OUT_DIR, "libdcgru_b200_jitter.so")
+
+
+def build(verbose=False, force=False, jitter=False):
+    """jitter=True: the stress variant libdcgru_b200_jitter.so (-DDCGRU_JITTER=3000: random sleeps in front of every mbarrier
+    operation, csrc/tc_common.cuh), objects under lib/jitter/; used by tests/test_gpu_stress.py only."""
+    if jitter:
+        return _build(verbose, force, os.path.join(OUT_DIR, "jitter"), JITTER_LIB, ["-DDCGRU_JITTER=3000"])
+    return _build(verbose, force, OUT_DIR, LIB, [])
+
+
+def _build(verbose, force, obj_dir, lib_path, extra):
+    os.makedirs(obj_dir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(ROOT, "include", "dcgru_b200.h"))
     objs, jobs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
+        o = os.path.join(obj_dir, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             jobs.append(cmd)
 
     def run(cmd):
@@ -47,14 +58,14 @@ def build(verbose=False, force=False):
             rcs = list(ex.map(run, jobs))
         if any(rcs):
             raise RuntimeError("nvcc failed")
-    if jobs or force or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+    if jobs or force or _stale(lib_path, objs):
+        cmd = [NVCC, "-shared", "-o", lib_path] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv, jitter="--jitter" in sys.argv))

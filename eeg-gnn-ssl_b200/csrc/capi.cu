@@ -348,6 +348,8 @@ int dcgru_fft_features(int32_t batch, int32_t num_nodes, int32_t seq_len, int32_
     if (stat_len != 0 && stat_len != 1 && stat_len != num_nodes) return fail("stat_len=%d must be 0, 1 or num_nodes", stat_len);
     if (stat_len && (!mean || !std)) return fail("null mean/std");
     if ((raw && !aligned16(raw)) || (x && !aligned16(x))) return fail("outputs must be 16-byte aligned");
+    if (!aligned16(signal) || stride_b % 4 || stride_n % 4)
+        return fail("signal must be 16-byte aligned with batch / channel strides that are multiples of 4 samples (bulk copies)");
     cudaStream_t st = (cudaStream_t)stream;
     LAUNCH("fft_features", launch_fft_features(batch, num_nodes, seq_len, signal, stride_b, stride_n, dest_channel, log_scale,
                                                mean, std, stat_len, raw, x, devinfo().sms, st));

@@ -15,14 +15,17 @@
 // = 51 packed (re, im) FMAs (fma.rn.f32x2) per bin instead of 400 scalar ones.  Thread = one bin k, its 51 (cos, sin)
 // twiddle pairs live in registers for the whole kernel;
 // a warp holds bins of one parity, so every folded (C_j, S_j) pair it needs comes from a broadcast LDS.128 for all 32 lanes.  A CTA
-// (128 threads: warps 0-1 even bins, 2-3 odd bins) is persistent over batches of FW windows: coalesced float4 loads ->
+// (128 threads: warps 0-1 even bins, 2-3 odd bins) is persistent over batches of FW windows: cp.async.bulk of the next
+// batch's samples (800 B per window, mbarrier) while this one is transformed ->
 // fold into shared memory -> 51 packed FMAs per (bin, window) -> log amplitude -> shared -> coalesced stores with the
 // augmentation and the scaler applied on the way out.  fp32 arithmetic on fp32 samples (the sums have 51 terms; measured
 // error vs the float64 reference <= 2e-6 of the largest feature, tests/test_gpu_fft.py).
 #include "common.cuh"
 #include "dw.cuh"
+#include "tc_common.cuh"
 
 namespace dcgru {
+using namespace tc;
 
 constexpr int FFT_W = 200;           // samples per window (FREQUENCY * time_step_size, constants.py / args.py)
 constexpr int FFT_K = FFT_W / 2;     // bins kept
@@ -47,12 +50,17 @@ __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
     return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
 }
 
+// offsets / scalers of the windows of batch `w0` -> shared memory (thread i < nw handles window i)
+struct FftWin { long long src, dst, dstx; float ls, m, sd; int pad; };
+
 __global__ void __launch_bounds__(FFT_THREADS) fft_features_kernel(const FftParams p) {
+    // raw samples of two batches (the next one is in flight while this one is transformed): cp.async.bulk, 800 B per window
+    __shared__ __align__(128) float rawb[2][FFT_FW][FFT_W];
     // folded values, interleaved so that one LDS.128 yields two ready (C_j, S_j) operand pairs of the packed FMA
     __shared__ __align__(16) float2 fold[FFT_FW][2][FFT_FLD];     // [window][even | odd bins][j] = (C_j, S_j)
     __shared__ __align__(16) float outb[FFT_FW][FFT_K];
-    __shared__ long long s_src[FFT_FW], s_dst[FFT_FW], s_dstx[FFT_FW];   // element offsets of the window in signal / raw / x
-    __shared__ float s_ls[FFT_FW], s_m[FFT_FW], s_sd[FFT_FW];
+    __shared__ FftWin win[2][FFT_FW];
+    __shared__ uint64_t bar_raw[2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int parity = warp >> 1;                                 // warps 0-1: even bins, 2-3: odd bins
     const int kidx = (warp & 1) * 32 + lane;                      // 0..63, 50 used
@@ -65,40 +73,62 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_features_kernel(const FftPara
         tw2[j] = pack2(p.tw[m], p.tw[200 + m]);
     }
     const int TN = p.T * p.N;
-    for (long long w0 = (long long)blockIdx.x * FFT_FW; w0 < p.nwin; w0 += (long long)gridDim.x * FFT_FW) {
+    if (tid == 0) {
+        mbar_init(&bar_raw[0], 1);
+        mbar_init(&bar_raw[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    // window order (b, n, t): consecutive windows are consecutive samples.  Warp 0 describes the windows of a batch and
+    // starts their copies; buffer `buf` is free (the fold of the batch that used it is behind a __syncthreads)
+    auto prefetch = [&](long long w0, int buf) {
         const int nw = (int)((p.nwin - w0 < FFT_FW) ? (p.nwin - w0) : FFT_FW);
-        __syncthreads();
-        if (tid < nw) {                                           // window order (b, n, t): consecutive windows are consecutive samples
-            const long long wi = w0 + tid;
+        if (lane < nw) {
+            const long long wi = w0 + lane;
             const int b = (int)(wi / TN);
             const int r = (int)(wi - (long long)b * TN);
             const int n = r / p.T, t = r - n * p.T;
-            s_src[tid] = (long long)b * p.sig_sb + (long long)n * p.sig_sn + (long long)t * FFT_W;
-            s_dst[tid] = (((long long)b * p.T + t) * p.N + n) * FFT_K;
+            FftWin w;
+            w.src = (long long)b * p.sig_sb + (long long)n * p.sig_sn + (long long)t * FFT_W;
+            w.dst = (((long long)b * p.T + t) * p.N + n) * FFT_K;
             const int no = p.perm ? p.perm[(long long)b * p.N + n] : n;
-            s_dstx[tid] = (((long long)b * p.T + t) * p.N + no) * FFT_K;
-            s_ls[tid] = p.log_scale ? p.log_scale[b] : 0.f;
+            w.dstx = (((long long)b * p.T + t) * p.N + no) * FFT_K;
+            w.ls = p.log_scale ? p.log_scale[b] : 0.f;
             const int si = p.stat_len == 1 ? 0 : no;
-            s_m[tid] = p.stat_len ? p.mean[si] : 0.f;
-            s_sd[tid] = p.stat_len ? p.stdv[si] : 1.f;
+            w.m = p.stat_len ? p.mean[si] : 0.f;
+            w.sd = p.stat_len ? p.stdv[si] : 1.f;
+            w.pad = 0;
+            win[buf][lane] = w;
+            if (lane == 0) mbar_expect_tx(&bar_raw[buf], (uint32_t)(nw * FFT_W * 4));
+            __syncwarp(__activemask());
+            bulk_g2s(&rawb[buf][lane][0], p.signal + w.src, FFT_W * 4, &bar_raw[buf]);
         }
-        __syncthreads();
-        // ---- load + fold: item = (window, j), j = 0..50: reads x_j, x_{200-j}, x_{100-j}, x_{100+j} ------------------
-        for (int it = tid; it < nw * 51; it += FFT_THREADS) {
-            const int w = it / 51, j = it - w * 51;
-            const float* s = p.signal + s_src[w];
+    };
+    const long long stride = (long long)gridDim.x * FFT_FW;
+    long long w0 = (long long)blockIdx.x * FFT_FW;
+    if (warp == 0 && w0 < p.nwin) prefetch(w0, 0);
+    for (int it = 0; w0 < p.nwin; w0 += stride, ++it) {
+        const int buf = it & 1;
+        const int nw = (int)((p.nwin - w0 < FFT_FW) ? (p.nwin - w0) : FFT_FW);
+        __syncthreads();                                          // every thread is done with batch it-1 (fold, outb, win[buf^1])
+        if (warp == 0 && w0 + stride < p.nwin) prefetch(w0 + stride, buf ^ 1);
+        mbar_wait(&bar_raw[buf], (it >> 1) & 1);
+        // ---- fold: item = (window, j), j = 0..50: x_j, x_{200-j}, x_{100-j}, x_{100+j} -----------------------------------
+        for (int i = tid; i < nw * 51; i += FFT_THREADS) {
+            const int w = i / 51, j = i - w * 51;
+            const float* s = rawb[buf][w];
             float ce, se, co, so;
             if (j == 0) {
-                const float x0 = __ldcs(s), x100 = __ldcs(s + 100);
+                const float x0 = s[0], x100 = s[100];
                 ce = x0 + x100; co = x0 - x100; se = 0.f; so = 0.f;
             } else if (j == 50) {
-                const float x50 = __ldcs(s + 50), x150 = __ldcs(s + 150);
+                const float x50 = s[50], x150 = s[150];
                 ce = x50 + x150;            // a_50 (even bins: times cos(pi k / 2))
                 co = 0.f;
                 se = 0.f;
                 so = x50 - x150;            // d_50 (odd bins: times sin(pi k / 2))
             } else {
-                const float xa = __ldcs(s + j), xb = __ldcs(s + 200 - j), xc = __ldcs(s + 100 - j), xd = __ldcs(s + 100 + j);
+                const float xa = s[j], xb = s[200 - j], xc = s[100 - j], xd = s[100 + j];
                 const float aj = xa + xb, dj = xa - xb;           // a_j, d_j
                 const float ar = xc + xd, dr = xc - xd;           // a_{100-j}, d_{100-j}
                 ce = aj + ar; co = aj - ar; se = dj - dr; so = dj + dr;
@@ -137,20 +167,21 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_features_kernel(const FftPara
         }
         __syncthreads();
         // ---- coalesced stores: raw features, and augmented + standardised x ------------------------------------------
-        for (int it = tid; it < nw * (FFT_K / 4); it += FFT_THREADS) {
-            const int w = it / (FFT_K / 4), q = it - w * (FFT_K / 4);
+        for (int i = tid; i < nw * (FFT_K / 4); i += FFT_THREADS) {
+            const int w = i / (FFT_K / 4), q = i - w * (FFT_K / 4);
+            const FftWin& wd = win[buf][w];
             float4 v = *reinterpret_cast<const float4*>(&outb[w][4 * q]);
-            if (p.raw) __stcs(reinterpret_cast<float4*>(p.raw + s_dst[w]) + q, v);
+            if (p.raw) __stcs(reinterpret_cast<float4*>(p.raw + wd.dst) + q, v);
             if (p.x) {
                 if (p.log_scale) {
-                    const float ls = s_ls[w];
+                    const float ls = wd.ls;
                     v.x += ls; v.y += ls; v.z += ls; v.w += ls;
                 }
                 if (p.stat_len > 0) {
-                    const float m = s_m[w], sd = s_sd[w];
+                    const float m = wd.m, sd = wd.sd;
                     v.x = (v.x - m) / sd; v.y = (v.y - m) / sd; v.z = (v.z - m) / sd; v.w = (v.w - m) / sd;
                 }
-                __stcs(reinterpret_cast<float4*>(p.x + s_dstx[w]) + q, v);
+                __stcs(reinterpret_cast<float4*>(p.x + wd.dstx) + q, v);
             }
         }
     }

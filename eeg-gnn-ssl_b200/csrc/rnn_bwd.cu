@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
                     unsigned fill;
                     rb_chunk(i, M, kind, m);
                     rb_slot(i, k, M, slot, fill);
+                    DBG_PROG(k * 100 + i);
                     const uint32_t ah = a_base + slot * SLOT, al = ah + PLANE;
                     const uint32_t d = taddr + (kind == 0 ? RB_ACC1 : RB_ACC2);
                     const uint32_t first = (i <= 1) ? 0u : 1u;
@@ -165,6 +166,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
                     const int piece0 = (kind == 0) ? 2 * m : 2 * M + 2 * (2 * m + (kind == 1 ? 1 : 0));
                     for (int pl = 0; pl < 2; ++pl, ++pc) {
                         const int ws = pc % RB_NW;
+                        DBG_PROG(k * 100 + i);
                         if (pc >= RB_NW) mbar_wait(&bar_wempty[ws], ((pc / RB_NW) - 1) & 1);
                         mbar_expect_tx(&bar_wfull[ws], RB_WPIECE);
                         bulk_g2s(Wring + ws * RB_WPIECE, p.wimg + (size_t)(piece0 + pl) * RB_WPIECE, RB_WPIECE, &bar_wfull[ws]);
@@ -184,6 +186,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
                     int slot;
                     unsigned fill;
                     rb_slot(i, k, M, slot, fill);
+                    DBG_PROG(k * 100 + i);
                     mbar_wait(&bar_afull[slot], fill & 1);
                     const int col = (i == 0) ? 2 * RB_H : (i == 1 ? RB_H : (i == 2 * M ? 0 : -1));   // image columns r | u | c
                     if (col >= 0) {
@@ -193,8 +196,11 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
                             bulk_commit();
                         }
                         bulk_wait_read();
-                        __syncwarp();
                     }
+                    // every lane has seen this chunk's phase before lane 0 lets the slot be refilled: found by the stress build --
+                    // without it, lanes that lag behind lane 0 (only its arrival gates the producers) can be overtaken by two
+                    // phases on a ring slot and then wait for ever
+                    __syncwarp();
                     if (lane == 0) mbar_arrive(&bar_stored[slot]);
                 }
             }
@@ -227,8 +233,10 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
             const int t = T - 1 - k;
             const float* ruc = p.ruc + ((size_t)t * p.B * N + rbase) * 3 * RB_H;
             const float* hp = (t > 0) ? p.hseq + (size_t)(t - 1) * p.B * NH + rbase * RB_H : p.h0 + rbase * RB_H;
+            DBG_PROG(k * 10 + 1);
             if (k >= 1) mbar_wait(&bar_gafree, (k - 1) & 1);
             tc_fence_after();
+            DBG_PROG(k * 10 + 2);
             // group A (needed by E1): u, c, upstream gradient, h_{t-1}.  h_{t-1} is also read by E2, so its TMEM columns alternate
             // between two buffers: the copy of step k is still being read when the one of step k+1 arrives (every worker warp
             // passes E2 of step k-1 before it frees group A of step k)
@@ -240,8 +248,10 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_gafull);
+            DBG_PROG(k * 10 + 3);
             if (k >= 1) mbar_wait(&bar_gbfree, (k - 1) & 1);
             tc_fence_after();
+            DBG_PROG(k * 10 + 4);
             load_cols(ruc, RB_R);                                         // group B (needed by E2 only): r
             tc_fence_before();
             __syncwarp();
@@ -312,12 +322,15 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
             const bool rec = p.dbg && blockIdx.x == 0 && tid == 0 && k < 64;
             long long* es = rb_dbg + k * 16;
             if (rec) es[0] = clock64();
+            DBG_PROG(k * 10 + 0);
             mbar_wait(&bar_gafull, k & 1);
+            DBG_PROG(k * 10 + 1);
             const uint32_t thp = tb + ((k & 1) ? RB_HP1 : RB_HP);
             if (rec) es[1] = clock64();
             if (k >= 1) mbar_wait(&bar_b2, (k - 1) & 1);                // dh_t's GEMM part (B2 of step t+1) is in acc2
             tc_fence_after();
             if (rec) es[2] = clock64();
+            DBG_PROG(k * 10 + 2);
             uint8_t* slc = Aslots + acquire(0, k) * SLOT;               // chunk [dA_c] (slot 0)
             uint8_t* slu = Aslots + acquire(1, k) * SLOT;               // chunk [dA_u] (slot 1)
 #pragma unroll
@@ -360,14 +373,18 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
             rb_worker_bar();                                            // both column halves of every row are written
             if (rec) es[4] = clock64();
             // ---- diffusion for B1, then the u half of B2 (independent of B1: fills B1's MMA latency) ---------------------
+            DBG_PROG(k * 10 + 3);
             diffuse_group(0, 2, k);
             if (rec) es[5] = clock64();
+            DBG_PROG(k * 10 + 4);
             diffuse_group(1, M + 1, k);
             if (rec) es[6] = clock64();
+            DBG_PROG(k * 10 + 5);
             mbar_wait2(&bar_b1, k & 1, &bar_gbfull, k & 1);            // d(rh) is in acc1; r of this step is in TMEM
             tc_fence_after();
             if (rec) es[7] = clock64();
             // ---- E2 ----------------------------------------------------------------------------------------------------
+            DBG_PROG(k * 10 + 6);
             uint8_t* slr = Aslots + acquire(2 * M, k) * SLOT;           // chunk [dA_r] (slot 0: every reader of [dA_c] is done, bar_b1)
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
@@ -395,8 +412,11 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
             if (lane == 0) mbar_arrive(&bar_gbfree);                    // r, h_{t-1} consumed
             publish(0);                                                 // [dA_r]
             if (rec) es[8] = clock64();
+            DBG_PROG(k * 10 + 7);
             rb_worker_bar();
+            DBG_PROG(k * 10 + 8);
             diffuse_group(0, 2 * M + 1, k);
+            DBG_PROG(k * 10 + 9);
             if (rec) es[9] = clock64();
         }
         // ---- dh0 = dh' + B2 of the last processed step (t = 0) ------------------------------------------------------------

@@ -12,6 +12,7 @@
 // so a thread that owns 4 consecutive k of one row writes one 16-byte word and consecutive rows are
 // consecutive words (conflict-free), and a sub-range of rows is just an address offset.
 #pragma once
+#include <cstdio>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -132,6 +133,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 }
 
 // ---- mbarrier -----------------------------------------------------------------------------------------
+// Stress build (-DDCGRU_JITTER=<ns>, libdcgru_b200_jitter.so, tests/test_gpu_stress.py): every mbarrier wait / arrive /
+// commit is preceded, one time in four, by a pseudo-random sleep of up to DCGRU_JITTER ns, so producers, issuer, loaders
+// and dump warps drift against each other by whole pipeline stages.  A wait that polls a phase a later phase can
+// overtake, or a slot reused before its consumer is done, then shows up within a few hundred iterations as a trap
+// (bounded spins) or as a result that differs from the un-jittered run.  The production build compiles this to nothing.
+#ifdef DCGRU_JITTER
+__device__ __forceinline__ void dbg_jitter() {
+    const unsigned long long c = clock64();
+    unsigned h = ((unsigned)c ^ (unsigned)(c >> 17)) * 2654435761u + threadIdx.x * 40503u + blockIdx.x * 9973u;
+    h ^= h >> 15;
+    if ((h & 3u) == 0u) __nanosleep((h >> 8) % (unsigned)(DCGRU_JITTER));
+}
+#else
+__device__ __forceinline__ void dbg_jitter() {}
+#endif
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -142,9 +158,39 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 // lanes/clk/SM, shared with MUFU and the fp16 conversions): ncu showed it 100 % busy over the whole rnn_fwd kernel and
 // 36 % of all executed warp instructions were SYNCS/BRA of these loops, which starved the epilogues.
 constexpr uint32_t MBAR_SUSPEND_NS = 1000000u;
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef DCGRU_JITTER
+constexpr uint32_t MBAR_SPINS = 1u << 12, MBAR_SPINS_RELAXED = 1u << 21;     // stress build: give up after a few seconds
+#else
+constexpr uint32_t MBAR_SPINS = 1u << 22, MBAR_SPINS_RELAXED = 1u << 24;
+#endif
+// a wait that never completes kills the context; the stress build first names the wait (source line, CTA, thread)
+#ifdef DCGRU_JITTER
+// progress marks of the stress build: one int per (CTA < 64, warp < 16), printed by the first wait that times out
+__device__ int g_dbg_prog[64 * 16];
+#define DBG_PROG(v) do { if ((threadIdx.x & 31) == 0 && blockIdx.x < 64) ((volatile int*)g_dbg_prog)[blockIdx.x * 16 + (threadIdx.x >> 5)] = (v); } while (0)
+static __device__ __noinline__ void mbar_timeout(int line) {
+    const unsigned act = __activemask();
+    if ((int)(threadIdx.x & 31) == __ffs(act) - 1) {
+        const volatile int* g = (const volatile int*)g_dbg_prog + (blockIdx.x < 64 ? blockIdx.x * 16 : 0);
+        printf("dcgru_b200: mbarrier wait timed out at line %d (block %d, warp %d of %d, lanes %08x) progress: %d %d %d %d %d %d %d %d | %d %d %d | %d %d %d %d\n",
+               line, (int)blockIdx.x, (int)(threadIdx.x >> 5), (int)(blockDim.x >> 5), act, g[0], g[1], g[2], g[3], g[4], g[5], g[6], g[7],
+               g[8], g[9], g[10], g[11], g[12], g[13], g[14]);
+    }
+    for (int i = 0; i < 3000; ++i) __nanosleep(1000000);      // let every other stuck warp report before the context dies
+    asm volatile("trap;\n");
+}
+#else
+#define DBG_PROG(v) do { } while (0)
+__device__ __forceinline__ void mbar_timeout(int) { asm volatile("trap;\n"); }
+#endif
+#define mbar_wait(...) mbar_wait_l(__LINE__, __VA_ARGS__)
+#define mbar_wait_relaxed(...) mbar_wait_relaxed_l(__LINE__, __VA_ARGS__)
+#define mbar_wait2(...) mbar_wait2_l(__LINE__, __VA_ARGS__)
+#define mbar_wait3(...) mbar_wait3_l(__LINE__, __VA_ARGS__)
+__device__ __forceinline__ void mbar_wait_l(int line, uint64_t* bar, uint32_t parity) {
+    dbg_jitter();
     uint32_t done = 0;
-    for (uint32_t it = 0; it < (1u << 22); ++it) {
+    for (uint32_t it = 0; it < MBAR_SPINS; ++it) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
@@ -152,14 +198,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "=r"(done) : "r"(smem_u32(bar)), "r"(parity), "r"(MBAR_SUSPEND_NS) : "memory");
         if (done) return;
     }
-    asm volatile("trap;\n");
+    mbar_timeout(line);
 }
 
 // for warps that are far off the critical path (ring loaders that run steps ahead, the image dump): poll with plain
 // test_wait and sleep in between, so that the waiting does not compete with the working warps for issue slots
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned ns = 256) {
+__device__ __forceinline__ void mbar_wait_relaxed_l(int line, uint64_t* bar, uint32_t parity, unsigned ns = 256) {
+    dbg_jitter();
     uint32_t done = 0;
-    for (uint32_t it = 0; it < (1u << 24); ++it) {
+    for (uint32_t it = 0; it < MBAR_SPINS_RELAXED; ++it) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
             "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -168,17 +215,20 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
         if (done) return;
         __nanosleep(ns);
     }
-    asm volatile("trap;\n");
+    mbar_timeout(line);
 }
 
 // ---- bulk copies (TMA, no tensor map) ----------------------------------------------------------------
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    dbg_jitter();
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
+    dbg_jitter();
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(n) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    dbg_jitter();
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 // global -> shared, completion counted in bytes on an mbarrier
@@ -241,10 +291,11 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t l
 
 // wait for two (three) barriers at once: the polls are issued back to back so their latencies (~200 cycles each,
 // even when the phase completed long ago) overlap instead of adding up on the waiting thread's critical path
-__device__ __forceinline__ void mbar_wait2(uint64_t* b0, uint32_t p0, uint64_t* b1, uint32_t p1) {
+__device__ __forceinline__ void mbar_wait2_l(int line, uint64_t* b0, uint32_t p0, uint64_t* b1, uint32_t p1) {
+    dbg_jitter();
     const uint32_t a0 = smem_u32(b0), a1 = smem_u32(b1);
     uint32_t d0 = 0, d1 = 0;
-    for (uint32_t it = 0; it < (1u << 22); ++it) {
+    for (uint32_t it = 0; it < MBAR_SPINS; ++it) {
         asm volatile(
             "{\n\t.reg .pred p, q;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%2], %3, %6;\n\t"
@@ -254,12 +305,13 @@ __device__ __forceinline__ void mbar_wait2(uint64_t* b0, uint32_t p0, uint64_t* 
             : "=r"(d0), "=r"(d1) : "r"(a0), "r"(p0), "r"(a1), "r"(p1), "r"(MBAR_SUSPEND_NS) : "memory");
         if (d0 & d1) return;
     }
-    asm volatile("trap;\n");
+    mbar_timeout(line);
 }
-__device__ __forceinline__ void mbar_wait3(uint64_t* b0, uint32_t p0, uint64_t* b1, uint32_t p1, uint64_t* b2, uint32_t p2) {
+__device__ __forceinline__ void mbar_wait3_l(int line, uint64_t* b0, uint32_t p0, uint64_t* b1, uint32_t p1, uint64_t* b2, uint32_t p2) {
+    dbg_jitter();
     const uint32_t a0 = smem_u32(b0), a1 = smem_u32(b1), a2 = smem_u32(b2);
     uint32_t d0 = 0, d1 = 0, d2 = 0;
-    for (uint32_t it = 0; it < (1u << 22); ++it) {
+    for (uint32_t it = 0; it < MBAR_SPINS; ++it) {
         asm volatile(
             "{\n\t.reg .pred p, q, r;\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%3], %4, %9;\n\t"
@@ -271,7 +323,7 @@ __device__ __forceinline__ void mbar_wait3(uint64_t* b0, uint32_t p0, uint64_t* 
             : "=r"(d0), "=r"(d1), "=r"(d2) : "r"(a0), "r"(p0), "r"(a1), "r"(p1), "r"(a2), "r"(p2), "r"(MBAR_SUSPEND_NS) : "memory");
         if (d0 & d1 & d2) return;
     }
-    asm volatile("trap;\n");
+    mbar_timeout(line);
 }
 
 // ---- 3xTF32 split ---------------------------------------------------------------------------------------

@@ -101,7 +101,7 @@ def fft_features(signal, mean=None, std=None, dest_channel=None, log_scale=None,
         raise ValueError("signal must be (B, N, T*window)")
     if signal.dtype != torch.float32:
         raise ValueError("signal must be float32")
-    if signal.stride(2) != 1:
+    if signal.stride(2) != 1 or signal.stride(0) % 4 or signal.stride(1) % 4 or signal.data_ptr() % 16:
         signal = signal.contiguous()
     b, n, s = signal.shape
     t = s // window

@@ -101,7 +101,8 @@ int dcgru_corr_supports(int32_t batch, int32_t seq_len, int32_t num_nodes, int32
  *   computeFFT), then _random_reflect / _random_scale (data/dataloader_detection.py:233-256:
  *   swap channel pairs; += log(scale_factor)), then StandardScaler.transform (utils.py:402-403).
  * signal: resampled EEG, element (b, n, s) at signal + b*stride_b + n*stride_n + s, seq_len*200
- *         contiguous samples per channel (the h5 layout, channels x samples)
+ *         contiguous samples per channel (the h5 layout, channels x samples); 16-byte aligned,
+ *         strides multiples of 4 samples (the windows are fetched with 800-byte bulk copies)
  * dest_channel: (B, N) int32 or NULL -- output channel that source channel n lands in (for the
  *         reference's pair swaps, an involution, this is the swapped index; NULL = no reflection)
  * log_scale: (B) or NULL -- log(scale_factor) of _random_scale

@@ -15,8 +15,8 @@
 // = 51 packed (re, im) FMAs (fma.rn.f32x2) per bin instead of 400 scalar ones.  Thread = one bin k, its 51 (cos, sin)
 // twiddle pairs live in registers for the whole kernel;
 // a warp holds bins of one parity, so every folded (C_j, S_j) pair it needs comes from a broadcast LDS.128 for all 32 lanes.  A CTA
-// (128 threads: warps 0-1 even bins, 2-3 odd bins) is persistent over batches of FW windows: cp.async.bulk of the next
-// batch's samples (800 B per window, mbarrier) while this one is transformed ->
+// (128 threads: warps 0-1 even bins, 2-3 odd bins) is persistent over items = (channel of a clip, 16 consecutive windows):
+// one cp.async.bulk fetches the next item's samples (12.8 KB, mbarrier) while this one is transformed ->
 // fold into shared memory -> 51 packed FMAs per (bin, window) -> log amplitude -> shared -> coalesced stores with the
 // augmentation and the scaler applied on the way out.  fp32 arithmetic on fp32 samples (the sums have 51 terms; measured
 // error vs the float64 reference <= 2e-6 of the largest feature, tests/test_gpu_fft.py).
@@ -50,16 +50,14 @@ __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
     return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
 }
 
-// offsets / scalers of the windows of batch `w0` -> shared memory (thread i < nw handles window i)
-struct FftWin { long long src, dst, dstx; float ls, m, sd; int pad; };
-
-__global__ void __launch_bounds__(FFT_THREADS) fft_features_kernel(const FftParams p) {
-    // raw samples of two batches (the next one is in flight while this one is transformed): cp.async.bulk, 800 B per window
+// Work item = (channel of a clip, block of FFT_FW consecutive windows): the samples of an item are one contiguous range
+// whatever the strides of the signal, and the augmentation / scaler constants are per item.
+__global__ void __launch_bounds__(FFT_THREADS, 3) fft_features_kernel(const FftParams p) {
+    // raw samples of two items (the next one is in flight while this one is transformed): one cp.async.bulk per item
     __shared__ __align__(128) float rawb[2][FFT_FW][FFT_W];
     // folded values, interleaved so that one LDS.128 yields two ready (C_j, S_j) operand pairs of the packed FMA
     __shared__ __align__(16) float2 fold[FFT_FW][2][FFT_FLD];     // [window][even | odd bins][j] = (C_j, S_j)
     __shared__ __align__(16) float outb[FFT_FW][FFT_K];
-    __shared__ FftWin win[2][FFT_FW];
     __shared__ uint64_t bar_raw[2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int parity = warp >> 1;                                 // warps 0-1: even bins, 2-3: odd bins
@@ -72,48 +70,41 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_features_kernel(const FftPara
         const int m = (j * k) % 200;
         tw2[j] = pack2(p.tw[m], p.tw[200 + m]);
     }
-    const int TN = p.T * p.N;
     if (tid == 0) {
         mbar_init(&bar_raw[0], 1);
         mbar_init(&bar_raw[1], 1);
         mbar_fence_init();
     }
     __syncthreads();
-    // window order (b, n, t): consecutive windows are consecutive samples.  Warp 0 describes the windows of a batch and
-    // starts their copies; buffer `buf` is free (the fold of the batch that used it is behind a __syncthreads)
-    auto prefetch = [&](long long w0, int buf) {
-        const int nw = (int)((p.nwin - w0 < FFT_FW) ? (p.nwin - w0) : FFT_FW);
-        if (lane < nw) {
-            const long long wi = w0 + lane;
-            const int b = (int)(wi / TN);
-            const int r = (int)(wi - (long long)b * TN);
-            const int n = r / p.T, t = r - n * p.T;
-            FftWin w;
-            w.src = (long long)b * p.sig_sb + (long long)n * p.sig_sn + (long long)t * FFT_W;
-            w.dst = (((long long)b * p.T + t) * p.N + n) * FFT_K;
-            const int no = p.perm ? p.perm[(long long)b * p.N + n] : n;
-            w.dstx = (((long long)b * p.T + t) * p.N + no) * FFT_K;
-            w.ls = p.log_scale ? p.log_scale[b] : 0.f;
-            const int si = p.stat_len == 1 ? 0 : no;
-            w.m = p.stat_len ? p.mean[si] : 0.f;
-            w.sd = p.stat_len ? p.stdv[si] : 1.f;
-            w.pad = 0;
-            win[buf][lane] = w;
-            if (lane == 0) mbar_expect_tx(&bar_raw[buf], (uint32_t)(nw * FFT_W * 4));
-            __syncwarp(__activemask());
-            bulk_g2s(&rawb[buf][lane][0], p.signal + w.src, FFT_W * 4, &bar_raw[buf]);
-        }
+    const int nbt = (p.T + FFT_FW - 1) / FFT_FW;                  // window blocks per channel
+    const int nitem = p.B * p.N * nbt;
+    auto prefetch = [&](int item, int buf) {                      // one thread
+        const int pair = item / nbt, tb = item - pair * nbt;
+        const int b = pair / p.N, n = pair - b * p.N;
+        const int t0 = tb * FFT_FW;
+        const int nw = (p.T - t0 < FFT_FW) ? (p.T - t0) : FFT_FW;
+        const uint32_t bytes = (uint32_t)(nw * FFT_W * 4);
+        mbar_expect_tx(&bar_raw[buf], bytes);
+        bulk_g2s(&rawb[buf][0][0], p.signal + (long long)b * p.sig_sb + (long long)n * p.sig_sn + (long long)t0 * FFT_W, bytes,
+                 &bar_raw[buf]);
     };
-    const long long stride = (long long)gridDim.x * FFT_FW;
-    long long w0 = (long long)blockIdx.x * FFT_FW;
-    if (warp == 0 && w0 < p.nwin) prefetch(w0, 0);
-    for (int it = 0; w0 < p.nwin; w0 += stride, ++it) {
+    int item = blockIdx.x;
+    if (tid == 0 && item < nitem) prefetch(item, 0);
+    for (int it = 0; item < nitem; item += gridDim.x, ++it) {
         const int buf = it & 1;
-        const int nw = (int)((p.nwin - w0 < FFT_FW) ? (p.nwin - w0) : FFT_FW);
-        __syncthreads();                                          // every thread is done with batch it-1 (fold, outb, win[buf^1])
-        if (warp == 0 && w0 + stride < p.nwin) prefetch(w0 + stride, buf ^ 1);
+        const int pair = item / nbt, tb = item - pair * nbt;
+        const int b = pair / p.N, n = pair - b * p.N;
+        const int t0 = tb * FFT_FW;
+        const int nw = (p.T - t0 < FFT_FW) ? (p.T - t0) : FFT_FW;
+        // constants of the item (loaded now, used by the stores at the end: the latency hides behind the transform)
+        const int no = p.perm ? p.perm[(long long)b * p.N + n] : n;           // destination channel of source channel n
+        const float ls = p.log_scale ? p.log_scale[b] : 0.f;
+        const float mean = p.stat_len ? p.mean[p.stat_len == 1 ? 0 : no] : 0.f;
+        const float sd = p.stat_len ? p.stdv[p.stat_len == 1 ? 0 : no] : 1.f;
+        __syncthreads();                                          // every thread is done with item it-1 (fold, outb, rawb[buf^1])
+        if (tid == 0 && item + (int)gridDim.x < nitem) prefetch(item + gridDim.x, buf ^ 1);
         mbar_wait(&bar_raw[buf], (it >> 1) & 1);
-        // ---- fold: item = (window, j), j = 0..50: x_j, x_{200-j}, x_{100-j}, x_{100+j} -----------------------------------
+        // ---- fold: work unit = (window, j), j = 0..50: x_j, x_{200-j}, x_{100-j}, x_{100+j} -------------------------------
         for (int i = tid; i < nw * 51; i += FFT_THREADS) {
             const int w = i / 51, j = i - w * 51;
             const float* s = rawb[buf][w];
@@ -138,50 +129,53 @@ __global__ void __launch_bounds__(FFT_THREADS) fft_features_kernel(const FftPara
             if (j == 50) { fold[w][0][51] = make_float2(0.f, 0.f); fold[w][1][51] = make_float2(0.f, 0.f); }
         }
         __syncthreads();
-        // ---- 51 packed FMAs per (bin, window): (re, im) += (C_j, S_j) * (cos, sin); folded values are warp-wide broadcasts
+        // ---- 51 packed FMAs per (bin, window): (re, im) += (C_j, S_j) * (cos, sin); folded values are warp-wide broadcasts.
+        //      Unrolled over the windows so that the loads of window w+1 and the logarithm of window w-1 overlap the FMAs of w.
         if (kvalid) {
-            for (int w = 0; w < nw; ++w) {
-                const ulonglong2* F = reinterpret_cast<const ulonglong2*>(fold[w][parity]);
-                unsigned long long acc0 = 0ull, acc1 = 0ull, acc2 = 0ull, acc3 = 0ull;      // four chains of (re, im) partial sums
+            float pw[FFT_FW];
 #pragma unroll
-                for (int q = 0; q < 24; q += 2) {
-                    const ulonglong2 f = F[q], g = F[q + 1];
-                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc0) : "l"(f.x), "l"(tw2[2 * q]));
-                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc1) : "l"(f.y), "l"(tw2[2 * q + 1]));
-                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2) : "l"(g.x), "l"(tw2[2 * q + 2]));
-                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc3) : "l"(g.y), "l"(tw2[2 * q + 3]));
+            for (int w = 0; w < FFT_FW; ++w) {
+                pw[w] = 1.f;
+                if (w < nw) {
+                    const ulonglong2* F = reinterpret_cast<const ulonglong2*>(fold[w][parity]);
+                    unsigned long long acc0 = 0ull, acc1 = 0ull, acc2 = 0ull, acc3 = 0ull;      // four chains of (re, im) partial sums
+#pragma unroll
+                    for (int q = 0; q < 24; q += 2) {
+                        const ulonglong2 f = F[q], g = F[q + 1];
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc0) : "l"(f.x), "l"(tw2[2 * q]));
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc1) : "l"(f.y), "l"(tw2[2 * q + 1]));
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2) : "l"(g.x), "l"(tw2[2 * q + 2]));
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc3) : "l"(g.y), "l"(tw2[2 * q + 3]));
+                    }
+                    {
+                        const ulonglong2 f = F[24], g = F[25];        // j = 48, 49, 50 (51 is padding)
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc0) : "l"(f.x), "l"(tw2[48]));
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc1) : "l"(f.y), "l"(tw2[49]));
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2) : "l"(g.x), "l"(tw2[50]));
+                    }
+                    const float re = (__uint_as_float((unsigned)acc0) + __uint_as_float((unsigned)acc1)) +
+                                     (__uint_as_float((unsigned)acc2) + __uint_as_float((unsigned)acc3));
+                    const float im = (__uint_as_float((unsigned)(acc0 >> 32)) + __uint_as_float((unsigned)(acc1 >> 32))) +
+                                     (__uint_as_float((unsigned)(acc2 >> 32)) + __uint_as_float((unsigned)(acc3 >> 32)));
+                    pw[w] = fmaf(re, re, im * im);                // log|X| = log(|X|^2) / 2
                 }
-                {
-                    const ulonglong2 f = F[24], g = F[25];        // j = 48, 49, 50 (51 is padding)
-                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc0) : "l"(f.x), "l"(tw2[48]));
-                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc1) : "l"(f.y), "l"(tw2[49]));
-                    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2) : "l"(g.x), "l"(tw2[50]));
-                }
-                const float re = (__uint_as_float((unsigned)acc0) + __uint_as_float((unsigned)acc1)) +
-                                 (__uint_as_float((unsigned)acc2) + __uint_as_float((unsigned)acc3));
-                const float im = (__uint_as_float((unsigned)(acc0 >> 32)) + __uint_as_float((unsigned)(acc1 >> 32))) +
-                                 (__uint_as_float((unsigned)(acc2 >> 32)) + __uint_as_float((unsigned)(acc3 >> 32)));
-                const float pw = fmaf(re, re, im * im);           // log|X| = log(|X|^2) / 2
-                outb[w][k] = pw == 0.0f ? -18.420680743952367f : 0.5f * logf(pw);      // data_utils.py:30: amp == 0 -> 1e-8
             }
+#pragma unroll
+            for (int w = 0; w < FFT_FW; ++w)
+                if (w < nw) outb[w][k] = pw[w] == 0.0f ? -18.420680743952367f : 0.5f * logf(pw[w]);      // data_utils.py:30: amp == 0 -> 1e-8
         }
         __syncthreads();
         // ---- coalesced stores: raw features, and augmented + standardised x ------------------------------------------
+        const long long dst0 = (((long long)b * p.T + t0) * p.N + n) * FFT_K, dstx0 = (((long long)b * p.T + t0) * p.N + no) * FFT_K;
+        const long long wstride = (long long)p.N * FFT_K;         // next window of the same channel
         for (int i = tid; i < nw * (FFT_K / 4); i += FFT_THREADS) {
             const int w = i / (FFT_K / 4), q = i - w * (FFT_K / 4);
-            const FftWin& wd = win[buf][w];
             float4 v = *reinterpret_cast<const float4*>(&outb[w][4 * q]);
-            if (p.raw) __stcs(reinterpret_cast<float4*>(p.raw + wd.dst) + q, v);
+            if (p.raw) __stcs(reinterpret_cast<float4*>(p.raw + dst0 + w * wstride) + q, v);
             if (p.x) {
-                if (p.log_scale) {
-                    const float ls = wd.ls;
-                    v.x += ls; v.y += ls; v.z += ls; v.w += ls;
-                }
-                if (p.stat_len > 0) {
-                    const float m = wd.m, sd = wd.sd;
-                    v.x = (v.x - m) / sd; v.y = (v.y - m) / sd; v.z = (v.z - m) / sd; v.w = (v.w - m) / sd;
-                }
-                __stcs(reinterpret_cast<float4*>(p.x + wd.dstx) + q, v);
+                if (p.log_scale) { v.x += ls; v.y += ls; v.z += ls; v.w += ls; }
+                if (p.stat_len > 0) { v.x = (v.x - mean) / sd; v.y = (v.y - mean) / sd; v.z = (v.z - mean) / sd; v.w = (v.w - mean) / sd; }
+                __stcs(reinterpret_cast<float4*>(p.x + dstx0 + w * wstride) + q, v);
             }
         }
     }
@@ -212,7 +206,7 @@ cudaError_t launch_fft_features(int B, int N, int T, const float* signal, long l
     if (e != cudaSuccess) return e;
     p.tw = tw;
     fft_twiddle_kernel<<<1, 256, 0, st>>>();
-    long long nbatch = (p.nwin + FFT_FW - 1) / FFT_FW;
+    long long nbatch = (long long)B * N * ((T + FFT_FW - 1) / FFT_FW);
     long long grid = (long long)nsms * 3;                        // persistent: 3 CTAs of 128 threads per SM (register-limited)
     if (grid > nbatch) grid = nbatch;
     fft_features_kernel<<<(unsigned)grid, FFT_THREADS, 0, st>>>(p);

@@ -77,6 +77,31 @@ const DevInfo& devinfo() {
     return d[dev];
 }
 
+// ---- side stream of the backward calls ---------------------------------------------------------------------------------
+// The bias gradient (column sums of the dA image) is independent of the dX and dW GEMMs that follow the recurrent BPTT
+// kernel, memory-bound and small: it is forked onto a library-owned non-blocking stream right after rnn_bwd and joined
+// before the call returns, so it shares the SMs (its CTAs fit next to bulk_dp / dw_mm16) and the spare HBM bandwidth with
+// them.  Plain event fork / join on the caller's stream: legal under CUDA-graph capture, no host synchronisation.  One
+// stream + two events per (host thread, device), created on first use and kept for the life of the process (the only
+// resources the library owns); DCGRU_SIDE_STREAM=0 and the per-kernel timing mode keep everything on the caller's stream.
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+static SideStream* side_stream() {
+    static thread_local SideStream tab[64];
+    { const char* e = getenv("DCGRU_SIDE_STREAM"); if (e && e[0] == '0') return nullptr; }
+    if (g_timing) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    SideStream& t = tab[dev];
+    if (!t.s) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        (void)cs;
+        if (cudaStreamCreateWithFlags(&t.s, cudaStreamNonBlocking) != cudaSuccess) { t.s = nullptr; return nullptr; }
+        if (cudaEventCreateWithFlags(&t.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&t.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    return (t.fork && t.join) ? &t : nullptr;
+}
+
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 int check_desc(const dcgru_cell_desc* d) {
@@ -661,6 +686,18 @@ static int encoder_layer_bwd_impl(const dcgru_cell_desc* d, int32_t batch, int32
                                                d_hsel, d_hsel ? nh : 0, reinterpret_cast<unsigned*>(scale + 8), scale, st));
         LAUNCH("rnn_bwd", launch_rnn_bwd(batch, seq_len, N, fin, M, d->activation, h0, h_seq, ruc, P, w->Wg, w->Wc, d_hseq,
                                          d_hlast, d_hsel, sel_t, wsb + ws.off_wb, scale, dh0, wsb + ws.off_img, st));
+        SideStream* side = gsave ? side_stream() : nullptr;
+        if (side) {
+            // db on the side stream, concurrent with the dX / dW GEMMs below (joined before the call returns)
+            CUDA_TRY(cudaEventRecord(side->fork, st));
+            CUDA_TRY(cudaStreamWaitEvent(side->s, side->fork, 0));
+            {
+                cudaStream_t st = side->s;                                  // (LAUNCH times and launches on `st`)
+                LAUNCH("colsum16", launch_colsum16(wsb + ws.off_img, batch, seq_len, H, reinterpret_cast<float*>(wsb + ws.off_cs), scale,
+                                                   g->dbg, g->dbc, st));
+            }
+            CUDA_TRY(cudaEventRecord(side->join, side->s));
+        }
         if (dx) {
             LAUNCH("pack_w16", launch_pack_w16(w->Wg, w->Wc, fin, H, M, 1, fin, g16_nq(3 * H, M), wsb + ws.off_wdx, st));
             LAUNCH("dx16", launch_bulk_dp(batch, seq_len, N, 3 * H, M, fin, 1, nullptr, 0, 0, wsb + ws.off_img, P, wsb + ws.off_wdx,
@@ -671,8 +708,10 @@ static int encoder_layer_bwd_impl(const dcgru_cell_desc* d, int32_t batch, int32
             // weight gradient: GEMM over the two fp16 operand images; bias gradient: column sums of the dA image
             LAUNCH("dw_mm16", launch_dw_mm16(fin, H, M, batch, seq_len, gsave, wsb + ws.off_img, reinterpret_cast<float*>(wsb + ws.off_part),
                                              scale, di.sms, g->dWg, g->dWc, st));
-            LAUNCH("colsum16", launch_colsum16(wsb + ws.off_img, batch, seq_len, H, reinterpret_cast<float*>(wsb + ws.off_cs), scale,
-                                               g->dbg, g->dbc, st));
+            if (side) CUDA_TRY(cudaStreamWaitEvent(st, side->join, 0));
+            else
+                LAUNCH("colsum16", launch_colsum16(wsb + ws.off_img, batch, seq_len, H, reinterpret_cast<float*>(wsb + ws.off_cs), scale,
+                                                   g->dbg, g->dbc, st));
             return 0;
         }
         // no operand image: bridge to the first-generation (recompute) weight-gradient kernels through a row-major fp32 dA

@@ -12,10 +12,11 @@
 //              Im = -sum_{0<j<50} (d_j - d_{100-j}) sin(pi j k / 100)
 //     odd  k:  Re = sum_{j<50} (a_j - a_{100-j}) cos(pi j k / 100)
 //              Im = -[ sum_{0<j<50} (d_j + d_{100-j}) sin(pi j k / 100) + d_50 sin(pi k / 2) ]
-// = 51 packed (re, im) FMAs (fma.rn.f32x2) per bin instead of 400 scalar ones.  Thread = one bin k, its 51 (cos, sin)
-// twiddle pairs live in registers for the whole kernel;
+// = 51 packed (re, im) FMAs (fma.rn.f32x2) instead of 400 scalar ones -- and they serve two bins: the twiddles of bin
+// 100 - k are those of bin k times (-1)^j, so sums split by the parity of j give both.  Thread = bin k (and its mirror), its
+// 51 (cos, sin) twiddle pairs live in registers for the whole kernel;
 // a warp holds bins of one parity, so every folded (C_j, S_j) pair it needs comes from a broadcast LDS.128 for all 32 lanes.  A CTA
-// (128 threads: warps 0-1 even bins, 2-3 odd bins) is persistent over items = (channel of a clip, 16 consecutive windows):
+// (128 threads: warp = (bin parity, half of the windows)) is persistent over items = (channel of a clip, 16 consecutive windows):
 // one cp.async.bulk fetches the next item's samples (12.8 KB, mbarrier) while this one is transformed ->
 // fold into shared memory -> 51 packed FMAs per (bin, window) -> log amplitude -> shared -> coalesced stores with the
 // augmentation and the scaler applied on the way out.  fp32 arithmetic on fp32 samples (the sums have 51 terms; measured
@@ -60,14 +61,18 @@ __global__ void __launch_bounds__(FFT_THREADS, 3) fft_features_kernel(const FftP
     __shared__ __align__(16) float outb[FFT_FW][FFT_K];
     __shared__ uint64_t bar_raw[2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int parity = warp >> 1;                                 // warps 0-1: even bins, 2-3: odd bins
-    const int kidx = (warp & 1) * 32 + lane;                      // 0..63, 50 used
-    const bool kvalid = kidx < FFT_K / 2;
-    const int k = kvalid ? 2 * kidx + parity : parity;
+    // warp = (bin parity, window half).  A lane owns bin k AND its mirror 100 - k: the mirror's twiddles are the same up to
+    // (-1)^j, so splitting the sums by the parity of j yields both bins from one set of FMAs (and one set of loads)
+    const int parity = warp & 1;                                  // even / odd bins
+    const int team = warp >> 1;                                   // windows [8 team, 8 team + 8)
+    const int k = 2 * lane + parity;                              // even: 0..50 (lanes 0..25), odd: 1..49 (lanes 0..24)
+    const bool kvalid = k <= 50;
+    const int kmir = 100 - k;
+    const bool mvalid = kvalid && kmir > 50 && kmir < 100;        // k = 0 and k = 50 have no mirror among the 100 bins kept
     unsigned long long tw2[51];                                   // (cos, sin)(pi j k / 100) as packed pairs
 #pragma unroll
     for (int j = 0; j <= 50; ++j) {
-        const int m = (j * k) % 200;
+        const int m = (j * (kvalid ? k : 0)) % 200;
         tw2[j] = pack2(p.tw[m], p.tw[200 + m]);
     }
     if (tid == 0) {
@@ -132,37 +137,45 @@ __global__ void __launch_bounds__(FFT_THREADS, 3) fft_features_kernel(const FftP
         // ---- 51 packed FMAs per (bin, window): (re, im) += (C_j, S_j) * (cos, sin); folded values are warp-wide broadcasts.
         //      Unrolled over the windows so that the loads of window w+1 and the logarithm of window w-1 overlap the FMAs of w.
         if (kvalid) {
-            float pw[FFT_FW];
+            float pw[FFT_FW / 2], pm[FFT_FW / 2];
 #pragma unroll
-            for (int w = 0; w < FFT_FW; ++w) {
-                pw[w] = 1.f;
+            for (int wi = 0; wi < FFT_FW / 2; ++wi) {
+                const int w = team * (FFT_FW / 2) + wi;
+                pw[wi] = 1.f; pm[wi] = 1.f;
                 if (w < nw) {
                     const ulonglong2* F = reinterpret_cast<const ulonglong2*>(fold[w][parity]);
-                    unsigned long long acc0 = 0ull, acc1 = 0ull, acc2 = 0ull, acc3 = 0ull;      // four chains of (re, im) partial sums
+                    unsigned long long e0 = 0ull, e1 = 0ull, o0 = 0ull, o1 = 0ull;      // (re, im) sums over even / odd j, two chains each
 #pragma unroll
                     for (int q = 0; q < 24; q += 2) {
-                        const ulonglong2 f = F[q], g = F[q + 1];
-                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc0) : "l"(f.x), "l"(tw2[2 * q]));
-                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc1) : "l"(f.y), "l"(tw2[2 * q + 1]));
-                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2) : "l"(g.x), "l"(tw2[2 * q + 2]));
-                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc3) : "l"(g.y), "l"(tw2[2 * q + 3]));
+                        const ulonglong2 f = F[q], g = F[q + 1];                         // j = 2q, 2q+1 | 2q+2, 2q+3
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(e0) : "l"(f.x), "l"(tw2[2 * q]));
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(o0) : "l"(f.y), "l"(tw2[2 * q + 1]));
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(e1) : "l"(g.x), "l"(tw2[2 * q + 2]));
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(o1) : "l"(g.y), "l"(tw2[2 * q + 3]));
                     }
                     {
                         const ulonglong2 f = F[24], g = F[25];        // j = 48, 49, 50 (51 is padding)
-                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc0) : "l"(f.x), "l"(tw2[48]));
-                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc1) : "l"(f.y), "l"(tw2[49]));
-                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2) : "l"(g.x), "l"(tw2[50]));
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(e0) : "l"(f.x), "l"(tw2[48]));
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(o0) : "l"(f.y), "l"(tw2[49]));
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(e1) : "l"(g.x), "l"(tw2[50]));
                     }
-                    const float re = (__uint_as_float((unsigned)acc0) + __uint_as_float((unsigned)acc1)) +
-                                     (__uint_as_float((unsigned)acc2) + __uint_as_float((unsigned)acc3));
-                    const float im = (__uint_as_float((unsigned)(acc0 >> 32)) + __uint_as_float((unsigned)(acc1 >> 32))) +
-                                     (__uint_as_float((unsigned)(acc2 >> 32)) + __uint_as_float((unsigned)(acc3 >> 32)));
-                    pw[w] = fmaf(re, re, im * im);                // log|X| = log(|X|^2) / 2
+                    const float ere = __uint_as_float((unsigned)e0) + __uint_as_float((unsigned)e1);
+                    const float eim = __uint_as_float((unsigned)(e0 >> 32)) + __uint_as_float((unsigned)(e1 >> 32));
+                    const float ore = __uint_as_float((unsigned)o0) + __uint_as_float((unsigned)o1);
+                    const float oim = __uint_as_float((unsigned)(o0 >> 32)) + __uint_as_float((unsigned)(o1 >> 32));
+                    const float re = ere + ore, im = eim + oim, rm = ere - ore, imm = eim - oim;
+                    pw[wi] = fmaf(re, re, im * im);               // |X_k|^2;  log|X| = log(|X|^2) / 2
+                    pm[wi] = fmaf(rm, rm, imm * imm);             // |X_{100-k}|^2
                 }
             }
 #pragma unroll
-            for (int w = 0; w < FFT_FW; ++w)
-                if (w < nw) outb[w][k] = pw[w] == 0.0f ? -18.420680743952367f : 0.5f * logf(pw[w]);      // data_utils.py:30: amp == 0 -> 1e-8
+            for (int wi = 0; wi < FFT_FW / 2; ++wi) {
+                const int w = team * (FFT_FW / 2) + wi;
+                if (w < nw) {
+                    outb[w][k < FFT_K ? k : 0] = pw[wi] == 0.0f ? -18.420680743952367f : 0.5f * logf(pw[wi]);      // data_utils.py:30: amp == 0 -> 1e-8
+                    if (mvalid) outb[w][kmir] = pm[wi] == 0.0f ? -18.420680743952367f : 0.5f * logf(pm[wi]);
+                }
+            }
         }
         __syncthreads();
         // ---- coalesced stores: raw features, and augmented + standardised x ------------------------------------------

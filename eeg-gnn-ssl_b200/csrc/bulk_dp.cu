@@ -48,6 +48,7 @@ struct BulkParams {
     const float* scale_ptr;               // optional device scalar: out *= 1 / *scale_ptr (gradient scaling, rnn_bwd.cu)
     const float* in_scale_ptr;            // optional device scalar: the fp32 source is multiplied by it before the hi/lo split
     int dump, img_col0;
+    int mma_diff;                         // chunks inside one term: diffusion on mma.sync (Cin % 64 == 0, DCGRU_MMA_DIFF_BULK=1; default: FMA loop)
     int off_w, off_x, off_pt, off_id;     // shared-memory offsets
 };
 
@@ -257,6 +258,21 @@ __global__ void __launch_bounds__(BK_THREADS, 1) bulk_dp_kernel(const BulkParams
                 const float* z = XT + s * srow + c;
                 const __half* zh = X16 + (s * (RG * 8)) * Cin + c;                  // image rows s*24 + n
                 const __half* zl = zh + IMG_ROWS * Cin;
+                // a chunk that lies inside one diffusion term (Cin % 64 == 0: layers >= 1, dX) goes through the warp-level tensor
+                // path like the recurrent kernels: polynomial fragments in registers, the source read once (f16_common.cuh)
+                const bool svalid = (tile * SB + s) < p.B;
+                if (p.mma_diff && svalid && 64 * q >= Cin && 64 * q + 64 <= kkmax) {
+                    const int mq = (64 * q) / Cin, c0 = 64 * q - mq * Cin;
+                    PFrag pf;
+                    load_pfrag(PTs + (s * (M - 1) + (mq - 1)) * PT_STRIDE, lane, pf);
+                    if (src16) diffuse_mma16_rm(X16 + (s * (RG * 8)) * Cin + c0, (uint32_t)(Cin * 2), (uint32_t)(IMG_ROWS * Cin * 2), pf, sl,
+                                                s * RP, lane, iscale);
+                    else diffuse_mma(XT + s * srow + c0, Cin, N, pf, sl, s * RP, lane, iscale);
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bar_afull[q]);
+                    continue;
+                }
                 float acc[NPAD][2];
                 if (__all_sync(0xffffffffu, m == 0)) {          // identity term (or padding): plain copy
 #pragma unroll
@@ -389,6 +405,9 @@ cudaError_t launch_bulk_dp(int B, int T, int N, int Cin, int M, int Nout, int tr
     p.src = src; p.ss_t = ss_t; p.ss_b = ss_b; p.P = P; p.wimg = reinterpret_cast<const uint8_t*>(wimg); p.bias = bias;
     p.out = out; p.os_t = os_t; p.os_b = os_b; p.out_ld = out_ld; p.out_scale = out_scale; p.scale_ptr = scale_ptr;
     p.dump = img != nullptr; p.img_col0 = img_col0;
+    // measured at config 2 (B200): no gain for the x pre-projection (1.14 ms either way) and dX 0.78 -> 0.84 ms (the row-major
+    // image tile makes the ldmatrix loads 8-way bank-conflicted), so the FMA loop stays the default here
+    { const char* e = getenv("DCGRU_MMA_DIFF_BULK"); p.mma_diff = (Cin % 64 == 0) && e && e[0] == '1'; }
     p.nout_valid = Nout; p.img_T = T; p.img_t0 = 0; p.src_T = T; p.src_t0 = 0;
     if (ex) {
         if (ex->nout_valid > 0) p.nout_valid = ex->nout_valid;

@@ -342,20 +342,21 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t sad
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];\n"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr) : "memory");
 }
-// Column groups [grp0, grp1) of 16 columns each are processed (the whole chunk = [0, 4)).
-__device__ __forceinline__ void diffuse_mma16(const uint8_t* src, int srow0, const PFrag& pf, uint8_t* slot, int row0, int lane,
-                                              float scale, int grp0 = 0, int grp1 = 4) {
+// Core: `addr(grp, nt)` = shared-memory address of this lane's source row (row index = lane), 16-byte unit holding columns
+// [16 grp + 8 nt, +8) of the hi plane; the lo plane lies lo_off bytes further.  Column groups [grp0, grp1) of 16 columns
+// each are processed (a whole 64-column chunk = [0, 4)).
+template <typename AddrF>
+__device__ __forceinline__ void diffuse_mma16_core(AddrF addr, uint32_t lo_off, const PFrag& pf, uint8_t* slot, int row0, int lane,
+                                                   float scale, int grp0, int grp1) {
     const int g = lane >> 2, t = lane & 3;
-    const int sr = srow0 + lane;                                        // lane i supplies the address of source row i
-    const uint32_t rbase = smem_u32(src) + (uint32_t)((sr >> 3) * 1024 + (sr & 7) * 128);
 #pragma unroll 1
     for (int grp = grp0; grp < grp1; ++grp) {
         uint32_t bh[2][4], bl[2][4];                                    // [n tile][kt0.b0, kt0.b1, kt1.b0, kt1.b1]
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
-            const uint32_t a = rbase + (uint32_t)((((2 * grp + nt) ^ (sr & 7)) << 4));
+            const uint32_t a = addr(grp, nt);
             ldmatrix_x4_trans(bh[nt], a);
-            ldmatrix_x4_trans(bl[nt], a + PLANE);
+            ldmatrix_x4_trans(bl[nt], a + lo_off);
         }
         float d[2][2][4];
 #pragma unroll
@@ -414,6 +415,24 @@ __device__ __forceinline__ void diffuse_mma16(const uint8_t* src, int srow0, con
                 }
             }
     }
+}
+
+// source = a K-major SWIZZLE_128B chunk slot (hi plane, lo plane PLANE further); srow0 = the sample's first tile row
+__device__ __forceinline__ void diffuse_mma16(const uint8_t* src, int srow0, const PFrag& pf, uint8_t* slot, int row0, int lane,
+                                              float scale, int grp0 = 0, int grp1 = 4) {
+    const int sr = srow0 + lane;                                        // lane i supplies the address of source row i
+    const uint32_t rbase = smem_u32(src) + (uint32_t)((sr >> 3) * 1024 + (sr & 7) * 128);
+    diffuse_mma16_core([&](int grp, int nt) { return rbase + (uint32_t)((((2 * grp + nt) ^ (sr & 7)) << 4)); }, (uint32_t)PLANE, pf,
+                       slot, row0, lane, scale, grp0, grp1);
+}
+// source = row-major fp16 planes (an operand-image slab copied to shared memory as it lies in HBM): hi points at (the sample's
+// first row, first column of the chunk), rows ld_bytes apart, the lo plane lo_off bytes further.  Rows 24..31 of the lane
+// addresses only have to be readable.  (Eight rows at a 128-byte-multiple stride share their banks: the loads are 8-way
+// conflicted, ~100 cycles per group against ~800 of MMA work.)
+__device__ __forceinline__ void diffuse_mma16_rm(const __half* hi, uint32_t ld_bytes, uint32_t lo_off, const PFrag& pf, uint8_t* slot,
+                                                 int row0, int lane, float scale) {
+    const uint32_t rbase = smem_u32(hi) + (uint32_t)lane * ld_bytes;
+    diffuse_mma16_core([&](int grp, int nt) { return rbase + (uint32_t)((2 * grp + nt) << 4); }, lo_off, pf, slot, row0, lane, scale, 0, 4);
 }
 
 // transposed polynomials of one tile into shared memory: PT[(s * nterm + m) * PT_STRIDE + j * NPAD + n]

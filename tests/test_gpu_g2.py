@@ -99,3 +99,54 @@ def test_dx_bulk(dev, B, T, fin, M):
     for m in range(1, M):
         ref += torch.einsum("bjn,tbjc->tbnc", P[:, m - 1].double(), dG[m])            # P^T
     assert _rel(out, ref) < 5e-6
+
+
+def test_side_stream_bias_gradient_identical_and_capturable(dev, monkeypatch):
+    """The bias gradient runs on the library's side stream next to the dX / dW GEMMs (capi.cu::side_stream): same bits as
+    on the caller's stream (DCGRU_SIDE_STREAM=0), also when the whole step is captured in a CUDA graph and replayed."""
+    import types
+    from eeg_gnn_ssl_b200.model.model import DCRNNModel_classification
+    torch.manual_seed(11)
+    args = types.SimpleNamespace(num_nodes=N, num_rnn_layers=2, rnn_units=64, input_dim=100, output_dim=100,
+                                 max_diffusion_step=2, dcgru_activation="tanh", filter_type="laplacian", dropout=0.0,
+                                 cl_decay_steps=3000, use_curriculum_learning=False)
+    model = DCRNNModel_classification(args, 1).to(dev)
+    B, T = 10, 6
+    x = torch.randn(B, T, N, 100, device=dev)
+    sl = torch.full((B,), T, device=dev)
+    sup = [torch.softmax(torch.randn(B, N, N, device=dev), -1)]
+
+    def grads():
+        model.zero_grad(set_to_none=True)
+        model(x, sl, sup).square().mean().backward()
+        torch.cuda.synchronize()
+        return [p.grad.clone() for p in model.parameters()]
+
+    monkeypatch.setenv("DCGRU_SIDE_STREAM", "0")
+    ref = grads()
+    monkeypatch.setenv("DCGRU_SIDE_STREAM", "1")
+    for a, b in zip(grads(), ref):
+        assert torch.equal(a, b)
+    # captured: the fork / join must be part of the graph (a side stream left outside would make the capture fail or the
+    # replay read stale bias gradients)
+    for p in model.parameters():
+        p.grad = torch.zeros_like(p)
+    stream = torch.cuda.Stream()
+    stream.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(stream):
+        for _ in range(2):
+            for p in model.parameters():
+                p.grad.zero_()
+            model(x, sl, sup).square().mean().backward()
+    torch.cuda.current_stream().wait_stream(stream)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for p in model.parameters():
+            p.grad.zero_()
+        model(x, sl, sup).square().mean().backward()
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    for p, b in zip(model.parameters(), ref):
+        assert torch.equal(p.grad, b)

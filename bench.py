@@ -580,8 +580,8 @@ def main():
 
     peaks = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json"), {})
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
-    prof = load_json(os.path.join(ROOT, "profiles", "traffic_r02.json")) or \
-        load_json(os.path.join(ROOT, "profiles", "traffic_r01.json"), {})
+    prof = load_json(os.path.join(ROOT, "profiles", "traffic_r02b.json")) or \
+        load_json(os.path.join(ROOT, "profiles", "traffic_r02.json"), {})
 
     with ClockSampler(local) as clk:
         w = Workload(cfg, dev, rank, world)
@@ -612,7 +612,7 @@ def main():
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback",
                 "frac_of_split_attainable": achieved / (peak / 3.0),
                 "tensor_pipe_active_pct": tensor_pct,
-                "profile_source": "profiles/ncu_*_r02.txt (ncu --set full --clock-control none on `bench.py --config 2 --steps 2 "
+                "profile_source": "profiles/ncu_*_r02b.txt (ncu --set full --clock-control none on `bench.py --config 2 --steps 2 "
                                   "--no-extra --no-cpu-baseline`; see profiles/README.md for commit and command)",
                 "note": "kernels compute in fp32-equivalent 2xFP16 on tcgen05 (3 kind::f16 MMAs per product at the bf16 rate: "
                         "the attainable peak of this arithmetic is 1/3 of the bf16 peak); FLOPs are the as-written count of "

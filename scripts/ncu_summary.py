@@ -2,7 +2,8 @@
 and the per-launch DRAM traffic table bench.py reports as roofline.traffic.   usage: python scripts/ncu_summary.py r01c"""
 import csv, json, subprocess, sys
 tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
-KERNELS = {"rnn_fwd": "rnn_fwd_kernel", "rnn_bwd": "rnn_bwd_kernel", "dw_mm16": "dw_mm16_kernel", "xproj": "bulk_dp_kernel"}
+KERNELS = {"rnn_fwd": "rnn_fwd_kernel", "rnn_bwd": "rnn_bwd_kernel", "dw_mm16": "dw_mm16_kernel", "xproj": "bulk_dp_kernel",
+           "fft_features": "fft_features_kernel"}
 COMMIT = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
 WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "launch__shared_mem_per_block_dynamic", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -19,12 +20,17 @@ UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
 traffic = {}
 for short, kern in KERNELS.items():
     rep = f"gpurun_out/full_{kern}.ncu-rep"
+    import os
+    if not os.path.exists(rep):
+        continue
+    fft = short == "fft_features"
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, vals = rows[0], rows[1], rows[2]
-    out = [f"# ncu --set full ({tag}, commit {COMMIT}): {kern}, first launch after warm-up = encoder layer 0 at BASELINE config 2 (B=512, T=60)",
-           f"# command: ncu --set full --clock-control none --import-source on -k regex:{kern} -s 4 -c 1 "
-           "python bench.py --config 2 --steps 2 --no-extra --no-cpu-baseline", ""]
+    out = [f"# ncu --set full ({tag}, commit {COMMIT}): {kern}, " + ("BASELINE config 2 batch (B=512, T=60: 583 680 windows), x + raw outputs" if fft else
+           "first launch after warm-up = encoder layer 0 at BASELINE config 2 (B=512, T=60)"),
+           f"# command: ncu --set full --clock-control none --import-source on -k regex:{kern} -s 4 -c 1 " +
+           ("python scripts/run_fft.py" if fft else "python bench.py --config 2 --steps 2 --no-extra --no-cpu-baseline"), ""]
     for w in WANT:
         if w in hdr:
             i = hdr.index(w)

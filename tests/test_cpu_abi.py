@@ -50,6 +50,16 @@ def test_argument_validation_reports_errors():
     assert rc != 0 and b"null" in L.dcgru_last_error()
     # no device here: the tensor-core operand image is not offered (0 bytes), nothing is emulated
     assert L.dcgru_encoder_layer_gsave_bytes(C.byref(ok), 512, 60) == 0
+    # input-feature kernel (N2): window length, statistics length, alignment are checked before anything is launched
+    one = C.c_void_p(16)                                    # non-null, 16-byte aligned dummy pointers: never dereferenced
+    assert L.dcgru_fft_features(2, 19, 4, 256, one, 19 * 1024, 1024, None, None, None, None, 0, None, one, None) != 0
+    assert b"window" in L.dcgru_last_error()
+    assert L.dcgru_fft_features(2, 19, 4, 200, one, 19 * 800, 800, None, None, one, one, 3, None, one, None) != 0
+    assert b"stat_len" in L.dcgru_last_error()
+    assert L.dcgru_fft_features(2, 19, 4, 200, one, 19 * 802, 802, None, None, None, None, 0, None, one, None) != 0
+    assert b"aligned" in L.dcgru_last_error()
+    assert L.dcgru_fft_features(2, 19, 4, 200, one, 19 * 800, 800, None, None, None, None, 0, None, None, None) != 0
+    assert b"no output" in L.dcgru_last_error()
 
 
 def test_cpu_tensors_are_rejected_not_emulated():

@@ -9,13 +9,14 @@
 // Work item = (tile of 4 samples, t); a persistent CTA owns a contiguous range of items (so the tile's polynomials
 // are reloaded only when the tile changes).  Per item the K dimension is cut into chunks of 64 (f16_common.cuh); the
 // K order is term-major, kk = m * Cin + c, so a chunk is a column range of at most two terms.
-//   warps 0-7  workers: one warp per (sample, chunk) task -- fp32 diffusion, hi/lo split, write the A chunk
-//                       (3-slot ring); afterwards the epilogue of the PREVIOUS item (TMEM -> bias/scale -> global),
-//                       so the MMAs of an item have a whole item's worth of diffusion time to finish
+//   warps 0-7  workers: one warp per (sample, chunk) task -- fp32 diffusion, hi/lo split, write the A chunk (3-slot ring)
 //   warp 8     MMA issuer (one thread): per chunk 3 x 4 kind::f16 MMAs into one of two TMEM accumulators
 //   warp 9     loader (one thread): source tile (one bulk copy per sample) and the weight pieces (hi / lo plane of
 //                       a chunk, pre-swizzled by pack_w16_kernel) from L2 into a ring, cp.async.bulk + mbarrier
 //   warp 10    operand-image dump: one 2-D tensor-map TMA store per (plane, sample) and chunk
+//   warps 11-14 epilogue of the PREVIOUS item while the workers diffuse the next one: TMEM -> scale / bias -> warp-private
+//                       staging tile -> whole 128-byte row pieces in global memory (thread = row stores cost 32 sectors per
+//                       instruction and shared the LSU with the workers' diffusion loads)
 #include <cstdlib>
 #include <cstring>
 
@@ -29,7 +30,9 @@ using namespace f16;
 
 constexpr int BK_NS = 3;                  // A chunk slots
 constexpr int BK_MAXQ = 16;               // chunks per item (M * Cin <= 1024)
-constexpr int BK_THREADS = 352;
+constexpr int BK_THREADS = 480;
+constexpr int BK_STG_LD = 36;                // staging tile row stride (floats)
+constexpr int BK_STG = 32 * BK_STG_LD * 4;     // one warp-private staging tile: 32 rows x 32 columns
 constexpr int BK_NWORK = 256;
 
 struct BulkParams {
@@ -49,12 +52,15 @@ struct BulkParams {
     const float* in_scale_ptr;            // optional device scalar: the fp32 source is multiplied by it before the hi/lo split
     int dump, img_col0;
     int mma_diff;                         // chunks inside one term: diffusion on mma.sync (Cin % 64 == 0, DCGRU_MMA_DIFF_BULK=1; default: FMA loop)
-    int off_w, off_x, off_pt, off_id;     // shared-memory offsets
+    int off_w, off_x, off_pt, off_id, off_stg;     // shared-memory offsets
 };
 
 __device__ __forceinline__ void named_bar_workers() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 
-__global__ void __launch_bounds__(BK_THREADS, 1) bulk_dp_kernel(const BulkParams p, const __grid_constant__ CUtensorMap tm_img) {
+// EPIW: the epilogue runs on four dedicated warps (480 threads, 128 registers) instead of on the workers (352 threads)
+template <bool EPIW>
+__global__ void __launch_bounds__(EPIW ? BK_THREADS : BK_THREADS - 128, 1) bulk_dp_kernel(const BulkParams p, const __grid_constant__ CUtensorMap tm_img) {
+    constexpr int NTHREADS = EPIW ? BK_THREADS : BK_THREADS - 128;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     __shared__ uint64_t bar_afull[BK_MAXQ], bar_aempty[BK_NS], bar_stored[BK_NS], bar_wfull[8], bar_wempty[8];
@@ -83,14 +89,14 @@ __global__ void __launch_bounds__(BK_THREADS, 1) bulk_dp_kernel(const BulkParams
         for (int i = 0; i < 8; ++i) { mbar_init(&bar_wfull[i], 1); mbar_init(&bar_wempty[i], 1); }
         mbar_init(&bar_xfull, 1);
         mbar_init(&bar_xfree, BK_NWORK / 32);
-        for (int i = 0; i < 2; ++i) { mbar_init(&bar_accfull[i], 1); mbar_init(&bar_accfree[i], BK_NWORK / 32); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bar_accfull[i], 1); mbar_init(&bar_accfree[i], EPIW ? 4 : BK_NWORK / 32); }
         mbar_fence_init();
     }
     // chunk slots, source tile and polynomial blocks start as zeros: pad rows / pad nodes are never written again
-    for (int i = tid; i < BK_NS * SLOT / 16; i += BK_THREADS) reinterpret_cast<uint4*>(Aslots)[i] = make_uint4(0, 0, 0, 0);
-    if (!src16) for (int i = tid; i < SB * srow; i += BK_THREADS) XT[i] = 0.f;
-    for (int i = tid; i < SB * (M - 1) * PT_STRIDE; i += BK_THREADS) PTs[i] = 0.f;
-    for (int i = tid; i < PT_STRIDE; i += BK_THREADS) PTid[i] = (i / NPAD == i % NPAD) ? 1.f : 0.f;
+    for (int i = tid; i < BK_NS * SLOT / 16; i += NTHREADS) reinterpret_cast<uint4*>(Aslots)[i] = make_uint4(0, 0, 0, 0);
+    if (!src16) for (int i = tid; i < SB * srow; i += NTHREADS) XT[i] = 0.f;
+    for (int i = tid; i < SB * (M - 1) * PT_STRIDE; i += NTHREADS) PTs[i] = 0.f;
+    for (int i = tid; i < PT_STRIDE; i += NTHREADS) PTid[i] = (i / NPAD == i % NPAD) ? 1.f : 0.f;
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -188,14 +194,59 @@ __global__ void __launch_bounds__(BK_THREADS, 1) bulk_dp_kernel(const BulkParams
             bulk_wait_all();
         }
         __syncwarp();
+    } else if (EPIW && warp >= 11) {
+        // =================================== epilogue warps: thread = row =================================================
+        const int quad = warp & 3, row = 32 * quad + lane;              // TMEM lane quadrant = warp % 4
+        float* stg = reinterpret_cast<float*>(smem + p.off_stg + (warp - 11) * BK_STG);
+        const int rq = lane >> 3, f4 = lane & 7;
+        float oscale = p.out_scale;
+        if (p.scale_ptr) oscale *= 1.f / __ldg(p.scale_ptr);
+        const uint32_t tb = taddr + ((uint32_t)(32 * quad) << 16);
+        for (int k = 0; k < nloc; ++k) {
+            const long it = it0 + k;
+            const int tile = (int)(it / p.T), t = (int)(it - (long)tile * p.T);
+            const int acc_i = k & 1;
+            const int b = tile * SB + quad;                             // this warp's sample
+            mbar_wait(&bar_accfull[acc_i], (k >> 1) & 1);
+            tc_fence_after();
+            float* obase = p.out + (size_t)t * p.os_t + (size_t)(b < p.B ? b : 0) * p.os_b;
+            for (int cb = 0; cb < p.Nout; cb += 32) {
+                float v[32];
+                tmem_ld32(tb + acc_i * 256 + cb, v);
+                if (cb >= p.nout_valid) continue;
+                __syncwarp();
+                float4* d = reinterpret_cast<float4*>(stg + lane * BK_STG_LD);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 bq = *reinterpret_cast<const float4*>(sbias + cb + 4 * j);
+                    d[j] = make_float4(fmaf(v[4 * j], oscale, bq.x), fmaf(v[4 * j + 1], oscale, bq.y), fmaf(v[4 * j + 2], oscale, bq.z),
+                                       fmaf(v[4 * j + 3], oscale, bq.w));
+                }
+                __syncwarp();
+                if (b < p.B && cb + 4 * f4 < p.nout_valid) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int n = rq + 4 * i;
+                        if (n < N)
+                            *reinterpret_cast<float4*>(obase + (size_t)n * p.out_ld + cb + 4 * f4) =
+                                *reinterpret_cast<const float4*>(stg + n * BK_STG_LD + 4 * f4);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_accfree[acc_i]);
+        }
     } else {
         // =================================== workers =====================================================================
         const int row = 32 * (warp & 3) + lane, half = warp >> 2;
-        const int es = row >> 5, en = row & 31;                 // epilogue: sample / node of this thread's row
+        const int es = row >> 5, en = row & 31;                 // (!EPIW) epilogue: sample / node of this thread's row
         const int ncol = p.Nout / 2;                            // columns per thread in the epilogue
         float oscale = p.out_scale;
         if (p.scale_ptr) oscale *= 1.f / __ldg(p.scale_ptr);
         const float iscale = p.in_scale_ptr ? __ldg(p.in_scale_ptr) : 1.f;
+        // epilogue on the workers (!EPIW): after the tasks of item k, the accumulator of item k-1 (so its MMAs had a whole item's
+        // worth of diffusion time to finish): TMEM -> scale / bias -> global, thread = (row, column half)
         auto epilogue = [&](int k) {
             const long it = it0 + k;
             const int tile = (int)(it / p.T), t = (int)(it - (long)tile * p.T);
@@ -297,9 +348,9 @@ __global__ void __launch_bounds__(BK_THREADS, 1) bulk_dp_kernel(const BulkParams
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_xfree);
-            if (k >= 1) epilogue(k - 1);
+            if (!EPIW && k >= 1) epilogue(k - 1);
         }
-        if (nloc > 0) epilogue(nloc - 1);
+        if (!EPIW && nloc > 0) epilogue(nloc - 1);
     }
     tc_fence_before();
     __syncthreads();
@@ -368,7 +419,8 @@ int g16_ntile(int B) { return (B + SB - 1) / SB; }
 size_t g16_image_bytes(int B, int T, int cols) { return (size_t)g16_ntile(B) * T * 2 * IMG_ROWS * cols * 2; }
 size_t bulk_wimg_bytes(int cin, int M, int nout) { return (size_t)g16_nq(cin, M) * 2 * nout * 128; }
 
-static bool bulk_layout(int N, int Cin, int M, int Nout, int smem_limit, bool src16, BulkParams* p) {
+// epiw: room for the four staging tiles of the epilogue warps
+static bool bulk_layout(int N, int Cin, int M, int Nout, int smem_limit, bool src16, BulkParams* p, bool epiw = false) {
     p->piece_bytes = Nout * 128;
     const int xbytes = (((src16 ? 2 * IMG_ROWS * Cin * 2 : SB * N * Cin * 4) + 1023) / 1024) * 1024;
     const int ptbytes = ((SB * (M - 1) * PT_STRIDE * 4 + 15) / 16) * 16;
@@ -378,11 +430,12 @@ static bool bulk_layout(int N, int Cin, int M, int Nout, int smem_limit, bool sr
         p->off_x = off; off += xbytes;
         p->off_pt = off; off += ptbytes;
         p->off_id = off; off += PT_STRIDE * 4;
+        p->off_stg = off; off += epiw ? 4 * BK_STG : 0;
         if (off + 1024 + 1024 <= smem_limit) { p->NW = nw; return true; }      // + alignment slack + static shared memory
     }
     return false;
 }
-static int bulk_smem(const BulkParams& p) { return p.off_id + PT_STRIDE * 4 + 1024; }
+static int bulk_smem(const BulkParams& p, bool epiw) { return p.off_stg + (epiw ? 4 * BK_STG : 0) + 1024; }
 
 bool bulk_dp_supported(int N, int Cin, int M, int Nout, bool src16, int smem_limit) {
     BulkParams p;
@@ -398,7 +451,13 @@ cudaError_t launch_bulk_dp(int B, int T, int N, int Cin, int M, int Nout, int tr
                            int img_col0, int nsms, int smem_limit, cudaStream_t st, const BulkExtra* ex) {
     BulkParams p;
     memset(&p, 0, sizeof p);
-    if (!bulk_layout(N, Cin, M, Nout, smem_limit, src16 != nullptr, &p)) return cudaErrorInvalidConfiguration;
+    // dedicated epilogue warps: measured at config 2 -- x pre-projection 1.13 -> 0.99 ms (wide outputs: 3H columns per row), dX
+    // 0.75 -> 0.86 ms (64 output columns: the epilogue is small and the ring loses a slot) -> used for fp32 sources with
+    // Nout = 192 when the staging tiles fit beside a 2-slot weight ring; DCGRU_BULK_EPIW=0 / 1 forces it off / on
+    bool epiw = src16 == nullptr && Nout == 192;
+    { const char* e = getenv("DCGRU_BULK_EPIW"); if (e && (e[0] == '0' || e[0] == '1')) epiw = e[0] == '1'; }
+    if (epiw && !bulk_layout(N, Cin, M, Nout, smem_limit, src16 != nullptr, &p, true)) epiw = false;
+    if (!epiw && !bulk_layout(N, Cin, M, Nout, smem_limit, src16 != nullptr, &p, false)) return cudaErrorInvalidConfiguration;
     p.src16 = reinterpret_cast<const __half*>(src16);
     p.B = B; p.T = T; p.N = N; p.Cin = Cin; p.M = M; p.Nout = Nout; p.transposeP = transposeP;
     p.ntile = g16_ntile(B); p.NQ = g16_nq(Cin, M);
@@ -425,12 +484,14 @@ cudaError_t launch_bulk_dp(int B, int T, int N, int Cin, int M, int Nout, int tr
         cudaError_t e = make_tmap(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, img, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (e != cudaSuccess) return e;
     }
-    const int smem = bulk_smem(p);
-    cudaError_t e = cudaFuncSetAttribute(bulk_dp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int smem = bulk_smem(p, epiw);
+    cudaError_t e = epiw ? cudaFuncSetAttribute(bulk_dp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                         : cudaFuncSetAttribute(bulk_dp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     long nitems = (long)p.ntile * T;
     int grid = nsms < nitems ? nsms : (int)nitems;
-    bulk_dp_kernel<<<grid, BK_THREADS, smem, st>>>(p, tm);
+    if (epiw) bulk_dp_kernel<true><<<grid, BK_THREADS, smem, st>>>(p, tm);
+    else bulk_dp_kernel<false><<<grid, BK_THREADS - 128, smem, st>>>(p, tm);
     return cudaGetLastError();
 }
 

@@ -266,12 +266,13 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
         const uint32_t tb = taddr + ((uint32_t)(32 * quad) << 16) + half * 32;
         const float gs = __ldg(p.scale_ptr), inv_gs = 1.f / gs;
         // slot of chunk i of step k, once its previous content was consumed by the MMAs (and dumped)
-        auto acquire = [&](int i, int k) -> int {
+        // (need_mma = false: the MMAs that read the previous content are known to be complete through bar_b1 / bar_b2)
+        auto acquire = [&](int i, int k, bool need_mma = true) -> int {
             int slot;
             unsigned fill;
             rb_slot(i, k, M, slot, fill);
             if (fill >= 1) {
-                mbar_wait(&bar_aempty[slot], (fill - 1) & 1);
+                if (need_mma) mbar_wait(&bar_aempty[slot], (fill - 1) & 1);
                 if (dump) mbar_wait(&bar_stored[slot], (fill - 1) & 1);
             }
             return slot;
@@ -331,8 +332,8 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
             tc_fence_after();
             if (rec) es[2] = clock64();
             DBG_PROG(k * 10 + 2);
-            uint8_t* slc = Aslots + acquire(0, k) * SLOT;               // chunk [dA_c] (slot 0)
-            uint8_t* slu = Aslots + acquire(1, k) * SLOT;               // chunk [dA_u] (slot 1)
+            uint8_t* slc = Aslots + acquire(0, k, false) * SLOT;        // chunk [dA_c] (slot 0; [dA_r] of step k-1 was read before bar_b2)
+            uint8_t* slu = Aslots + acquire(1, k, false) * SLOT;        // chunk [dA_u] (slot 1; likewise)
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {                            // 16 columns at a time (TMEM loads are paid per instruction)
                 float u[16], c[16], hp[16], g[16], a2[16];
@@ -385,7 +386,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rnn_bwd_kernel(const RnnBwdPara
             if (rec) es[7] = clock64();
             // ---- E2 ----------------------------------------------------------------------------------------------------
             DBG_PROG(k * 10 + 6);
-            uint8_t* slr = Aslots + acquire(2 * M, k) * SLOT;           // chunk [dA_r] (slot 0: every reader of [dA_c] is done, bar_b1)
+            uint8_t* slr = Aslots + acquire(2 * M, k, false) * SLOT;    // chunk [dA_r] (slot 0: every reader of [dA_c] is done, bar_b1)
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
                 float a1[16], hp[16], r[16];

@@ -290,7 +290,10 @@ __global__ void __launch_bounds__(RF_THREADS, 1) rnn_fwd_kernel(const RnnFwdPara
             for (int m = 1; m < M; ++m) {
                 const int slot = 1 + ((m - 1) & 1);
                 if (st && m == 1) st[0] = clock64();
-                acquire(slot, true);
+                // terms 1 and 2 reuse the slots of the previous phase's last two terms: their MMAs completed before bar_gate /
+                // bar_cand, which this thread has already waited for -> only the image dump has to be awaited (a try_wait costs
+                // ~200 cycles even when the phase completed long ago)
+                acquire(slot, m > 2);
                 if (st && m == 1) st[1] = clock64();
                 PFrag pf;
                 load_pfrag(PTs + (quad * (M - 1) + (m - 1)) * PT_STRIDE, lane, pf);

@@ -686,7 +686,11 @@ static int encoder_layer_bwd_impl(const dcgru_cell_desc* d, int32_t batch, int32
                                                d_hsel, d_hsel ? nh : 0, reinterpret_cast<unsigned*>(scale + 8), scale, st));
         LAUNCH("rnn_bwd", launch_rnn_bwd(batch, seq_len, N, fin, M, d->activation, h0, h_seq, ruc, P, w->Wg, w->Wc, d_hseq,
                                          d_hlast, d_hsel, sel_t, wsb + ws.off_wb, scale, dh0, wsb + ws.off_img, st));
-        SideStream* side = gsave ? side_stream() : nullptr;
+        // db = column sums of the dA image: fused into the weight-gradient GEMM, whose CTAs stream those rows through shared
+        // memory anyway (DCGRU_FUSE_DB=0: separate colsum16 kernel, on the side stream when there is one)
+        bool fuse_db = gsave != nullptr;
+        { const char* e = getenv("DCGRU_FUSE_DB"); if (e && e[0] == '0') fuse_db = false; }
+        SideStream* side = (gsave && !fuse_db) ? side_stream() : nullptr;
         if (side) {
             // db on the side stream, concurrent with the dX / dW GEMMs below (joined before the call returns)
             CUDA_TRY(cudaEventRecord(side->fork, st));
@@ -707,7 +711,9 @@ static int encoder_layer_bwd_impl(const dcgru_cell_desc* d, int32_t batch, int32
         if (gsave) {
             // weight gradient: GEMM over the two fp16 operand images; bias gradient: column sums of the dA image
             LAUNCH("dw_mm16", launch_dw_mm16(fin, H, M, batch, seq_len, gsave, wsb + ws.off_img, reinterpret_cast<float*>(wsb + ws.off_part),
-                                             scale, di.sms, g->dWg, g->dWc, st));
+                                             scale, di.sms, g->dWg, g->dWc, st, fuse_db ? reinterpret_cast<float*>(wsb + ws.off_cs) : nullptr,
+                                             g->dbg, g->dbc));
+            if (fuse_db) return 0;
             if (side) CUDA_TRY(cudaStreamWaitEvent(st, side->join, 0));
             else
                 LAUNCH("colsum16", launch_colsum16(wsb + ws.off_img, batch, seq_len, H, reinterpret_cast<float*>(wsb + ws.off_cs), scale,

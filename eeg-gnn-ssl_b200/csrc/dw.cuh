@@ -157,7 +157,8 @@ size_t dw_mm16_part_floats(int nsms);
 size_t colsum16_part_floats(int H);
 int dw_mm16_smem_bytes();
 cudaError_t launch_dw_mm16(int fin, int H, int M, int B, int T, const void* G, const void* DA, float* part, const float* scale_ptr,
-                           int nsms, float* dWg, float* dWc, cudaStream_t st);
+                           int nsms, float* dWg, float* dWc, cudaStream_t st, float* dbpart = nullptr, float* dbg = nullptr,
+                           float* dbc = nullptr);
 cudaError_t launch_colsum16(const void* daimg, int B, int T, int H, float* partial, const float* scale_ptr, float* dbg, float* dbc,
                             cudaStream_t st);
 

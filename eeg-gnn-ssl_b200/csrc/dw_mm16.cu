@@ -27,7 +27,7 @@ constexpr int D16_NSTAGE = 4;
 constexpr int D16_KROWS = 16;                         // image rows per K block (one MMA k-step)
 constexpr int D16_KB_PER_SLAB = IMG_ROWS / D16_KROWS; // 6
 constexpr int D16_FLUSH = 80;                         // K blocks between flushes (1280 rows)
-constexpr int D16_THREADS = 320;
+constexpr int D16_THREADS = 352;                       // loader, issuer, 8 flush warps, column-sum warp
 constexpr int D16_BLK = D16_KROWS * 128;              // one 64-column block of one plane: 16 rows x 128 B = 2 KB
 constexpr int D16_BOXBLK = 4;                         // G column blocks per TMA box (2 tiles)
 constexpr int D16_BOX = 2 * D16_BOXBLK * D16_BLK;     // [hi | lo][4 blocks] = 16 KB
@@ -41,6 +41,7 @@ struct Dw16Set { int ntile, ncoltot, cta0, ncta, gblk0, nbox; Dw16Tile tile[4]; 
 struct Dw16Params {
     const uint8_t* G; const uint8_t* DA;
     float* part;                                      // [cta][512 columns][128 rows]
+    float* dbpart;                                    // [CTA of set 0][192]: column sums of the dA image over the CTA's K range (db), or nullptr
     const float* scale_ptr;
     long nkb;
     int kkp, nset, ncta;
@@ -64,7 +65,8 @@ __global__ void __launch_bounds__(D16_THREADS, 1) dw_mm16_kernel(const Dw16Param
 
     if (warp == 0) tmem_alloc<512>(&tmem_slot);
     if (tid == 0) {
-        for (int i = 0; i < D16_NSTAGE; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+        // (in the CTAs of set 0 a stage has two consumers when db is fused: the MMAs and the column-sum warp)
+        for (int i = 0; i < D16_NSTAGE; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], (p.dbpart && si == 0) ? 2 : 1); }
         mbar_init(&bar_accfull, 1);
         mbar_init(&bar_accempty, 8);
         mbar_fence_init();
@@ -131,6 +133,46 @@ __global__ void __launch_bounds__(D16_THREADS, 1) dw_mm16_kernel(const Dw16Param
             }
         }
         __syncwarp();
+    } else if (warp == 10) {
+        // =================================== column sums of dA (db) ====================================================
+        // The dA rows of every K block pass through shared memory anyway; the CTAs of set 0 cover every image row exactly once.
+        // Lane u < 24 owns the 16-byte unit u of a row (8 columns): 16 rows x (hi + lo) per K block, fp32 partial sums folded
+        // into double every D16_FLUSH blocks.  The tiles are SWIZZLE_128B: unit cu of row k sits at unit cu ^ (k & 7).
+        if (p.dbpart && si == 0) {
+            float a[8];
+            double d[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { a[j] = 0.f; d[j] = 0.0; }
+            const int blk = lane >> 3, cu = lane & 7;
+            int st = 0, ph = 0, since = 0;
+            for (int i = 0; i < nkb; ++i) {
+                mbar_wait(&bar_full[st], ph);
+                if (lane < 24) {
+                    const uint8_t* b = smem + st * D16_STAGE + D16_A_BYTES + blk * D16_BLK;
+#pragma unroll
+                    for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+                        for (int k = 0; k < D16_KROWS; ++k) {
+                            const uint4 q = *reinterpret_cast<const uint4*>(b + pl * 3 * D16_BLK + k * 128 + ((cu ^ (k & 7)) << 4));
+                            const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); a[2 * j] += f.x; a[2 * j + 1] += f.y; }
+                        }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_empty[st]);
+                if (++since == D16_FLUSH) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { d[j] += (double)a[j]; a[j] = 0.f; }
+                    since = 0;
+                }
+                if (++st == D16_NSTAGE) { st = 0; ph ^= 1; }
+            }
+            if (lane < 24) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) p.dbpart[(size_t)split * 192 + 8 * lane + j] = (float)(d[j] + (double)a[j]);
+            }
+        }
     } else {
         // =================================== flush warps ============================================================
         const int quad = warp & 3, half = (warp - 2) >> 2;
@@ -289,13 +331,15 @@ size_t dw_mm16_part_floats(int nsms) { return (size_t)nsms * 512 * 128; }
 size_t colsum16_part_floats(int H) { return (size_t)CS16_CTAS * 3 * H; }
 int dw_mm16_smem_bytes() { return D16_SMEM; }
 
+// dbpart != nullptr: db is fused (column sums of the dA rows by one more warp of the set-0 CTAs; dbpart holds >= sms * 192 floats)
 cudaError_t launch_dw_mm16(int fin, int H, int M, int B, int T, const void* G, const void* DA, float* part, const float* scale_ptr,
-                           int nsms, float* dWg, float* dWc, cudaStream_t st) {
+                           int nsms, float* dWg, float* dWc, cudaStream_t st, float* dbpart, float* dbg, float* dbc) {
     Dw16Params p;
     memset(&p, 0, sizeof p);
     const long nslab = (long)g16_ntile(B) * T;
     if (!dw_mm16_plan(fin, H, M, nslab, nsms, &p)) return cudaErrorInvalidConfiguration;
     p.G = reinterpret_cast<const uint8_t*>(G); p.DA = reinterpret_cast<const uint8_t*>(DA); p.part = part; p.scale_ptr = scale_ptr;
+    p.dbpart = dbpart;
     // 4-D views of the row-major fp16 images: (64 columns = one 128-byte row piece | image row | column block | hi / lo plane);
     // column blocks beyond the image width are out of bounds (zero-filled)
     CUtensorMap tg, td;
@@ -322,6 +366,9 @@ cudaError_t launch_dw_mm16(int fin, int H, int M, int B, int T, const void* G, c
     if (e != cudaSuccess) return e;
     const int n = (fin + H) * M * 3 * H;
     dw_mm16_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(p, fin, H, M, dWg, dWc);
+    e = cudaGetLastError();
+    if (e != cudaSuccess || !dbpart) return e;
+    colsum16_final_kernel<<<1, 3 * H, 0, st>>>(dbpart, p.set[0].ncta, H, scale_ptr, dbg, dbc);
     return cudaGetLastError();
 }
 

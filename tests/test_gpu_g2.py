@@ -122,11 +122,22 @@ def test_side_stream_bias_gradient_identical_and_capturable(dev, monkeypatch):
         torch.cuda.synchronize()
         return [p.grad.clone() for p in model.parameters()]
 
-    monkeypatch.setenv("DCGRU_SIDE_STREAM", "0")
+    monkeypatch.setenv("DCGRU_FUSE_DB", "0")                  # separate colsum16 kernel ...
+    monkeypatch.setenv("DCGRU_SIDE_STREAM", "0")              # ... on the caller's stream
     ref = grads()
-    monkeypatch.setenv("DCGRU_SIDE_STREAM", "1")
+    monkeypatch.setenv("DCGRU_SIDE_STREAM", "1")              # ... on the library's side stream
     for a, b in zip(grads(), ref):
         assert torch.equal(a, b)
+    # default: db fused into the weight-gradient GEMM (column sums by one more warp of dw_mm16): another summation order for
+    # the biases, every other gradient bit-identical
+    monkeypatch.delenv("DCGRU_FUSE_DB")
+    names = [n for n, _ in model.named_parameters()]
+    for n, a, b in zip(names, grads(), ref):
+        if n.endswith("biases") and "encoder" in n:
+            assert float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)) < 5e-6, n
+        else:
+            assert torch.equal(a, b), n
+    monkeypatch.setenv("DCGRU_FUSE_DB", "0")
     # captured: the fork / join must be part of the graph (a side stream left outside would make the capture fail or the
     # replay read stale bias gradients)
     for p in model.parameters():

@@ -1253,11 +1253,15 @@ static int decoder_bwd_impl(const dcgru_cell_desc* d, int32_t L, int32_t B, int3
             const uint8_t* g0 = reinterpret_cast<const uint8_t*>(gsave);
             float* part = reinterpret_cast<float*>(wsb + ws.off_part);
             float* cs = reinterpret_cast<float*>(wsb + ws.off_cs);
-            LAUNCH("dw_mm16", launch_dw_mm16(Fo, H, M, B, T, g0, dimg0, part, scale, di.sms, g[0].dWg, g[0].dWc, st));
-            LAUNCH("colsum16", launch_colsum16(dimg0, B, T, H, cs, scale, g[0].dbg, g[0].dbc, st));
+            bool fuse_db = true;                                        // db inside the weight-gradient GEMM (see the encoder path)
+            { const char* e = getenv("DCGRU_FUSE_DB"); if (e && e[0] == '0') fuse_db = false; }
+            LAUNCH("dw_mm16", launch_dw_mm16(Fo, H, M, B, T, g0, dimg0, part, scale, di.sms, g[0].dWg, g[0].dWc, st, fuse_db ? cs : nullptr,
+                                             g[0].dbg, g[0].dbc));
+            if (!fuse_db) LAUNCH("colsum16", launch_colsum16(dimg0, B, T, H, cs, scale, g[0].dbg, g[0].dbc, st));
             if (L > 1) {
-                LAUNCH("dw_mm16", launch_dw_mm16(H, H, M, B, T * (L - 1), g0 + gi.bytes0, dimg1, part, scale, di.sms, g[1].dWg, g[1].dWc, st));
-                LAUNCH("colsum16", launch_colsum16(dimg1, B, T * (L - 1), H, cs, scale, g[1].dbg, g[1].dbc, st));
+                LAUNCH("dw_mm16", launch_dw_mm16(H, H, M, B, T * (L - 1), g0 + gi.bytes0, dimg1, part, scale, di.sms, g[1].dWg, g[1].dWc, st,
+                                                 fuse_db ? cs : nullptr, g[1].dbg, g[1].dbc));
+                if (!fuse_db) LAUNCH("colsum16", launch_colsum16(dimg1, B, T * (L - 1), H, cs, scale, g[1].dbg, g[1].dbc, st));
             }
             cells_done = true;
         } else {

@@ -659,8 +659,10 @@ static int encoder_layer_bwd_impl(const dcgru_cell_desc* d, int32_t batch, int32
         use_mm = true;
     }
     if (njobs > DW_MAXJOBS) return fail("too many weight-gradient jobs (%d)", njobs);
-    LAUNCH("transpose", launch_transpose(w->Wg, CM, 2 * H, WgT, CM, st));
-    LAUNCH("transpose", launch_transpose(w->Wc, CM, H, WcT, CM, st));
+    if (!(g2_path && g2base)) {                                 // (only the fp32 / first-generation BPTT kernels read transposed weights)
+        LAUNCH("transpose", launch_transpose(w->Wg, CM, 2 * H, WgT, CM, st));
+        LAUNCH("transpose", launch_transpose(w->Wc, CM, H, WcT, CM, st));
+    }
     BwdPlan pl;
     if (!plan_bwd(H, M, batch, 0, &pl)) return fail("no backward tiling fits shared memory");
     BwdParams p;

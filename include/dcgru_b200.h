@@ -5,8 +5,12 @@
  * class surface of model/cell.py and model/model.py.  These entry points are what
  * a binding for that surface has to call; every one cites the reference code it replaces.
  * All tensors are dense fp32, row-major, device pointers owned by the caller; the library
- * allocates nothing persistent, keeps no thread-local state except the last error string,
- * launches on the caller's stream and never synchronises it.
+ * allocates no device memory, keeps no thread-local state except the last error string,
+ * launches on the caller's stream and never synchronises it.  One exception, only when the
+ * bias gradient is not fused into the weight-gradient GEMM (DCGRU_FUSE_DB=0): the backward
+ * calls fork that small pass onto a library-owned non-blocking stream (one stream + two events
+ * per host thread and device, created on first use) and join it before they return -- plain
+ * event dependencies, legal under CUDA-graph capture.
  *
  * Return value: 0 on success, non-zero on error (message via dcgru_last_error()).
  *

@@ -355,7 +355,7 @@ int dcgru_corr_supports(int32_t batch, int32_t seq_len, int32_t num_nodes, int32
     if (num_nodes < 2 || num_nodes > NP) return fail("num_nodes=%d unsupported", num_nodes);
     if (top_k < 0) return fail("top_k < 0 (the reference raises ValueError for top_k=None)");
     if (!clip || !support0 || !support1) return fail("null pointer");
-    if ((size_t)num_nodes * (feat | 1) * 4 > (size_t)devinfo().smem) return fail("feature dim too large");
+    if ((size_t)num_nodes * (feat | 1) * 8 > (size_t)devinfo().smem) return fail("feature dim too large");
     cudaStream_t st = (cudaStream_t)stream;
     LAUNCH("corr_supports", launch_corr_supports(batch, seq_len, num_nodes, feat, clip, stride_b, stride_t, scale,
                                                  shift, top_k, adj, support0, support1, st));

@@ -56,9 +56,9 @@ cudaError_t launch_graph_poly(int B, int N, int K, int S, const float* const* su
 __global__ void __launch_bounds__(NT) corr_supports_kernel(int T, int N, int F, const float* clip, long long sb,
                                                            long long st_, float scale, float shift, int top_k,
                                                            float* adj_out, float* sup0, float* sup1) {
-    extern __shared__ __align__(16) float sm[];
+    extern __shared__ __align__(16) double sm[];
     const int FL = F | 1;                        // odd row stride: conflict-free across rows
-    float* X = sm;                               // [N][FL]
+    double* X = sm;                              // [N][FL] as double: one conversion per element, not one per pair and element
     __shared__ double G[NP * NP];
     __shared__ float A[NP * NP];
     __shared__ float dr[NP], dc[NP];
@@ -75,19 +75,48 @@ __global__ void __launch_bounds__(NT) corr_supports_kernel(int T, int N, int F, 
     }
     double acc = 0.0;
     const float* base = clip + (size_t)b * sb;
+    // the next step's slice is fetched into registers while this one is reduced (the loop was a chain of exposed global and
+    // shared-memory latencies: 0.47 ms for 512 clips of 60 steps); four independent fp64 accumulators per pair
+    constexpr int PF = 8;                        // N*F <= PF * NT elements per step (19 x 100 = 1900 <= 2048)
+    const int nel = N * F;
+    const bool pre = nel <= PF * NT;
+    float nxt[PF];
+    if (pre) {
+#pragma unroll
+        for (int k = 0; k < PF; ++k) { const int idx = tid + k * NT; nxt[k] = idx < nel ? __ldcs(base + idx) : 0.f; }
+    }
     for (int t = 0; t < T; ++t) {
         __syncthreads();
-        for (int idx = tid; idx < N * F; idx += NT) {
-            int n = idx / F, f = idx - n * F;
-            X[n * FL + f] = base[(size_t)t * st_ + idx] * scale + shift;
+        if (pre) {
+#pragma unroll
+            for (int k = 0; k < PF; ++k) {
+                const int idx = tid + k * NT;
+                if (idx < nel) { const int n = idx / F, f = idx - n * F; X[n * FL + f] = (double)(nxt[k] * scale + shift); }
+            }
+            if (t + 1 < T) {
+#pragma unroll
+                for (int k = 0; k < PF; ++k) { const int idx = tid + k * NT; nxt[k] = idx < nel ? __ldcs(base + (size_t)(t + 1) * st_ + idx) : 0.f; }
+            }
+        } else {
+            for (int idx = tid; idx < nel; idx += NT) {
+                int n = idx / F, f = idx - n * F;
+                X[n * FL + f] = (double)(base[(size_t)t * st_ + idx] * scale + shift);
+            }
         }
         __syncthreads();
         if (tid < npair) {
-            const float* xi = X + pi * FL;
-            const float* xj = X + pj * FL;
-            double a = 0.0;
-            for (int f = 0; f < F; ++f) a += (double)xi[f] * (double)xj[f];
-            acc += a;
+            const double* xi = X + pi * FL;
+            const double* xj = X + pj * FL;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int f = 0;
+            for (; f + 3 < F; f += 4) {
+                a0 = fma(xi[f], xj[f], a0);
+                a1 = fma(xi[f + 1], xj[f + 1], a1);
+                a2 = fma(xi[f + 2], xj[f + 2], a2);
+                a3 = fma(xi[f + 3], xj[f + 3], a3);
+            }
+            for (; f < F; ++f) a0 = fma(xi[f], xj[f], a0);
+            acc += (a0 + a1) + (a2 + a3);
         }
     }
     if (tid < npair) { G[pi * N + pj] = acc; G[pj * N + pi] = acc; }
@@ -138,7 +167,7 @@ __global__ void __launch_bounds__(NT) corr_supports_kernel(int T, int N, int F, 
 cudaError_t launch_corr_supports(int B, int T, int N, int F, const float* clip, long long sb, long long st_,
                                  float scale, float shift, int top_k, float* adj, float* s0, float* s1,
                                  cudaStream_t st) {
-    int smem = N * (F | 1) * 4;
+    int smem = N * (F | 1) * 8;
     cudaError_t e = cudaFuncSetAttribute(corr_supports_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     corr_supports_kernel<<<B, NT, smem, st>>>(T, N, F, clip, sb, st_, scale, shift, top_k, adj, s0, s1);

@@ -66,6 +66,8 @@ def _compare(ours, ref64, ref32, tol):
         worst[k] = (e, e32)
         assert e < BAR, (k, e, e32)
         assert e < max(tol, 8 * e32), (k, e, e32)
+    kmax = max(worst, key=lambda k_: worst[k_][0])
+    print(f"[fullchain] worst of {len(worst)} tensors vs fp64 oracle: {kmax} {worst[kmax][0]:.2e} (fp32 oracle: {worst[kmax][1]:.2e})")
     return worst
 
 

@@ -64,9 +64,14 @@ def test_argument_validation_reports_errors():
 
 def test_cpu_tensors_are_rejected_not_emulated():
     from eeg_gnn_ssl_b200.model.cell import DCGRUCell
+    from eeg_gnn_ssl_b200 import ops
     cell = DCGRUCell(100, 64, 2, 19)
     with pytest.raises(RuntimeError, match="CUDA"):
         cell([torch.eye(19)], torch.zeros(2, 1900), torch.zeros(2, 19 * 64))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.fft_features(torch.zeros(2, 19, 400))                      # input-feature kernel: no CPU path either
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.corr_supports(torch.zeros(2, 4, 19, 100))
 
 
 def _args(**kw):
